@@ -1,0 +1,108 @@
+/*
+ * ccv2_oracle.h -- CPU oracle for the cloud_codec_v2 intra encode/decode hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load it, and there only as the checker / the CPU side of a comparison.
+ *
+ * What it is: a dependency-free C restatement of the algorithm the reference
+ * (cwi-dis/cwi-pcl-codec, /root/reference) runs for
+ *   OctreePointCloudCodecV2<PointXYZRGB>::encodePointCloud / decodePointCloud
+ *   (cloud_codec_v2/include/pcl/cloud_codec_v2/impl/point_cloud_codec_v2_impl.hpp:80-310)
+ * including the arithmetic the reference inherits from two un-vendored third
+ * parties: PCL 1.8-1.10 (octree bbox growth / key generation / serializeTree /
+ * StaticRangeCoder / ColorCoding) and libjpeg-turbo (baseline JPEG, via jpeg_io).
+ *
+ * PARITY STATUS
+ *   - JPEG encode bytes / decode pixels: PINNED against libjpeg-turbo through the
+ *     golden vectors in tests/golden/ (generated with Pillow by
+ *     tests/golden/make_jpeg_golden.py).
+ *   - PCL-inherited parts (bbox growth, keys, DFS order, range coder, header):
+ *     PARITY UNPINNED -- the reference ships no tests/golden vectors and PCL is
+ *     not available offline, so these follow SURVEY.md Appendix B only.  Frozen
+ *     inputs + SHA-256 of the oracle's streams live in tests/golden/ so a later
+ *     run of real PCL can be diffed in one command.
+ *   - The reference itself cannot be compiled here (needs PCL, Boost, Eigen,
+ *     jpeglib.h) => no oracle/_ref.
+ */
+#ifndef CCV2_ORACLE_H
+#define CCV2_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ctor surface of OctreePointCloudCodecV2 (point_cloud_codec_v2.h:108-143), MANUAL_CONFIGURATION */
+typedef struct orc_params {
+  double point_resolution;      /* pointResolution_arg  */
+  double octree_resolution;     /* octreeResolution_arg */
+  int do_voxel_grid;            /* doVoxelGridDownDownSampling_arg (only 1 is implemented) */
+  int do_color;                 /* doColorEncoding_arg */
+  int color_bit_resolution;     /* colorBitResolution_arg */
+  int color_coding_type;        /* 0 = PCL avg (bit-reduced), 1 = SNAKE jpeg, 2 = LINES jpeg, 3 = GRID (raw) */
+  int do_centroid;              /* doVoxelGridCentroid_arg */
+  int create_scalable;          /* createScalableStream_arg */
+  int code_connectivity;        /* codeConnectivity_arg */
+  int jpeg_quality;             /* jpeg_quality_arg */
+  int macroblock_size;          /* header only (16) */
+  int do_icp_color_offset;      /* header only (0) */
+} orc_params;
+
+typedef struct orc_info {
+  uint32_t depth;               /* realised octree depth */
+  double bb_min[3], bb_max[3];
+  uint64_t n_finite;            /* points that passed isFinite */
+  uint64_t n_leaves;            /* V */
+  uint64_t n_tree_bytes;        /* B */
+  uint64_t n_color_bytes;       /* bytes handed to the range coder for colour (J for jpeg modes) */
+  uint64_t coded[3];            /* compression_performance_metrics (impl.hpp:1697,1710,1723) */
+  double t_ms[8];               /* stage timings of the oracle run (bbox/keys, sort, serialise, colour, jpeg, entropy, ...) */
+} orc_info;
+
+/* intermediates, for stage-by-stage parity tests; every pointer is malloc'd by the oracle, free with orc_free */
+typedef struct orc_debug {
+  uint64_t *leaf_keys;          /* V Morton codes (x = MSB of each triple), ascending */
+  uint8_t *tree_bytes;          /* B */
+  uint8_t *avg_colors;          /* 3V bytes, B,G,R per leaf, before jpeg */
+  uint8_t *color_payload;       /* n_color_bytes */
+  uint8_t *centroid_bytes;      /* 3V or NULL */
+} orc_debug;
+
+void orc_default_params(orc_params *p);
+
+/* encodePointCloud (impl.hpp:80-213). pts: n x 32-byte PointXYZRGB (x,y,z f32 @0,4,8; b,g,r,a @16..19).
+ * frame_id is the value written to the header (the codec pre-increments, first frame = 1).
+ * Returns 0, or <0 on error; an empty / all-non-finite cloud yields *out_len = 0 (impl.hpp:206-212). */
+int orc_encode(const orc_params *p, uint32_t frame_id, const void *pts, size_t n,
+               uint8_t **out, size_t *out_len, orc_info *info, orc_debug *dbg);
+
+/* decodePointCloud (impl.hpp:224-310). Output: *n x 32-byte points, malloc'd. */
+int orc_decode(const uint8_t *in, size_t len, void **pts, size_t *n, orc_info *info);
+
+void orc_free(void *p);
+void orc_free_debug(orc_debug *d);
+
+/* ---- building blocks, exported for unit tests ---- */
+/* PCL StaticRangeCoder::encodeCharVectorToStream: out gets 1028 + k + 8 bytes */
+int orc_range_encode(const uint8_t *in, size_t n, uint8_t **out, size_t *out_len);
+/* decodeStreamToCharVector: consumes exactly *consumed bytes of in */
+int orc_range_decode(const uint8_t *in, size_t in_len, uint8_t *out, size_t n, size_t *consumed);
+/* libjpeg baseline encoder as jpeg_io drives it (jpeg_io.hpp:259-311); rgb interleaved 3 bytes/pixel */
+int orc_jpeg_encode(const uint8_t *rgb, int w, int h, int quality, uint8_t **out, size_t *out_len);
+/* libjpeg decoder defaults (jpeg_io.hpp:140-162): ISLOW + fancy upsampling */
+int orc_jpeg_decode(const uint8_t *in, size_t len, uint8_t **rgb, int *w, int *h);
+/* snake_grid_mapping.h:46-71 (literal iterator) and SURVEY App. B.7 (closed form): position of linear index i */
+void orc_snake_positions_literal(int w, int h, int32_t *pos /* w*h */);
+int32_t orc_snake_pos_closed(int w, int h, int64_t i);
+/* sequential bbox growth + keys. keys_xyz: 3*n u32 (undefined for non-finite), finite: n bytes */
+int orc_bbox_keys(const void *pts, size_t n, double resolution, double bb_min[3], double bb_max[3],
+                  uint32_t *depth, uint32_t *keys_xyz, uint8_t *finite);
+/* recursive DFS reference of Octree2BufBase::serializeTreeRecursive over distinct Morton leaf codes
+ * (used to cross-check the sort-based emission) */
+int orc_dfs_recursive(const uint64_t *leaf_codes, size_t v, uint32_t depth, uint8_t **bytes, size_t *nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
