@@ -1,0 +1,332 @@
+"""ctypes binding of libccv2.so (the C ABI in include/ccv2.h) and a Python mirror of the reference's
+``pcl::io::OctreePointCloudCodecV2<PointXYZRGB>`` interface (cloud_codec_v2/include/pcl/cloud_codec_v2/
+point_cloud_codec_v2.h:70-368) for tests and bench.
+
+There is no CPU path here: if libccv2.so is missing or no CUDA device is usable, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libccv2.so")
+
+MANUAL_CONFIGURATION = 12  # pcl::io::compression_Profiles_e
+
+
+class Ccv2Error(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("ccv2 status %d (%s): %s" % (status, _status_string(status), msg))
+        self.status = status
+
+
+class Params(C.Structure):
+    """ccv2_params == the constructor surface of OctreePointCloudCodecV2 (codec.h:108-143)."""
+    _fields_ = [("profile", C.c_int32), ("show_statistics", C.c_int32),
+                ("point_resolution", C.c_double), ("octree_resolution", C.c_double),
+                ("do_voxel_grid_downsampling", C.c_int32), ("i_frame_rate", C.c_uint32),
+                ("do_color_encoding", C.c_int32), ("color_bit_resolution", C.c_uint8),
+                ("color_coding_type", C.c_uint8), ("_pad0", C.c_uint8 * 2),
+                ("do_voxel_grid_centroid", C.c_int32), ("create_scalable_stream", C.c_int32),
+                ("code_connectivity", C.c_int32), ("jpeg_quality", C.c_int32), ("num_threads", C.c_int32),
+                ("macroblock_size", C.c_int32), ("do_icp_color_offset", C.c_int32)]
+
+
+class FrameInfo(C.Structure):
+    _fields_ = [("depth", C.c_uint32), ("n_finite", C.c_uint32), ("n_leaves", C.c_uint32),
+                ("n_tree_bytes", C.c_uint32), ("n_color_bytes", C.c_uint32), ("error", C.c_uint32),
+                ("bb_min", C.c_double * 3), ("bb_max", C.c_double * 3), ("coded", C.c_uint64 * 3)]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libccv2.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libccv2.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(make -C cwi_pcl_codec_b200/csrc). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vpp, szp = C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)
+    L.ccv2_default_params.argtypes = [C.POINTER(Params)]
+    L.ccv2_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(C.c_void_p)]
+    L.ccv2_destroy.argtypes = [C.c_void_p]
+    L.ccv2_destroy.restype = None
+    L.ccv2_max_compressed_size.argtypes = [C.c_size_t]
+    L.ccv2_max_compressed_size.restype = C.c_size_t
+    L.ccv2_encode_batch.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, szp]
+    L.ccv2_decode_batch.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, szp]
+    L.ccv2_peek_point_count.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
+    L.ccv2_get_metrics.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.ccv2_set_frame_id.argtypes = [C.c_void_p, C.c_uint32]
+    L.ccv2_get_frame_id.argtypes = [C.c_void_p]
+    L.ccv2_get_frame_id.restype = C.c_uint32
+    L.ccv2_last_launch_count.argtypes = [C.c_void_p]
+    L.ccv2_last_launch_count.restype = C.c_uint64
+    L.ccv2_last_device_ms.argtypes = [C.c_void_p]
+    L.ccv2_last_device_ms.restype = C.c_float
+    L.ccv2_last_error.argtypes = [C.c_void_p]
+    L.ccv2_last_error.restype = C.c_char_p
+    L.ccv2_status_string.argtypes = [C.c_int]
+    L.ccv2_status_string.restype = C.c_char_p
+    L.ccv2_host_alloc.argtypes = [C.c_size_t]
+    L.ccv2_host_alloc.restype = C.c_void_p
+    L.ccv2_host_free.argtypes = [C.c_void_p]
+    L.ccv2_host_free.restype = None
+    L.ccv2_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, szp]
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = ["ccv2_default_params", "ccv2_create", "ccv2_destroy", "ccv2_max_compressed_size",
+                    "ccv2_encode_batch", "ccv2_decode_batch", "ccv2_peek_point_count", "ccv2_get_metrics",
+                    "ccv2_set_frame_id", "ccv2_get_frame_id", "ccv2_last_launch_count", "ccv2_last_device_ms",
+                    "ccv2_last_error", "ccv2_status_string", "ccv2_host_alloc", "ccv2_host_free", "ccv2_debug_fetch"]
+
+
+def _status_string(s):
+    try:
+        return load_library().ccv2_status_string(s).decode()
+    except Exception:  # pragma: no cover
+        return "?"
+
+
+def default_params(**kw):
+    """evaluate_compression's configuration (eval.hpp:377-395) with parameter_config.txt values; keyword
+    overrides use the ccv2_params field names, or octree_bits / enh_bits / color_bits / keep_centroid."""
+    p = Params()
+    load_library().ccv2_default_params(C.byref(p))
+    bits = kw.pop("octree_bits", None)
+    enh = kw.pop("enh_bits", 0)
+    if bits is not None:
+        p.octree_resolution = 2.0 ** -bits
+        p.point_resolution = 2.0 ** -(bits + enh)
+    if "color_bits" in kw:
+        cb = kw.pop("color_bits")
+        p.color_bit_resolution = cb
+        p.do_color_encoding = 1 if cb > 0 else 0      # eval.hpp:387
+    if "keep_centroid" in kw:
+        p.do_voxel_grid_centroid = kw.pop("keep_centroid")
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+class PinnedBuffer:
+    """cudaMallocHost'ed byte buffer exposed as a numpy array (for full-speed PCIe copies)."""
+
+    def __init__(self, nbytes):
+        L = load_library()
+        self.nbytes = int(nbytes)
+        self.ptr = L.ccv2_host_alloc(max(1, self.nbytes))
+        if not self.ptr:
+            raise MemoryError("ccv2_host_alloc(%d) failed" % nbytes)
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(max(1, self.nbytes),))
+
+    def close(self):
+        if self.ptr:
+            load_library().ccv2_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _ptr_len(x):
+    """(address, nbytes) of a numpy array / bytes / (ptr, nbytes) tuple / object with data_ptr() (torch tensor)."""
+    if isinstance(x, tuple):
+        return int(x[0]), int(x[1])
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C contiguous")
+        return x.ctypes.data, x.nbytes
+    if hasattr(x, "data_ptr"):
+        return int(x.data_ptr()), int(x.numel() * x.element_size())
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(x, np.uint8)
+        return a.ctypes.data, a.size
+    raise TypeError(type(x))
+
+
+class Codec:
+    """Thin handle over ccv2_codec: batch encode/decode with host or device buffers."""
+
+    def __init__(self, params=None, device=0):
+        self._L = load_library()
+        self.params = params or default_params()
+        h = C.c_void_p()
+        rc = self._L.ccv2_create(C.byref(self.params), device, C.byref(h))
+        if rc:
+            raise Ccv2Error(rc, (self._L.ccv2_last_error(None) or b"").decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ccv2_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise Ccv2Error(rc, (self._L.ccv2_last_error(self._h) or b"").decode())
+
+    # ---- raw pointer API (host or device addresses)
+    def encode_batch_raw(self, in_ptrs, npts, out_ptrs, out_caps):
+        n = len(in_ptrs)
+        a_in = (C.c_void_p * n)(*in_ptrs)
+        a_n = (C.c_size_t * n)(*npts)
+        a_out = (C.c_void_p * n)(*out_ptrs)
+        a_cap = (C.c_size_t * n)(*out_caps)
+        a_len = (C.c_size_t * n)()
+        rc = self._L.ccv2_encode_batch(self._h, n, a_in, a_n, a_out, a_cap, a_len)
+        self._check(rc)
+        return list(a_len)
+
+    def decode_batch_raw(self, in_ptrs, in_lens, out_ptrs, out_caps):
+        n = len(in_ptrs)
+        a_in = (C.c_void_p * n)(*in_ptrs)
+        a_n = (C.c_size_t * n)(*in_lens)
+        a_out = (C.c_void_p * n)(*out_ptrs)
+        a_cap = (C.c_size_t * n)(*out_caps)
+        a_len = (C.c_size_t * n)()
+        rc = self._L.ccv2_decode_batch(self._h, n, a_in, a_n, a_out, a_cap, a_len)
+        self._check(rc)
+        return list(a_len)
+
+    # ---- numpy convenience API
+    def encode_batch(self, clouds):
+        """clouds: list of arrays of 32-byte PointXYZRGB records (any dtype, nbytes % 32 == 0). Returns list of bytes."""
+        ins, ns, outs, caps, keep = [], [], [], [], []
+        for cl in clouds:
+            a = np.ascontiguousarray(cl)
+            if a.nbytes % 32:
+                raise ValueError("cloud bytes must be a multiple of 32")
+            n = a.nbytes // 32
+            cap = min(self._L.ccv2_max_compressed_size(n), 6 * n + (1 << 16))
+            o = np.empty(cap, np.uint8)
+            keep.append((a, o))
+            ins.append(a.ctypes.data if n else None)
+            ns.append(n)
+            outs.append(o.ctypes.data)
+            caps.append(cap)
+        lens = self.encode_batch_raw(ins, ns, outs, caps)
+        return [keep[i][1][:lens[i]].tobytes() for i in range(len(clouds))]
+
+    def decode_batch(self, streams):
+        """streams: list of bytes. Returns list of (n, 32) uint8 arrays (PointXYZRGB records)."""
+        ins, lens, outs, caps, keep = [], [], [], [], []
+        for s in streams:
+            a = np.frombuffer(s, np.uint8)
+            cnt = C.c_uint64(0)
+            rc = self._L.ccv2_peek_point_count(a.ctypes.data if a.size else None, a.size, C.byref(cnt))
+            if rc:
+                raise Ccv2Error(rc, "not a cloud_codec_v2 frame")
+            o = np.zeros((max(1, cnt.value), 32), np.uint8)
+            keep.append((a, o))
+            ins.append(a.ctypes.data)
+            lens.append(a.size)
+            outs.append(o.ctypes.data)
+            caps.append(max(1, cnt.value))
+        ns = self.decode_batch_raw(ins, lens, outs, caps)
+        return [keep[i][1][:ns[i]] for i in range(len(streams))]
+
+    # ---- accessors
+    def metrics(self):
+        m = (C.c_uint64 * 3)()
+        self._check(self._L.ccv2_get_metrics(self._h, m))
+        return list(m)
+
+    @property
+    def frame_id(self):
+        return self._L.ccv2_get_frame_id(self._h)
+
+    @frame_id.setter
+    def frame_id(self, v):
+        self._check(self._L.ccv2_set_frame_id(self._h, v))
+
+    @property
+    def last_launch_count(self):
+        return int(self._L.ccv2_last_launch_count(self._h))
+
+    @property
+    def last_device_ms(self):
+        return float(self._L.ccv2_last_device_ms(self._h))
+
+    def debug_fetch(self, frame, what):
+        """Test hook: 0 leaf codes (u64), 1 tree bytes, 2 avg colours, 3 colour payload, 4 sorted indices, 5 info."""
+        ln = C.c_size_t()
+        if what == 5:
+            info = FrameInfo()
+            self._check(self._L.ccv2_debug_fetch(self._h, frame, 5, C.byref(info), C.sizeof(info), C.byref(ln)))
+            return info
+        rc = self._L.ccv2_debug_fetch(self._h, frame, what, None, 0, C.byref(ln))
+        if rc not in (0, -4):
+            self._check(rc)
+        buf = np.zeros(max(1, ln.value), np.uint8)
+        self._check(self._L.ccv2_debug_fetch(self._h, frame, what, buf.ctypes.data, buf.size, C.byref(ln)))
+        buf = buf[:ln.value]
+        if what == 0:
+            return buf.view(np.uint64)
+        if what == 4:
+            return buf.view(np.uint32)
+        return buf
+
+
+class OctreePointCloudCodecV2:
+    """Python mirror of pcl::io::OctreePointCloudCodecV2<PointXYZRGB> (codec.h:70-368) over the C ABI.
+
+    Same constructor argument order and meaning as codec.h:108-143; ``encodePointCloud`` returns the bytes the
+    reference writes to its ostream and ``decodePointCloud`` returns the decoded cloud (an (n, 32) uint8 array
+    of PointXYZRGB records).  Like the reference, the calls return nothing useful on an empty cloud / a stream
+    without a frame header (impl.hpp:206-212, :231)."""
+
+    def __init__(self, compressionProfile=MANUAL_CONFIGURATION, showStatistics=False, pointResolution=0.001,
+                 octreeResolution=0.01, doVoxelGridDownDownSampling=False, iFrameRate=0, doColorEncoding=True,
+                 colorBitResolution=6, colorCodingType=0, doVoxelGridCentroid=True, createScalableStream=True,
+                 codeConnectivity=False, jpeg_quality=75, num_threads=0, device=0):
+        p = Params()
+        p.profile = compressionProfile
+        p.show_statistics = int(showStatistics)
+        p.point_resolution = pointResolution
+        p.octree_resolution = octreeResolution
+        p.do_voxel_grid_downsampling = int(doVoxelGridDownDownSampling)
+        p.i_frame_rate = iFrameRate
+        p.do_color_encoding = int(doColorEncoding)
+        p.color_bit_resolution = colorBitResolution
+        p.color_coding_type = colorCodingType
+        p.do_voxel_grid_centroid = int(doVoxelGridCentroid)
+        p.create_scalable_stream = int(createScalableStream)
+        p.code_connectivity = int(codeConnectivity)
+        p.jpeg_quality = jpeg_quality
+        p.num_threads = num_threads
+        p.macroblock_size = 16            # codec.h:138
+        p.do_icp_color_offset = 0         # codec.h:141
+        self._codec = Codec(p, device)
+
+    def encodePointCloud(self, cloud):
+        return self._codec.encode_batch([cloud])[0]
+
+    def decodePointCloud(self, data):
+        try:
+            return self._codec.decode_batch([data])[0]
+        except Ccv2Error as e:
+            if e.status == -6:            # sync failure => silent return (impl.hpp:231)
+                return np.zeros((0, 32), np.uint8)
+            raise
+
+    def getPerformanceMetrics(self):
+        return self._codec.metrics()

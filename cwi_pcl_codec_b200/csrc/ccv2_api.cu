@@ -1,0 +1,649 @@
+// ccv2_api.cu -- C ABI (include/ccv2.h) and host-side orchestration of the CUDA pipelines.
+//
+// Execution model: a batch of frames is cut into groups; every group runs start-to-finish on one CUDA stream of
+// a small round-robin pool (H2D of the inputs, the parallel kernels with blockIdx.y = frame, the serial
+// one-warp-per-stream range coder, assembly, D2H of the results).  Groups on different streams overlap, which
+// is what hides the serial entropy stage behind other groups' parallel work.  No host synchronisation happens
+// inside a group: all sizes (depth, V, B, J, stream length) are device-side values in the frame records.
+#include "../../include/ccv2.h"
+#include "common.cuh"
+#include "enc_kernels.cuh"
+#include "jpeg_enc_kernels.cuh"
+#include "entropy_kernels.cuh"
+#include "dec_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct HostBuf {
+  void *p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes + 4096);
+    if (e == cudaSuccess) cap = bytes + 4096;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// bump allocator over a DevBuf: first pass (base == nullptr) only measures
+struct Carver {
+  uint8_t *base; size_t off = 0;
+  explicit Carver(void *b) : base((uint8_t *)b) {}
+  template <typename T> T *take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T *r = base ? (T *)(base + off) : nullptr;
+    off += count * sizeof(T);
+    return r;
+  }
+};
+
+constexpr int MAX_STREAMS = 16;
+
+}  // namespace
+
+struct ccv2_codec {
+  ccv2_params prm;
+  int device = 0;
+  int n_streams = 8, group = 8;
+  cudaStream_t main_stream = nullptr;
+  cudaStream_t streams[MAX_STREAMS] = {};
+  cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_fork = nullptr;
+  std::vector<cudaEvent_t> ev_group;
+  JpegTables *d_tables = nullptr;
+  uint32_t *d_frame_counter = nullptr;
+  uint32_t frame_id = 0;
+  // encode workspaces
+  DevBuf enc_frames, enc_slots, enc_persist, enc_input;
+  HostBuf h_frames;
+  std::vector<EncFrame> enc_host;        // host mirror of the last batch's frame records (with device pointers)
+  // decode workspaces
+  DevBuf dec_frames, dec_work, dec_input, dec_output;
+  HostBuf h_dframes;
+  uint64_t metrics[3] = {0, 0, 0};
+  uint64_t launches = 0;
+  float device_ms = 0.f;
+  std::string err;
+};
+
+namespace {
+
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e__); return CCV2_ERR_CUDA; } } while (0)
+
+bool is_device_ptr(const void *p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- JPEG tables on the host (libjpeg std tables)
+const uint8_t ZZ_H[64] = { 0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14,
+  21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
+const uint8_t QL_H[64] = { 16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57, 69, 56,
+  14, 17, 22, 29, 51, 87, 80, 62, 18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92,
+  49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99 };
+const uint8_t QC_H[64] = { 17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99, 99, 99,
+  47, 66, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+  99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99 };
+const uint8_t DCL_BITS[16] = { 0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0 };
+const uint8_t DCC_BITS[16] = { 0, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0 };
+const uint8_t DC_VALS_H[12] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 };
+const uint8_t ACL_BITS[16] = { 0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 0x7d };
+const uint8_t ACL_VALS[162] = { 0x01, 0x02, 0x03, 0x00, 0x04, 0x11, 0x05, 0x12, 0x21, 0x31, 0x41, 0x06, 0x13, 0x51, 0x61, 0x07, 0x22, 0x71,
+  0x14, 0x32, 0x81, 0x91, 0xa1, 0x08, 0x23, 0x42, 0xb1, 0xc1, 0x15, 0x52, 0xd1, 0xf0, 0x24, 0x33, 0x62, 0x72, 0x82, 0x09, 0x0a, 0x16,
+  0x17, 0x18, 0x19, 0x1a, 0x25, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x34, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47,
+  0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a, 0x73, 0x74, 0x75,
+  0x76, 0x77, 0x78, 0x79, 0x7a, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a,
+  0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5,
+  0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe1, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8,
+  0xe9, 0xea, 0xf1, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa };
+const uint8_t ACC_BITS[16] = { 0, 2, 1, 2, 4, 4, 3, 4, 7, 5, 4, 4, 0, 1, 2, 0x77 };
+const uint8_t ACC_VALS[162] = { 0x00, 0x01, 0x02, 0x03, 0x11, 0x04, 0x05, 0x21, 0x31, 0x06, 0x12, 0x41, 0x51, 0x07, 0x61, 0x71, 0x13, 0x22,
+  0x32, 0x81, 0x08, 0x14, 0x42, 0x91, 0xa1, 0xb1, 0xc1, 0x09, 0x23, 0x33, 0x52, 0xf0, 0x15, 0x62, 0x72, 0xd1, 0x0a, 0x16, 0x24, 0x34,
+  0xe1, 0x25, 0xf1, 0x17, 0x18, 0x19, 0x1a, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46,
+  0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a, 0x73, 0x74,
+  0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x82, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98,
+  0x99, 0x9a, 0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3,
+  0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7,
+  0xe8, 0xe9, 0xea, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa };
+
+void huff_codes(const uint8_t bits[16], const uint8_t *vals, uint16_t *code, uint8_t *len) {
+  unsigned c = 0; int k = 0;
+  for (int l = 1; l <= 16; l++) {
+    for (int i = 0; i < bits[l - 1]; i++) { code[vals[k]] = (uint16_t)c; len[vals[k]] = (uint8_t)l; c++; k++; }
+    c <<= 1;
+  }
+}
+void build_jpeg_tables(int quality, JpegTables &T) {
+  memset(&T, 0, sizeof T);
+  memcpy(T.zz, ZZ_H, 64);
+  int q = quality; if (q <= 0) q = 1; if (q > 100) q = 100;
+  int scale = q < 50 ? 5000 / q : 200 - q * 2;
+  for (int t = 0; t < 2; t++) for (int i = 0; i < 64; i++) {
+    long v = ((long)(t ? QC_H[i] : QL_H[i]) * scale + 50L) / 100L;
+    if (v <= 0) v = 1; if (v > 255) v = 255;
+    T.q[t][i] = (uint16_t)v;
+  }
+  huff_codes(DCL_BITS, DC_VALS_H, T.dc_code[0], T.dc_len[0]); huff_codes(DCC_BITS, DC_VALS_H, T.dc_code[1], T.dc_len[1]);
+  huff_codes(ACL_BITS, ACL_VALS, T.ac_code[0], T.ac_len[0]); huff_codes(ACC_BITS, ACC_VALS, T.ac_code[1], T.ac_len[1]);
+  // header template (623 bytes): SOI APP0 DQT DQT SOF0 DHTx4 SOS ; height patched per frame, width 256
+  std::vector<uint8_t> h;
+  auto p8 = [&](int v) { h.push_back((uint8_t)v); };
+  auto p16 = [&](int v) { h.push_back((uint8_t)(v >> 8)); h.push_back((uint8_t)v); };
+  p16(0xFFD8);
+  const uint8_t app0[] = { 0xFF, 0xE0, 0x00, 0x10, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0 };
+  h.insert(h.end(), app0, app0 + sizeof app0);
+  for (int t = 0; t < 2; t++) { p16(0xFFDB); p16(67); p8(t); for (int i = 0; i < 64; i++) p8(T.q[t][ZZ_H[i]]); }
+  p16(0xFFC0); p16(17); p8(8); p16(0); p16(256); p8(3); p8(1); p8(0x22); p8(0); p8(2); p8(0x11); p8(1); p8(3); p8(0x11); p8(1);
+  auto dht = [&](int id, const uint8_t *bits, const uint8_t *vals) { int n = 0; for (int i = 0; i < 16; i++) n += bits[i]; p16(0xFFC4); p16(19 + n); p8(id); h.insert(h.end(), bits, bits + 16); h.insert(h.end(), vals, vals + n); };
+  dht(0x00, DCL_BITS, DC_VALS_H); dht(0x10, ACL_BITS, ACL_VALS); dht(0x01, DCC_BITS, DC_VALS_H); dht(0x11, ACC_BITS, ACC_VALS);
+  p16(0xFFDA); p16(12); p8(3); p8(1); p8(0x00); p8(2); p8(0x11); p8(3); p8(0x11); p8(0); p8(63); p8(0);
+  if (h.size() != JPEG_HDR_BYTES) { fprintf(stderr, "ccv2: jpeg header template is %zu bytes\n", h.size()); abort(); }
+  memcpy(T.header, h.data(), JPEG_HDR_BYTES);
+}
+
+// ---- capacity rules (bytes) for a frame of n points
+size_t tree_cap_for(size_t n) { return ((8 * n + 1024) + 255) & ~size_t(255); }
+size_t cpay_cap_for(size_t n) { return ((4 * n + 8192) + 255) & ~size_t(255); }
+size_t cen_cap_for(size_t n) { return ((3 * n + 256) + 255) & ~size_t(255); }
+size_t rc_cap_for(size_t raw_cap) { return ((raw_cap + raw_cap / 8 + 4096) + 255) & ~size_t(255); }
+size_t stream_cap_for(size_t n, bool cen) {
+  return FRAME_HDR_BYTES + 8 + rc_cap_for(tree_cap_for(n)) + (cen ? 4 + rc_cap_for(cen_cap_for(n)) : 0) + 8 + rc_cap_for(cpay_cap_for(n));
+}
+
+struct EncSlotLayout { size_t bytes; size_t zero_off, zero_bytes; };
+
+// carve the per-frame group-slot workspace; returns total bytes (measure when base == nullptr)
+size_t carve_enc_slot(uint8_t *base, size_t n, EncFrame *f, const ccv2_params &prm, size_t *zero_off, size_t *zero_bytes) {
+  Carver cv(base);
+  const uint32_t tiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE) + 1;
+  const uint32_t scan_tiles = (uint32_t)(n / 1024) + 8;
+  const size_t img_h = n / 256 + 1, mcu_h = (img_h + 15) / 16;
+  const size_t jbits_words = ((4 * n + 8192) / 4 + 63) & ~size_t(63);
+  // --- zero-initialised region first
+  cv.off = 0;
+  uint32_t *ghist = cv.take<uint32_t>(8 * 256);
+  size_t z0 = 0;
+  uint32_t *sort_status = cv.take<uint32_t>((size_t)8 * tiles * 256);
+  uint64_t *scan_status = cv.take<uint64_t>((size_t)3 * scan_tiles);
+  uint32_t *jbits = cv.take<uint32_t>(jbits_words + 16);
+  size_t z1 = (cv.off + 255) & ~size_t(255);
+  // --- rest
+  uint64_t *k0 = cv.take<uint64_t>(n + 8), *k1 = cv.take<uint64_t>(n + 8);
+  uint32_t *v0 = cv.take<uint32_t>(n + 8), *v1 = cv.take<uint32_t>(n + 8);
+  uint64_t *leaf_key = cv.take<uint64_t>(n + 8);
+  uint32_t *leaf_start = cv.take<uint32_t>(n + 8), *leaf_off = cv.take<uint32_t>(n + 8);
+  uint8_t *first_new = cv.take<uint8_t>(n + 8);
+  uint8_t *avg = cv.take<uint8_t>(3 * n + 64);
+  int16_t *coef = cv.take<int16_t>(mcu_h * 16 * 384 + 64);
+  (void)prm;
+  if (f) {
+    f->ghist = ghist; f->sort_status = sort_status; f->tiles_max = tiles; f->scan_status = scan_status; f->scan_tiles_max = scan_tiles;
+    f->jbits_buf = jbits; f->jbits_cap_words = (uint32_t)jbits_words;
+    f->keys[0] = k0; f->keys[1] = k1; f->vals[0] = v0; f->vals[1] = v1;
+    f->leaf_key = leaf_key; f->leaf_start = leaf_start; f->leaf_off = leaf_off; f->first_new = first_new;
+    f->avg = avg; f->coef = coef;
+  }
+  if (zero_off) *zero_off = z0;
+  if (zero_bytes) *zero_bytes = z1 - z0;
+  return (cv.off + 255) & ~size_t(255);
+}
+size_t carve_enc_persist(uint8_t *base, size_t n, EncFrame *f, bool cen) {
+  Carver cv(base);
+  uint8_t *tree = cv.take<uint8_t>(tree_cap_for(n));
+  uint8_t *cenb = cv.take<uint8_t>(cen ? cen_cap_for(n) : 256);
+  uint8_t *cpay = cv.take<uint8_t>(cpay_cap_for(n));
+  uint8_t *rc0 = cv.take<uint8_t>(cen ? rc_cap_for(cen_cap_for(n)) : 256);
+  uint8_t *rc1 = cv.take<uint8_t>(rc_cap_for(cpay_cap_for(n)));
+  uint8_t *stream = cv.take<uint8_t>(stream_cap_for(n, cen));
+  if (f) {
+    f->tree = tree; f->tree_cap = (uint32_t)tree_cap_for(n) - 64; f->cen = cenb; f->cpay = cpay; f->cpay_cap = (uint32_t)cpay_cap_for(n) - 64;
+    f->rc_tmp[0] = rc0; f->rc_tmp[1] = rc1; f->rc_tmp_cap[0] = (uint32_t)(cen ? rc_cap_for(cen_cap_for(n)) : 0); f->rc_tmp_cap[1] = (uint32_t)rc_cap_for(cpay_cap_for(n));
+    f->stream = stream; f->stream_cap = stream_cap_for(n, cen);
+  }
+  return (cv.off + 255) & ~size_t(255);
+}
+
+int check_params(const ccv2_params *p, std::string &err) {
+  if (!p) { err = "null params"; return CCV2_ERR_ARG; }
+  if (p->profile != CCV2_MANUAL_CONFIGURATION) { err = "only MANUAL_CONFIGURATION is implemented"; return CCV2_ERR_UNSUPPORTED; }
+  if (!p->do_voxel_grid_downsampling) { err = "detail mode (doVoxelGridDownDownSampling=false) is not implemented"; return CCV2_ERR_UNSUPPORTED; }
+  if (!(p->octree_resolution > 0)) { err = "octree_resolution must be > 0"; return CCV2_ERR_ARG; }
+  if (p->color_coding_type == 2) { err = "colorCodingType 2 (JPEG lines) is not implemented yet"; return CCV2_ERR_UNSUPPORTED; }
+  if (p->color_coding_type > 3) { err = "unknown colorCodingType"; return CCV2_ERR_ARG; }
+  if (p->color_bit_resolution > 8) { err = "colorBitResolution > 8"; return CCV2_ERR_ARG; }
+  return CCV2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ccv2_default_params(ccv2_params *p) {
+  memset(p, 0, sizeof *p);
+  p->profile = CCV2_MANUAL_CONFIGURATION;
+  p->point_resolution = ldexp(1.0, -11); p->octree_resolution = ldexp(1.0, -11);
+  p->do_voxel_grid_downsampling = 1; p->i_frame_rate = 0; p->do_color_encoding = 1; p->color_bit_resolution = 8;
+  p->color_coding_type = 1; p->do_voxel_grid_centroid = 0; p->create_scalable_stream = 0; p->code_connectivity = 0;
+  p->jpeg_quality = 85; p->num_threads = 1; p->macroblock_size = 16; p->do_icp_color_offset = 0;
+}
+
+const char *ccv2_status_string(int s) {
+  switch (s) {
+    case CCV2_OK: return "ok";
+    case CCV2_ERR_ARG: return "bad argument";
+    case CCV2_ERR_CUDA: return "CUDA error";
+    case CCV2_ERR_UNSUPPORTED: return "configuration not implemented";
+    case CCV2_ERR_CAPACITY: return "output buffer too small";
+    case CCV2_ERR_WORKSPACE: return "internal workspace bound exceeded";
+    case CCV2_ERR_STREAM: return "malformed compressed stream";
+    case CCV2_ERR_DEPTH: return "octree depth > 21";
+    default: return "unknown";
+  }
+}
+const char *ccv2_last_error(const ccv2_codec *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
+  if (!out) return CCV2_ERR_ARG;
+  *out = nullptr;
+  int rc = check_params(p, g_create_error);
+  if (rc) return rc;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "bad ordinal");
+    cudaGetLastError();
+    return CCV2_ERR_CUDA;
+  }
+  ccv2_codec *c = new ccv2_codec();
+  c->prm = *p; c->device = device;
+  if (const char *s = getenv("CCV2_STREAMS")) c->n_streams = std::max(1, std::min(MAX_STREAMS, atoi(s)));
+  if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(1, std::min(64, atoi(s)));
+  auto fail = [&](cudaError_t ee, const char *what) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ee); ccv2_destroy(c); return CCV2_ERR_CUDA; };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+  if ((e = cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+  for (int i = 0; i < c->n_streams; i++) if ((e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+  if ((e = cudaEventCreate(&c->ev_start)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  JpegTables T; build_jpeg_tables(p->jpeg_quality, T);
+  if ((e = cudaMalloc(&c->d_tables, sizeof T)) != cudaSuccess) return fail(e, "cudaMalloc");
+  if ((e = cudaMemcpy(c->d_tables, &T, sizeof T, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "cudaMemcpy");
+  if ((e = cudaMalloc(&c->d_frame_counter, 4)) != cudaSuccess) return fail(e, "cudaMalloc");
+  if ((e = cudaMemset(c->d_frame_counter, 0, 4)) != cudaSuccess) return fail(e, "cudaMemset");
+  *out = c;
+  return CCV2_OK;
+}
+
+void ccv2_destroy(ccv2_codec *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto ev : c->ev_group) cudaEventDestroy(ev);
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
+  if (c->ev_end) cudaEventDestroy(c->ev_end);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (int i = 0; i < MAX_STREAMS; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+  if (c->main_stream) cudaStreamDestroy(c->main_stream);
+  if (c->d_tables) cudaFree(c->d_tables);
+  if (c->d_frame_counter) cudaFree(c->d_frame_counter);
+  c->enc_frames.release(); c->enc_slots.release(); c->enc_persist.release(); c->enc_input.release();
+  c->dec_frames.release(); c->dec_work.release(); c->dec_input.release(); c->dec_output.release();
+  c->h_frames.release(); c->h_dframes.release();
+  delete c;
+}
+
+size_t ccv2_max_compressed_size(size_t npts) { return stream_cap_for(npts, true); }
+
+void *ccv2_host_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+void ccv2_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int ccv2_get_metrics(ccv2_codec *c, uint64_t m[3]) { if (!c || !m) return CCV2_ERR_ARG; for (int i = 0; i < 3; i++) m[i] = c->metrics[i]; return CCV2_OK; }
+int ccv2_set_frame_id(ccv2_codec *c, uint32_t v) {
+  if (!c) return CCV2_ERR_ARG;
+  cudaSetDevice(c->device);
+  c->frame_id = v;
+  CU(cudaMemcpy(c->d_frame_counter, &v, 4, cudaMemcpyHostToDevice));
+  return CCV2_OK;
+}
+uint32_t ccv2_get_frame_id(const ccv2_codec *c) { return c ? c->frame_id : 0; }
+uint64_t ccv2_last_launch_count(const ccv2_codec *c) { return c ? c->launches : 0; }
+float ccv2_last_device_ms(const ccv2_codec *c) { return c ? c->device_ms : 0.f; }
+
+int ccv2_peek_point_count(const void *in_host, size_t len, uint64_t *npts) {
+  if (!in_host || !npts || len < FRAME_HDR_BYTES) return CCV2_ERR_ARG;
+  const uint8_t *b = (const uint8_t *)in_host;
+  if (memcmp(b, "<PCL-OCT-CODECV2-COMPRESSED><PCL-OCT-COMPRESSED>", 48) != 0) return CCV2_ERR_STREAM;
+  memcpy(npts, b + 55, 8);
+  return CCV2_OK;
+}
+
+// ================================================================================================ encode
+int ccv2_encode_batch(ccv2_codec *c, int nframes, const void *const *pts, const size_t *npts,
+                      void *const *out, const size_t *out_cap, size_t *out_len) {
+  if (!c || nframes < 0 || (nframes && (!pts || !npts || !out || !out_cap || !out_len))) return CCV2_ERR_ARG;
+  c->err.clear(); c->launches = 0; c->device_ms = 0;
+  if (nframes == 0) return CCV2_OK;
+  CU(cudaSetDevice(c->device));
+  const ccv2_params &prm = c->prm;
+  const bool cen = prm.do_voxel_grid_centroid != 0, color = prm.do_color_encoding != 0;
+  const int G = c->group, NS = c->n_streams;
+  const int ngroups = (nframes + G - 1) / G;
+  size_t nmax = 1;
+  for (int i = 0; i < nframes; i++) { if (npts[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; } if (npts[i] && !pts[i]) return CCV2_ERR_ARG; nmax = std::max(nmax, npts[i]); }
+
+  // ---- workspaces. Slots: one per (stream, frame-in-group); persist + input staging: one per frame of the batch
+  size_t zoff = 0, zbytes = 0;
+  const size_t slot_bytes = carve_enc_slot(nullptr, nmax, nullptr, prm, &zoff, &zbytes);
+  const int nslots = std::min(ngroups, NS) * G;
+  CU(c->enc_slots.ensure(slot_bytes * nslots));
+  std::vector<size_t> persist_off(nframes + 1, 0), input_off(nframes + 1, 0);
+  std::vector<char> in_dev(nframes), out_dev(nframes);
+  for (int i = 0; i < nframes; i++) {
+    persist_off[i + 1] = persist_off[i] + carve_enc_persist(nullptr, npts[i], nullptr, cen);
+    in_dev[i] = npts[i] ? is_device_ptr(pts[i]) : 1;
+    out_dev[i] = out[i] ? is_device_ptr(out[i]) : 0;
+    input_off[i + 1] = input_off[i] + (in_dev[i] ? 0 : ((32 * npts[i] + 255) & ~size_t(255)));
+  }
+  CU(c->enc_persist.ensure(persist_off[nframes]));
+  CU(c->enc_input.ensure(input_off[nframes] + 256));
+  const size_t frames_bytes = (sizeof(EncFrame) * nframes + 255) & ~size_t(255);
+  CU(c->enc_frames.ensure(frames_bytes + (size_t)nframes * 3 * 256 * 4));
+  CU(c->h_frames.ensure(sizeof(EncFrame) * nframes));
+  while ((int)c->ev_group.size() < ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_group.push_back(ev); }
+
+  EncFrame *hf = (EncFrame *)c->h_frames.p;
+  EncFrame *df = (EncFrame *)c->enc_frames.p;
+  memset(hf, 0, sizeof(EncFrame) * nframes);
+  for (int i = 0; i < nframes; i++) {
+    EncFrame &f = hf[i];
+    const int g = i / G, slot = (g % NS) * G + (i % G);
+    f.pts = in_dev[i] ? (const uint8_t *)pts[i] : (const uint8_t *)c->enc_input.p + input_off[i];
+    f.n = (uint32_t)npts[i];
+    f.violator = NONE_U32;
+    carve_enc_slot((uint8_t *)c->enc_slots.p + slot_bytes * slot, nmax, &f, prm, nullptr, nullptr);
+    carve_enc_persist((uint8_t *)c->enc_persist.p + persist_off[i], npts[i], &f, cen);
+    f.hist = (uint32_t *)((uint8_t *)c->enc_frames.p + frames_bytes) + (size_t)i * 3 * 256;
+    if (color && prm.color_coding_type != 1) f.avg = f.cpay;       // raw averages are the colour payload (types 0, 3)
+  }
+
+  EncParams P;
+  P.res = prm.octree_resolution;
+  { int ex; double m = frexp(P.res, &ex); P.res_pow2 = (m == 0.5); P.inv_res = P.res_pow2 ? 1.0 / P.res : 0.0; }
+  P.do_color = color; P.color_type = prm.color_coding_type; P.do_centroid = cen;
+  P.color_reduction = (prm.color_coding_type == 0) ? std::max(0, 8 - (int)prm.color_bit_resolution) : 0;   // jp_color_coder_ is never configured
+  P.prefix_len = 16384;
+  HeaderParams H;
+  H.octree_res = prm.octree_resolution; H.point_res = (double)(float)prm.point_resolution;
+  H.do_voxel_grid = 1; H.with_color = color; H.color_bits = prm.color_bit_resolution; H.do_centroid = cen;
+  H.connectivity = prm.code_connectivity != 0; H.scalable = prm.create_scalable_stream != 0; H.icp_offset = prm.do_icp_color_offset != 0; H._p = 0;
+  H.color_type = prm.color_coding_type; H.macroblock = prm.macroblock_size;
+
+  cudaStream_t ms = c->main_stream;
+  CU(cudaEventRecord(c->ev_start, ms));
+  CU(cudaMemcpyAsync(df, hf, sizeof(EncFrame) * nframes, cudaMemcpyHostToDevice, ms));
+  CU(cudaMemsetAsync((uint8_t *)c->enc_frames.p + frames_bytes, 0, (size_t)nframes * 3 * 256 * 4, ms));
+  cudaEvent_t ev_setup = c->ev_fork;
+  CU(cudaEventRecord(ev_setup, ms));
+
+  uint64_t launches = 0;
+  uint32_t *counter = c->d_frame_counter;
+  for (int g = 0; g < ngroups; g++) {
+    cudaStream_t st = c->streams[g % NS];
+    const int f0 = g * G, gf = std::min(G, nframes - f0);
+    EncFrame *dg = df + f0;
+    CU(cudaStreamWaitEvent(st, ev_setup, 0));
+    size_t gn = 1;
+    for (int i = 0; i < gf; i++) {
+      gn = std::max(gn, npts[f0 + i]);
+      if (!in_dev[f0 + i] && npts[f0 + i]) CU(cudaMemcpyAsync((void *)hf[f0 + i].pts, pts[f0 + i], 32 * npts[f0 + i], cudaMemcpyHostToDevice, st));
+      const int slot = (g % NS) * G + i;
+      CU(cudaMemsetAsync((uint8_t *)c->enc_slots.p + slot_bytes * slot + zoff, 0, zbytes, st));
+    }
+    const unsigned gx256 = (unsigned)((gn + 255) / 256), gtiles = (unsigned)((gn + SORT_TILE - 1) / SORT_TILE);
+    bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 0);
+    bbox_fixup_kernel<<<gf, 32, 0, st>>>(dg, P);
+    keygen_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P, 0);
+    bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 1);
+    keygen_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P, 1);
+    // frame ids are sequential over the batch: group g's setup needs group g-1's setup kernel to have run
+    if (g > 0) CU(cudaStreamWaitEvent(st, c->ev_group[g - 1], 0));
+    frame_setup_kernel<<<1, 32, 0, st>>>(dg, gf, counter);
+    CU(cudaEventRecord(c->ev_group[g], st));
+    sort_hist_kernel<<<dim3(gtiles, gf), 256, 0, st>>>(dg);
+    launches += 7;
+    for (int p = 0; p < 8; p++) { sort_pass_kernel<<<dim3(gtiles, gf), SORT_THREADS, 0, st>>>(dg, p); launches++; }
+    leaf_scan_kernel<<<dim3((unsigned)((gn + LEAF_TILE - 1) / LEAF_TILE), gf), LEAF_THREADS, 0, st>>>(dg);
+    leaf_emit_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P);
+    launches += 2;
+    if (color && prm.color_coding_type == 1) {
+      const size_t img_h = gn / 256 + 1, mcu_h = (img_h + 15) / 16, nblk = mcu_h * 16 * 6;
+      jpeg_mcu_kernel<<<dim3((unsigned)(mcu_h * 16), gf), 256, 0, st>>>(dg, c->d_tables);
+      jpeg_huff_kernel<<<dim3((unsigned)((nblk + HUFF_THREADS - 1) / HUFF_THREADS), gf), HUFF_THREADS, 0, st>>>(dg, c->d_tables);
+      const size_t jb = 4 * gn + 8192;
+      jpeg_stuff_kernel<<<dim3((unsigned)((jb + STUFF_THREADS * STUFF_BYTES - 1) / (STUFF_THREADS * STUFF_BYTES)), gf), STUFF_THREADS, 0, st>>>(dg, c->d_tables);
+      launches += 3;
+    }
+    const size_t hmax = std::max(tree_cap_for(gn), cpay_cap_for(gn));
+    hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), 3, gf), 256, 0, st>>>(dg);
+    rc_encode_kernel<<<dim3(3, gf), 32, 0, st>>>(dg, cen, color);
+    assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H);
+    launches += 3;
+    CU(cudaMemcpyAsync(hf + f0, dg, sizeof(EncFrame) * gf, cudaMemcpyDeviceToHost, st));
+    CU(cudaGetLastError());
+  }
+  // ---- collect: per group wait for its record copy, then move the streams out with exact sizes
+  int rc = CCV2_OK;
+  for (int g = 0; g < ngroups; g++) {
+    cudaStream_t st = c->streams[g % NS];
+    // the D2H of the records is the last op queued on st for this group so far
+    cudaEvent_t ev = c->ev_group[g];
+    CU(cudaEventRecord(ev, st));
+    CU(cudaEventSynchronize(ev));
+    const int f0 = g * G, gf = std::min(G, nframes - f0);
+    for (int i = 0; i < gf; i++) {
+      EncFrame &f = hf[f0 + i];
+      out_len[f0 + i] = 0;
+      if (f.error) {
+        if (rc == CCV2_OK) {
+          rc = (f.error & FERR_DEPTH) ? CCV2_ERR_DEPTH : CCV2_ERR_WORKSPACE;
+          char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x", f0 + i, f.error); c->err = b;
+        }
+        continue;
+      }
+      if (f.out_len == 0) continue;
+      if (f.out_len > out_cap[f0 + i] || !out[f0 + i]) { if (rc == CCV2_OK) { rc = CCV2_ERR_CAPACITY; c->err = "output buffer too small"; } continue; }
+      CU(cudaMemcpyAsync(out[f0 + i], f.stream, f.out_len, out_dev[f0 + i] ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+      out_len[f0 + i] = f.out_len;
+    }
+    CU(cudaEventRecord(ev, st));
+    CU(cudaStreamWaitEvent(ms, ev, 0));
+  }
+  CU(cudaEventRecord(c->ev_end, ms));
+  CU(cudaEventSynchronize(c->ev_end));
+  CU(cudaEventElapsedTime(&c->device_ms, c->ev_start, c->ev_end));
+  CU(cudaMemcpy(&c->frame_id, counter, 4, cudaMemcpyDeviceToHost));
+  c->launches = launches;
+  c->enc_host.assign(hf, hf + nframes);
+  for (int i = nframes - 1; i >= 0; i--) if (hf[i].out_len) { for (int k = 0; k < 3; k++) c->metrics[k] = hf[i].coded[k]; break; }
+  return rc;
+}
+
+int ccv2_debug_fetch(ccv2_codec *c, int frame, int what, void *host_buf, size_t cap, size_t *len) {
+  if (!c || frame < 0 || frame >= (int)c->enc_host.size() || !len) return CCV2_ERR_ARG;
+  CU(cudaSetDevice(c->device));
+  const EncFrame &f = c->enc_host[frame];
+  const void *src = nullptr; size_t n = 0;
+  ccv2_frame_info info;
+  switch (what) {
+    case 0: src = f.leaf_key; n = (size_t)f.V * 8; break;
+    case 1: src = f.tree; n = f.B; break;
+    case 2: src = f.avg; n = (size_t)f.V * 3; break;
+    case 3: src = f.cpay; n = f.ncolor; break;
+    case 4: src = f.vals[f.npasses & 1]; n = (size_t)f.n_finite * 4; break;
+    case 5:
+      memset(&info, 0, sizeof info);
+      info.depth = f.depth; info.n_finite = f.n_finite; info.n_leaves = f.V; info.n_tree_bytes = f.B; info.n_color_bytes = f.ncolor; info.error = f.error;
+      for (int a = 0; a < 3; a++) { info.bb_min[a] = f.bmin[a]; info.bb_max[a] = f.bmax[a]; info.coded[a] = f.coded[a]; }
+      *len = sizeof info;
+      if (cap < sizeof info || !host_buf) return CCV2_ERR_CAPACITY;
+      memcpy(host_buf, &info, sizeof info);
+      return CCV2_OK;
+    default: return CCV2_ERR_ARG;
+  }
+  *len = n;
+  if (n > cap || !host_buf) return CCV2_ERR_CAPACITY;
+  if (n) CU(cudaMemcpy(host_buf, src, n, cudaMemcpyDeviceToHost));
+  return CCV2_OK;
+}
+
+// ================================================================================================ decode
+static size_t carve_dec(uint8_t *base, size_t pcap, DecFrame *f, size_t *zero_off, size_t *zero_bytes) {
+  Carver cv(base);
+  const size_t img_h = pcap / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
+  const uint32_t scan_tiles = (uint32_t)(pcap / NODE_THREADS) + 8;
+  uint64_t *scan_status = cv.take<uint64_t>(scan_tiles);
+  int16_t *coef = cv.take<int16_t>(nblocks * 64 + 64);
+  size_t z1 = (cv.off + 255) & ~size_t(255);
+  uint8_t *tree = cv.take<uint8_t>(tree_cap_for(pcap));
+  uint8_t *cen = cv.take<uint8_t>(cen_cap_for(pcap));
+  uint8_t *col = cv.take<uint8_t>(cpay_cap_for(pcap));
+  uint64_t *node_prefix = cv.take<uint64_t>(pcap + 8);
+  uint8_t *node_byte = cv.take<uint8_t>(pcap + 8);
+  uint8_t *planes = cv.take<uint8_t>(mcu_h * 16 * 256 * 3 / 2 + 256);
+  uint16_t *qt = cv.take<uint16_t>(128);
+  if (f) {
+    f->scan_status = scan_status; f->scan_tiles_max = scan_tiles; f->coef = coef; f->coef_cap_blocks = (uint32_t)nblocks;
+    f->tree = tree; f->tree_cap = (uint32_t)tree_cap_for(pcap) - 64; f->cen = cen; f->cen_cap = (uint32_t)cen_cap_for(pcap) - 64;
+    f->col = col; f->col_cap = (uint32_t)cpay_cap_for(pcap) - 64;
+    f->node_prefix = node_prefix; f->node_byte = node_byte; f->node_cap = (uint32_t)pcap;
+    f->planes = planes; f->planes_cap = (uint32_t)(mcu_h * 16 * 256 * 3 / 2); f->qt = qt;
+  }
+  if (zero_off) *zero_off = 0;
+  if (zero_bytes) *zero_bytes = z1;
+  return (cv.off + 255) & ~size_t(255);
+}
+
+int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const size_t *in_len,
+                      void *const *pts_out, const size_t *pts_cap, size_t *npts_out) {
+  if (!c || nframes < 0 || (nframes && (!in || !in_len || !pts_out || !pts_cap || !npts_out))) return CCV2_ERR_ARG;
+  c->err.clear(); c->launches = 0; c->device_ms = 0;
+  if (nframes == 0) return CCV2_OK;
+  CU(cudaSetDevice(c->device));
+  const int G = c->group, NS = c->n_streams;
+  const int ngroups = (nframes + G - 1) / G;
+  std::vector<size_t> work_off(nframes + 1, 0), input_off(nframes + 1, 0), output_off(nframes + 1, 0), zb(nframes, 0);
+  std::vector<char> in_dev(nframes), out_dev(nframes);
+  for (int i = 0; i < nframes; i++) {
+    if (pts_cap[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; }
+    if ((in_len[i] && !in[i]) || (pts_cap[i] && !pts_out[i])) return CCV2_ERR_ARG;
+    size_t zo;
+    work_off[i + 1] = work_off[i] + carve_dec(nullptr, pts_cap[i], nullptr, &zo, &zb[i]);
+    in_dev[i] = in_len[i] ? is_device_ptr(in[i]) : 1;
+    out_dev[i] = pts_cap[i] ? is_device_ptr(pts_out[i]) : 1;
+    input_off[i + 1] = input_off[i] + (in_dev[i] ? 0 : ((in_len[i] + 64 + 255) & ~size_t(255)));
+    output_off[i + 1] = output_off[i] + (out_dev[i] ? 0 : ((32 * pts_cap[i] + 255) & ~size_t(255)));
+  }
+  CU(c->dec_work.ensure(work_off[nframes]));
+  CU(c->dec_input.ensure(input_off[nframes] + 256));
+  CU(c->dec_output.ensure(output_off[nframes] + 256));
+  CU(c->dec_frames.ensure(sizeof(DecFrame) * nframes));
+  CU(c->h_dframes.ensure(sizeof(DecFrame) * nframes));
+  while ((int)c->ev_group.size() < ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_group.push_back(ev); }
+  DecFrame *hf = (DecFrame *)c->h_dframes.p, *df = (DecFrame *)c->dec_frames.p;
+  memset(hf, 0, sizeof(DecFrame) * nframes);
+  for (int i = 0; i < nframes; i++) {
+    DecFrame &f = hf[i];
+    f.in = in_dev[i] ? (const uint8_t *)in[i] : (const uint8_t *)c->dec_input.p + input_off[i];
+    f.in_len = in_len[i];
+    f.out_pts = out_dev[i] ? (uint8_t *)pts_out[i] : (uint8_t *)c->dec_output.p + output_off[i];
+    f.out_cap = pts_cap[i];
+    carve_dec((uint8_t *)c->dec_work.p + work_off[i], pts_cap[i], &f, nullptr, nullptr);
+    if (in_len[i] == 0) f.error = FERR_BAD_STREAM;
+  }
+  cudaStream_t ms = c->main_stream;
+  CU(cudaEventRecord(c->ev_start, ms));
+  CU(cudaMemcpyAsync(df, hf, sizeof(DecFrame) * nframes, cudaMemcpyHostToDevice, ms));
+  cudaEvent_t ev_setup = c->ev_fork;
+  CU(cudaEventRecord(ev_setup, ms));
+  uint64_t launches = 0;
+  for (int g = 0; g < ngroups; g++) {
+    cudaStream_t st = c->streams[g % NS];
+    const int f0 = g * G, gf = std::min(G, nframes - f0);
+    DecFrame *dg = df + f0;
+    CU(cudaStreamWaitEvent(st, ev_setup, 0));
+    size_t pmax = 1;
+    for (int i = 0; i < gf; i++) {
+      const int k = f0 + i;
+      pmax = std::max(pmax, pts_cap[k]);
+      if (!in_dev[k] && in_len[k]) CU(cudaMemcpyAsync((void *)hf[k].in, in[k], in_len[k], cudaMemcpyHostToDevice, st));
+      CU(cudaMemsetAsync((uint8_t *)c->dec_work.p + work_off[k], 0, zb[k], st));
+    }
+    dec_entropy_kernel<<<gf, 32, 0, st>>>(dg);
+    dec_serial_kernel<<<dim3(2, gf), 32, 0, st>>>(dg);
+    const size_t img_h = pmax / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
+    jpeg_idct_kernel<<<dim3((unsigned)((nblocks + 31) / 32), gf), 256, 0, st>>>(dg, c->d_tables);
+    dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg);
+    launches += 4;
+    CU(cudaMemcpyAsync(hf + f0, dg, sizeof(DecFrame) * gf, cudaMemcpyDeviceToHost, st));
+    CU(cudaGetLastError());
+  }
+  int rc = CCV2_OK;
+  for (int g = 0; g < ngroups; g++) {
+    cudaStream_t st = c->streams[g % NS];
+    cudaEvent_t ev = c->ev_group[g];
+    CU(cudaEventRecord(ev, st));
+    CU(cudaEventSynchronize(ev));
+    const int f0 = g * G, gf = std::min(G, nframes - f0);
+    for (int i = 0; i < gf; i++) {
+      const int k = f0 + i;
+      DecFrame &f = hf[k];
+      npts_out[k] = 0;
+      if (f.error) {
+        if (rc == CCV2_OK) {
+          rc = (f.error & FERR_OUT_CAP) ? CCV2_ERR_CAPACITY : (f.error & FERR_DEPTH) ? CCV2_ERR_DEPTH : (f.error & FERR_UNSUPPORTED) ? CCV2_ERR_UNSUPPORTED
+             : (f.error & (FERR_TREE_CAP | FERR_JPEG_CAP)) ? CCV2_ERR_WORKSPACE : CCV2_ERR_STREAM;
+          char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x", k, f.error); c->err = b;
+        }
+        continue;
+      }
+      npts_out[k] = f.V;
+      if (!out_dev[k] && f.V) CU(cudaMemcpyAsync(pts_out[k], f.out_pts, 32ull * f.V, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaEventRecord(ev, st));
+    CU(cudaStreamWaitEvent(ms, ev, 0));
+  }
+  CU(cudaEventRecord(c->ev_end, ms));
+  CU(cudaEventSynchronize(c->ev_end));
+  CU(cudaEventElapsedTime(&c->device_ms, c->ev_start, c->ev_end));
+  c->launches = launches;
+  for (int i = nframes - 1; i >= 0; i--) if (!hf[i].error) { for (int k = 0; k < 3; k++) c->metrics[k] = hf[i].coded[k]; c->frame_id = hf[i].frame_id; break; }
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+// common.cuh -- shared device structs and primitives for libccv2 (sm_100a).
+//
+// Layout rule: one EncFrame / DecFrame record per frame lives in device memory; every kernel is launched
+// over a *group* of frames with blockIdx.y = frame-in-group and reads its sizes from the record, so the
+// host never has to synchronise between stages (all sizes -- depth, V, B, J -- are device-side values).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CCV2_MAX_DEPTH 21
+#define FULL_MASK 0xFFFFFFFFu
+#define NONE_U32 0xFFFFFFFFu
+
+// error bits written by kernels into frame.error
+enum : uint32_t {
+  FERR_DEPTH = 1u << 0,       // realised depth > CCV2_MAX_DEPTH
+  FERR_TREE_CAP = 1u << 1,    // tree bytes exceed workspace cap
+  FERR_STREAM_CAP = 1u << 2,  // compressed stream exceeds arena/caller cap
+  FERR_JPEG_CAP = 1u << 3,    // jpeg buffers exceeded
+  FERR_BAD_STREAM = 1u << 4,  // decoder: malformed input
+  FERR_OUT_CAP = 1u << 5,     // decoder: caller's point buffer too small
+  FERR_UNSUPPORTED = 1u << 6, // decoder: stream uses a mode outside the implemented scope
+};
+
+enum : int { TK_SORT0 = 0, TK_LEAF = 8, TK_HUFF = 9, TK_STUFF = 10, TK_NODES = 11, TK_COUNT = 16 };
+
+struct __align__(16) JpegTables {   // per codec, device resident
+  uint16_t q[2][64];           // quant tables, natural order (lum, chroma)
+  uint16_t dc_code[2][12]; uint8_t dc_len[2][12];
+  uint16_t ac_code[2][256]; uint8_t ac_len[2][256];
+  uint8_t header[623];         // JFIF header template for this quality (height patched per frame)
+  uint8_t zz[64];              // zigzag index -> natural index
+};
+
+struct EncParams {             // by value to kernels
+  double res, inv_res;         // octree resolution; inv_res valid iff res_pow2
+  int res_pow2;
+  int do_color, color_type, color_reduction, do_centroid;
+  int prefix_len;              // points handled exactly by the single-CTA bbox kernel
+};
+
+struct EncFrame {
+  // input
+  const uint8_t *pts; uint32_t n; uint32_t _pad0;
+  // bbox / keys
+  double bmin[3], bmax[3];
+  uint32_t depth, defined, n_finite, violator, rekey, npasses;
+  // leaves
+  uint32_t V, B;
+  // jpeg geometry / sizes
+  uint32_t img_h, mcu_h, jbits, J;
+  uint32_t ncolor;             // bytes handed to the range coder for the colour layer
+  uint32_t ncen;               // centroid bytes (3V) when enabled
+  uint32_t ticket[TK_COUNT];
+  // results
+  uint32_t error, frame_id;
+  uint64_t out_len; uint64_t coded[3];
+  uint32_t rc_len[3];          // coded bytes per layer incl. table (tree, centroid, colour)
+  uint32_t _pad1;
+  // group-slot workspace
+  uint64_t *keys[2]; uint32_t *vals[2];
+  uint32_t *ghist;             // [8][256]
+  uint32_t *sort_status;       // [8][tiles_max][256]
+  uint32_t tiles_max, _pad2;
+  uint64_t *leaf_key; uint32_t *leaf_start; uint32_t *leaf_off; uint8_t *first_new;
+  uint64_t *scan_status;       // chained-scan status words (leaf / huff / stuff), 3 x scan_tiles_max
+  uint32_t scan_tiles_max, _pad3;
+  uint8_t *avg;                // 3 bytes per leaf (B,G,R)
+  int16_t *coef;               // jpeg coefficients [mcu][6][64] zigzag order
+  uint32_t *jbits_buf;         // unstuffed entropy-coded bits
+  uint32_t jbits_cap_words, _pad4;
+  // per-frame persistent buffers (live until the frame's stream is assembled)
+  uint8_t *tree; uint32_t tree_cap; uint32_t _pad5;
+  uint8_t *cen;                // centroid residual bytes
+  uint8_t *cpay; uint32_t cpay_cap; uint32_t _pad6;   // colour payload (jpeg file or raw averages)
+  uint32_t *hist;              // [3][256]
+  uint8_t *stream; uint64_t stream_cap;
+  uint8_t *rc_tmp[2]; uint32_t rc_tmp_cap[2];         // range-coded centroid / colour layers before assembly
+};
+
+struct DecFrame {
+  const uint8_t *in; uint64_t in_len;
+  uint8_t *out_pts; uint64_t out_cap;       // points
+  // header
+  double res, bmin[3], bmax[3];
+  uint64_t point_count;
+  uint32_t depth, cct, frame_id;
+  uint32_t data_with_color, do_centroid, color_bits;
+  uint32_t B, ncen, ncol;
+  uint32_t n_bottom, V;
+  uint32_t img_w, img_h, mcu_w, mcu_h, n_blocks;
+  uint32_t ticket[TK_COUNT];
+  uint32_t error, _pad0;
+  uint64_t coded[3];
+  // buffers
+  uint8_t *tree; uint32_t tree_cap, _pad1;
+  uint8_t *cen; uint32_t cen_cap, _pad2;
+  uint8_t *col; uint32_t col_cap, _pad3;
+  uint64_t *node_prefix; uint8_t *node_byte; uint32_t node_cap, _pad4;
+  int16_t *coef; uint32_t coef_cap_blocks, _pad5;
+  uint8_t *planes; uint32_t planes_cap, _pad6;   // Y | Cb | Cr
+  uint16_t *qt;                                  // [2][64] natural order, written by the huffman stage
+  uint64_t *scan_status; uint32_t scan_tiles_max, _pad7;
+};
+
+// ---------------------------------------------------------------- small device helpers
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p) { return *(const volatile uint64_t *)p; }
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+
+// spread the low 21 bits of v so that bit i lands at bit 3i
+__device__ __forceinline__ uint64_t spread3(uint32_t v) {
+  uint64_t x = v & 0x1FFFFFull;
+  x = (x | (x << 32)) & 0x1F00000000FFFFull;
+  x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+  x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+  x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+  x = (x | (x << 2)) & 0x1249249249249249ull;
+  return x;
+}
+__device__ __forceinline__ uint32_t compact3(uint64_t x) {
+  x &= 0x1249249249249249ull;
+  x = (x | (x >> 2)) & 0x10C30C30C30C30C3ull;
+  x = (x | (x >> 4)) & 0x100F00F00F00F00Full;
+  x = (x | (x >> 8)) & 0x1F0000FF0000FFull;
+  x = (x | (x >> 16)) & 0x1F00000000FFFFull;
+  x = (x | (x >> 32)) & 0x1FFFFFull;
+  return (uint32_t)x;
+}
+// Morton code with x as the most significant bit of each triple (child index = x<<2 | y<<1 | z, [PCL] OctreeKey)
+__device__ __forceinline__ uint64_t morton_xyz(uint32_t kx, uint32_t ky, uint32_t kz) {
+  return (spread3(kx) << 2) | (spread3(ky) << 1) | spread3(kz);
+}
+
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint64_t t = __shfl_up_sync(FULL_MASK, v, o); if (lane_id() >= (uint32_t)o) v += t; }
+  return v;
+}
+
+// Block-wide exclusive scan of one u64 per thread (blockDim.x multiple of 32, <= 1024).
+// Returns the exclusive prefix; *total receives the block aggregate (valid in every thread).
+__device__ __forceinline__ uint64_t block_excl_scan_u64(uint64_t v, uint64_t *total, uint64_t *s_warp /* >= 33 */) {
+  uint32_t lane = lane_id(), w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint64_t inc = warp_incl_scan_u64(v);
+  if (lane == 31) s_warp[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint64_t x = lane < nw ? s_warp[lane] : 0;
+    uint64_t xi = warp_incl_scan_u64(x);
+    s_warp[lane] = xi - x;
+    if (lane == 31) s_warp[32] = xi;
+  }
+  __syncthreads();
+  uint64_t r = s_warp[w] + inc - v;
+  *total = s_warp[32];
+  __syncthreads();
+  return r;
+}
+
+// Decoupled look-back (single-pass chained scan).  status[tile]: bits 63:62 = 0 empty / 1 aggregate / 2 inclusive
+// prefix; low 62 bits = value.  Must be called by all 32 lanes of ONE warp of the block; returns the exclusive
+// prefix of `tile` in every lane.  Tiles must be handed out by an atomic ticket so predecessors are running.
+#define SCAN_FLAG_A (1ull << 62)
+#define SCAN_FLAG_P (2ull << 62)
+#define SCAN_VMASK ((1ull << 62) - 1)
+__device__ __forceinline__ uint64_t scan_lookback(uint64_t *status, uint32_t tile, uint64_t aggregate) {
+  uint32_t lane = lane_id();
+  if (tile == 0) {
+    if (lane == 0) { *(volatile uint64_t *)&status[0] = SCAN_FLAG_P | aggregate; }
+    return 0;
+  }
+  if (lane == 0) *(volatile uint64_t *)&status[tile] = SCAN_FLAG_A | aggregate;
+  uint64_t excl = 0;
+  int look = (int)tile - 1;
+  for (;;) {
+    int idx = look - (int)lane;
+    uint64_t s;
+    do {
+      s = idx >= 0 ? ld_volatile_u64(&status[idx]) : SCAN_FLAG_P;
+    } while (__any_sync(FULL_MASK, (s >> 62) == 0));
+    uint32_t pm = __ballot_sync(FULL_MASK, (s >> 62) == 2);
+    if (pm) {
+      uint32_t first = __ffs(pm) - 1;
+      excl += warp_sum_u64(lane <= first ? (s & SCAN_VMASK) : 0);
+      break;
+    }
+    excl += warp_sum_u64(s & SCAN_VMASK);
+    look -= 32;
+  }
+  if (lane == 0) *(volatile uint64_t *)&status[tile] = SCAN_FLAG_P | (excl + aggregate);
+  return excl;
+}
+
+// Granlund-Montgomery division of a 32-bit value by an invariant d (2 <= d < 2^31): q = n / d exactly.
+struct FastDiv { uint32_t m, sh; };
+__host__ __device__ inline FastDiv fastdiv_make(uint32_t d) {
+  uint32_t l = 0; while ((1ull << l) < d) l++;
+  FastDiv f; f.m = (uint32_t)((((1ull << 32) * ((1ull << l) - d)) / d) + 1); f.sh = l - 1; return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, FastDiv f) {
+  uint32_t t = __umulhi(f.m, n);
+  return (t + ((n - t) >> 1)) >> f.sh;
+}

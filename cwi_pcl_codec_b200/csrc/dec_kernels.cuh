@@ -1,0 +1,405 @@
+// dec_kernels.cuh -- decode side: header parse + range decode (serial, one warp per frame), DFS walk of the
+// occupancy bytes ([PCL] Octree2BufBase::deserializeTree, impl.hpp:278), JPEG Huffman decode + IDCT + fancy
+// upsampling + colour ([libjpeg] defaults, jpeg_io.hpp:140-162), inverse snake (snake.h:123-137) and point
+// materialisation (deserializeTreeCallback impl.hpp:1584-1653, [PCL] ColorCoding::decodePoints).
+#pragma once
+#include "common.cuh"
+#include "entropy_kernels.cuh"
+#include "jpeg_enc_kernels.cuh"
+
+__device__ __forceinline__ double ld_f64_unaligned(const uint8_t *p) { uint64_t v = 0; for (int k = 7; k >= 0; k--) v = (v << 8) | p[k]; return __longlong_as_double((long long)v); }
+__device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t *p) { uint64_t v = 0; for (int k = 7; k >= 0; k--) v = (v << 8) | p[k]; return v; }
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+// ---- stage 1: header + entropy decoding of the layers (impl.hpp:231-261, 1766-1835). grid (frames), 32 threads
+__global__ void __launch_bounds__(32) dec_entropy_kernel(DecFrame *frames) {
+  DecFrame &f = frames[blockIdx.x];
+  __shared__ uint32_t freq[257];
+  const uint32_t lane = lane_id();
+  const uint8_t *in = f.in;
+  const uint64_t len = f.in_len;
+  uint32_t err = 0;
+  // syncToHeader: the reference scans for the magic (impl.hpp:1660-1676); we require it at offset 0 or scan forward
+  uint64_t pos = 0;
+  {
+    const char id2[] = "<PCL-OCT-CODECV2-COMPRESSED>", id1[] = "<PCL-OCT-COMPRESSED>";
+    uint32_t hp = 0; bool ok = true;
+    while (hp < 28) {
+      if (pos >= len) { ok = false; break; }
+      uint8_t c = in[pos++];
+      if (c == 0xFF) { ok = false; break; }               // (char)0xFF == EOF quirk, SURVEY App. C-9
+      if (c != (uint8_t)id2[hp++]) hp = ((uint8_t)id2[0] == c) ? 1 : 0;
+    }
+    hp = 0;
+    while (ok && hp < 20) {
+      if (pos >= len) { ok = false; break; }
+      uint8_t c = in[pos++];
+      if (c != (uint8_t)id1[hp++]) hp = ((uint8_t)id1[0] == c) ? 1 : 0;
+    }
+    if (!ok || pos + 92 + 8 > len) err = FERR_BAD_STREAM;
+  }
+  if (err) { if (lane == 0) { f.error |= err; f.V = 0; f.B = 0; f.point_count = 0; } return; }
+  const uint8_t *h = in + pos;
+  const uint32_t frame_id = ld_u32_unaligned(h);
+  const uint8_t data_with_color = h[6];
+  const uint64_t point_count = ld_u64_unaligned(h + 7);
+  const double res = ld_f64_unaligned(h + 15);
+  const uint8_t color_bits = h[23];
+  double bmin[3], bmax[3];
+  for (int a = 0; a < 3; a++) { bmin[a] = ld_f64_unaligned(h + 32 + 8 * a); bmax[a] = ld_f64_unaligned(h + 56 + 8 * a); }
+  const uint8_t do_centroid = h[80];
+  const uint32_t cct = ld_u32_unaligned(h + 83);
+  pos += 92;
+  // [PCL] readFrameHeader -> defineBoundingBox -> getKeyBitSize
+  const double eps = 1.1920928955078125e-07;
+  uint32_t mk = 2;
+  for (int a = 0; a < 3; a++) {
+    double t = ceil(__ddiv_rn(__dsub_rn(__dsub_rn(bmax[a], bmin[a]), eps), res));
+    uint32_t k = (t >= 4294967295.0 || !(t == t)) ? 0xFFFFFFFFu : (t > 0 ? (uint32_t)t : 0u);
+    if (k > mk) mk = k;
+  }
+  uint32_t depth = 0; while ((1ull << depth) < mk) depth++;
+  if (depth > CCV2_MAX_DEPTH || !(res > 0)) err = FERR_DEPTH;
+  if (point_count > f.out_cap) err |= FERR_OUT_CAP;
+  const uint64_t B = ld_u64_unaligned(in + pos); pos += 8;
+  if (B > f.tree_cap) err |= FERR_TREE_CAP;
+  if (lane == 0) {
+    f.frame_id = frame_id; f.data_with_color = data_with_color; f.point_count = point_count; f.res = res; f.color_bits = color_bits;
+    for (int a = 0; a < 3; a++) { f.bmin[a] = bmin[a]; f.bmax[a] = bmax[a]; }
+    f.do_centroid = do_centroid; f.cct = cct; f.depth = depth;
+  }
+  if (err) { if (lane == 0) { f.error |= err; f.V = 0; f.B = 0; } return; }
+  ByteFeed feed; feed.init(in, len, pos);
+  uint64_t coded[3] = { 0, 0, 0 };
+  bool ok = rc_decode_layer(feed, f.tree, (uint32_t)B, freq, &coded[0]);
+  uint32_t ncen = 0, ncol = 0;
+  if (ok && do_centroid) {
+    if (feed.pos + 4 > len) ok = false;
+    else {
+      ncen = ld_u32_unaligned(in + feed.pos); feed.pos += 4; feed.wbase = ~0ull;
+      if (ncen > f.cen_cap) { ok = false; err |= FERR_TREE_CAP; }
+      else ok = rc_decode_layer(feed, f.cen, ncen, freq, &coded[1]);
+    }
+  }
+  if (ok && data_with_color) {
+    if (feed.pos + 8 > len) ok = false;
+    else {
+      uint64_t nc = ld_u64_unaligned(in + feed.pos); feed.pos += 8; feed.wbase = ~0ull;
+      if (nc > f.col_cap) { ok = false; err |= FERR_JPEG_CAP; }
+      else { ncol = (uint32_t)nc; ok = rc_decode_layer(feed, f.col, ncol, freq, &coded[2]); }
+    }
+  }
+  // trailing bytes would switch the reference into detail mode (impl.hpp:1802-1806): outside the implemented scope
+  if (ok && feed.pos != len) { ok = false; err |= FERR_UNSUPPORTED; }
+  if (lane == 0) {
+    if (!ok) { f.error |= err ? err : FERR_BAD_STREAM; f.B = 0; f.V = 0; }
+    else { f.B = (uint32_t)B; f.ncen = ncen; f.ncol = ncol; f.coded[0] = coded[0]; f.coded[1] = coded[1]; f.coded[2] = coded[2]; }
+  }
+}
+
+// ---- stage 2a: DFS walk of the occupancy bytes. Emits one (prefix, byte) record per bottom-level branch
+// (level depth-1); leaves are expanded in parallel afterwards.  Serial by nature (a node's position is known
+// only after its left siblings' subtrees are consumed).  One thread; 16-byte loads.
+struct SeqBytes {
+  const uint8_t *p; uint32_t n, pos; uint4 cur; uint32_t cbase;
+  __device__ __forceinline__ void init(const uint8_t *ptr, uint32_t len) { p = ptr; n = len; pos = 0; cbase = NONE_U32; }
+  __device__ __forceinline__ uint32_t next() {
+    uint32_t b = pos & ~15u;
+    if (b != cbase) { cur = *(const uint4 *)(p + b); cbase = b; }
+    uint32_t w = (pos & 8) ? ((pos & 4) ? cur.w : cur.z) : ((pos & 4) ? cur.y : cur.x);
+    uint32_t v = (w >> (8 * (pos & 3))) & 255;
+    pos++;
+    return v;
+  }
+};
+__device__ inline void dfs_walk(DecFrame &f) {
+  const uint32_t B = f.B, d = f.depth;
+  if (B == 0 || d == 0) { f.n_bottom = 0; return; }
+  SeqBytes sb; sb.init(f.tree, B);
+  uint32_t nb = 0; const uint32_t cap = f.node_cap;
+  uint64_t m0 = 0, m1 = 0, m2 = 0;                       // child masks of the open branches, 8 bits per level
+  auto getm = [&](uint32_t l) -> uint32_t { uint64_t w = l < 8 ? m0 : (l < 16 ? m1 : m2); return (uint32_t)(w >> (8 * (l & 7))) & 255u; };
+  auto setm = [&](uint32_t l, uint32_t v) { uint64_t sh = 8 * (l & 7), msk = ~(255ull << sh), nv = (uint64_t)v << sh;
+    if (l < 8) m0 = (m0 & msk) | nv; else if (l < 16) m1 = (m1 & msk) | nv; else m2 = (m2 & msk) | nv; };
+  bool bad = false;
+  if (d == 1) {
+    if (nb < cap) { f.node_prefix[0] = 0; f.node_byte[0] = (uint8_t)sb.next(); nb = 1; }
+  } else {
+    uint32_t level = 0; uint64_t prefix = 0;
+    setm(0, sb.next());
+    for (;;) {
+      uint32_t m = getm(level);
+      if (m == 0) { if (level == 0) break; level--; prefix >>= 3; continue; }
+      uint32_t c = __ffs(m) - 1;
+      setm(level, m & (m - 1));
+      if (sb.pos >= B) { bad = true; break; }
+      uint32_t byte = sb.next();
+      uint64_t child = (prefix << 3) | c;
+      if (level + 2 < d) { level++; prefix = child; setm(level, byte); }
+      else {                                             // child is a bottom-level branch: record it, do not descend
+        if (nb >= cap) { bad = true; break; }
+        f.node_prefix[nb] = child; f.node_byte[nb] = (uint8_t)byte; nb++;
+      }
+    }
+  }
+  if (sb.pos != B) bad = true;                            // [PCL] would simply stop; a well-formed frame consumes every byte
+  if (bad) { f.error |= FERR_BAD_STREAM; nb = 0; }
+  f.n_bottom = nb;
+}
+
+// ---- stage 2b: JPEG marker parse + Huffman decode of the single SNAKE image (serial; no restart markers)
+struct HuffDec { int mincode[17]; int maxcode[17]; int valptr[17]; uint8_t vals[256]; uint16_t look[512]; };   // look: (len << 8) | sym for codes <= 9 bits
+struct JBits {
+  const uint8_t *p; uint32_t n, pos; uint64_t acc; int nb; bool marker;
+  __device__ __forceinline__ void fill() {
+    while (nb <= 48) {
+      uint32_t c = 0;
+      if (!marker && pos < n) {
+        c = p[pos];
+        if (c == 0xFF) { if (pos + 1 < n && p[pos + 1] == 0) pos += 2; else { marker = true; c = 0; } }
+        else pos++;
+      }
+      acc = (acc << 8) | c; nb += 8;
+    }
+  }
+  __device__ __forceinline__ uint32_t peek(int k) { return (uint32_t)(acc >> (nb - k)) & ((1u << k) - 1); }
+  __device__ __forceinline__ void skip(int k) { nb -= k; }
+};
+__device__ inline int huff_sym(JBits &b, const HuffDec &h) {
+  b.fill();
+  uint32_t e = h.look[b.peek(9)];
+  if (e) { b.skip(e >> 8); return e & 255; }
+  for (int l = 10; l <= 16; l++) {
+    int code = (int)b.peek(l);
+    if (code <= h.maxcode[l]) { b.skip(l); return h.vals[(h.valptr[l] + code - h.mincode[l]) & 255]; }
+  }
+  b.skip(16);
+  return 0;
+}
+__device__ inline void huff_build(HuffDec &h, const uint8_t *bits, const uint8_t *vals, int nvals) {
+  for (int k = 0; k < 256; k++) h.vals[k] = k < nvals ? vals[k] : 0;
+  for (int k = 0; k < 512; k++) h.look[k] = 0;
+  int code = 0, k = 0;
+  for (int l = 1; l <= 16; l++) {
+    int cnt = bits[l - 1];
+    h.mincode[l] = code; h.valptr[l] = k;
+    h.maxcode[l] = cnt ? code + cnt - 1 : -1;
+    if (l <= 9) for (int c = 0; c < cnt; c++) {
+      int cc = code + c;
+      for (int fv = 0; fv < (1 << (9 - l)); fv++) h.look[((cc << (9 - l)) | fv) & 511] = (uint16_t)((l << 8) | vals[k + c]);
+    }
+    code += cnt; k += cnt; code <<= 1;
+  }
+}
+__device__ __forceinline__ int jextend(int v, int n) { return n == 0 ? 0 : (v < (1 << (n - 1)) ? v - (1 << n) + 1 : v); }
+
+__device__ inline void jpeg_huff_decode(DecFrame &f, HuffDec *hd /* smem[4]: dc0 dc1 ac0 ac1 */) {
+  const uint8_t *in = f.col; const uint32_t len = f.ncol;
+  bool bad = false;
+  uint32_t w = 0, h = 0, scan = 0;
+  uint32_t have = 0;
+  if (len < 4 || in[0] != 0xFF || in[1] != 0xD8) bad = true;
+  uint32_t pos = 2;
+  while (!bad && pos + 4 <= len) {
+    if (in[pos] != 0xFF) { bad = true; break; }
+    uint32_t m = in[pos + 1], L = ((uint32_t)in[pos + 2] << 8) | in[pos + 3];
+    const uint8_t *s = in + pos + 4;
+    if (L < 2 || pos + 2 + L > len) { bad = true; break; }
+    if (m == 0xDB) {
+      uint32_t o = 0;
+      while (o + 65 <= L - 2) { uint32_t t = s[o] & 15; if ((s[o] >> 4) || t > 1) { bad = true; break; } for (int i = 0; i < 64; i++) f.qt[t * 64 + i] = s[o + 1 + i]; have |= 1u << t; o += 65; }   // zigzag order kept
+    } else if (m == 0xC0) {
+      h = ((uint32_t)s[1] << 8) | s[2]; w = ((uint32_t)s[3] << 8) | s[4];
+      if (s[0] != 8 || s[5] != 3 || s[7] != 0x22 || s[10] != 0x11 || s[13] != 0x11 || s[8] != 0 || s[11] != 1 || s[14] != 1) bad = true;
+    } else if (m == 0xC4) {
+      uint32_t o = 0;
+      while (o + 17 <= L - 2) {
+        uint32_t tc = s[o] >> 4, th = s[o] & 15, nv = 0;
+        if (tc > 1 || th > 1) { bad = true; break; }
+        for (int i = 0; i < 16; i++) nv += s[o + 1 + i];
+        if (nv > 256 || o + 17 + nv > L - 2) { bad = true; break; }
+        huff_build(hd[tc * 2 + th], s + o + 1, s + o + 17, (int)nv);
+        have |= 4u << (tc * 2 + th);
+        o += 17 + nv;
+      }
+    } else if (m == 0xDA) { scan = pos + 2 + L; break; }
+    else if (m == 0xC2 || m == 0xDD) { bad = true; break; }      // progressive / restart intervals: libjpeg as driven by jpeg_io never emits them
+    pos += 2 + L;
+  }
+  if (!scan || w != 256 || h == 0 || have != 0x3F) bad = true;  // SNAKE images are 256 wide (cjpeg.h:197)
+  const uint32_t mcu_w = (w + 15) / 16, mcu_h = (h + 15) / 16, nblocks = mcu_w * mcu_h * 6;
+  if (!bad && nblocks > f.coef_cap_blocks) { bad = true; f.error |= FERR_JPEG_CAP; }
+  if (bad) { f.error |= FERR_BAD_STREAM; f.img_w = f.img_h = f.mcu_w = f.mcu_h = f.n_blocks = 0; return; }
+  f.img_w = w; f.img_h = h; f.mcu_w = mcu_w; f.mcu_h = mcu_h; f.n_blocks = nblocks;
+  JBits br; br.p = in; br.n = len; br.pos = scan; br.acc = 0; br.nb = 0; br.marker = false;
+  int pred[3] = { 0, 0, 0 };
+  short *coef = f.coef;                                   // pre-zeroed; zigzag order, quantised
+  for (uint32_t g = 0; g < nblocks; g++) {
+    const uint32_t blk = g % 6; const int comp = blk < 4 ? 0 : (int)blk - 3; const int ts = comp ? 1 : 0;
+    short *c = coef + (size_t)g * 64;
+    int n = huff_sym(br, hd[ts]);
+    br.fill();
+    int diff = n ? jextend((int)br.peek(n), n) : 0; br.skip(n);
+    pred[comp] += diff; c[0] = (short)pred[comp];
+    for (int k = 1; k < 64; k++) {
+      int rs = huff_sym(br, hd[2 + ts]), r = rs >> 4, s = rs & 15;
+      if (s == 0) { if (r == 15) { k += 15; continue; } break; }
+      k += r;
+      br.fill();
+      int v = jextend((int)br.peek(s), s); br.skip(s);
+      if (k > 63) break;
+      c[k] = (short)v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32) dec_serial_kernel(DecFrame *frames) {
+  DecFrame &f = frames[blockIdx.y];
+  __shared__ HuffDec hd[4];
+  if (threadIdx.x != 0) return;
+  if (f.error) { if (blockIdx.x == 0) f.n_bottom = 0; else { f.n_blocks = 0; } return; }
+  if (blockIdx.x == 0) dfs_walk(f);
+  else if (f.data_with_color && f.cct == 1) jpeg_huff_decode(f, hd);
+}
+
+// ---- stage 3: dequantise + ISLOW IDCT. 8 threads per block, 32 blocks per CTA; writes Y / Cb / Cr planes
+__device__ __forceinline__ uint8_t jpeg_range_limit(int x) {
+  int v = x & 1023;
+  return v < 128 ? (uint8_t)(v + 128) : (v < 512 ? 255 : (v < 896 ? 0 : (uint8_t)(v - 896)));
+}
+__device__ __forceinline__ void idct8(const int *v, int *o, bool first) {
+  int z2 = v[2], z3 = v[6], z1 = (z2 + z3) * 4433;
+  int t2 = z1 - z3 * 15137, t3 = z1 + z2 * 6270;
+  int t0 = (v[0] + v[4]) * 8192, t1 = (v[0] - v[4]) * 8192;
+  int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+  int a0 = v[7], a1 = v[5], a2 = v[3], a3 = v[1];
+  z1 = a0 + a3; z2 = a1 + a2; z3 = a0 + a2; int z4 = a1 + a3, z5 = (z3 + z4) * 9633;
+  a0 *= 2446; a1 *= 16819; a2 *= 25172; a3 *= 12299;
+  z1 *= -7373; z2 *= -20995; z3 = z3 * (-16069) + z5; z4 = z4 * (-3196) + z5;
+  a0 += z1 + z3; a1 += z2 + z4; a2 += z2 + z3; a3 += z1 + z4;
+  const int n = first ? 11 : 18;
+  o[0] = JDESCALE(t10 + a3, n); o[1] = JDESCALE(t11 + a2, n); o[2] = JDESCALE(t12 + a1, n); o[3] = JDESCALE(t13 + a0, n);
+  o[4] = JDESCALE(t13 - a0, n); o[5] = JDESCALE(t12 - a1, n); o[6] = JDESCALE(t11 - a2, n); o[7] = JDESCALE(t10 - a3, n);
+}
+__device__ __forceinline__ void dec_plane_ptrs(const DecFrame &f, uint8_t *&Y, uint8_t *&Cb, uint8_t *&Cr, uint32_t &YW, uint32_t &CW) {
+  YW = f.mcu_w * 16; CW = f.mcu_w * 8;
+  const size_t ysz = (size_t)YW * f.mcu_h * 16, csz = (size_t)CW * f.mcu_h * 8;
+  Y = f.planes; Cb = f.planes + ysz; Cr = Cb + csz;
+}
+__global__ void __launch_bounds__(256) jpeg_idct_kernel(DecFrame *frames, const JpegTables *T) {
+  DecFrame &f = frames[blockIdx.y];
+  const uint32_t nblocks = f.n_blocks;
+  if (f.error || blockIdx.x * 32 >= nblocks) return;
+  __shared__ int ws[32][64];
+  __shared__ uint8_t zz[64];
+  if (threadIdx.x < 64) zz[threadIdx.x] = T->zz[threadIdx.x];
+  __syncthreads();
+  const uint32_t lb = threadIdx.x >> 3, k = threadIdx.x & 7, g = blockIdx.x * 32 + lb;
+  const bool act = g < nblocks;
+  const uint32_t blk = g % 6, mcu = g / 6;
+  if (act) {
+    const short *c = f.coef + (size_t)g * 64;
+    const uint16_t *q = f.qt + (blk >= 4 ? 64 : 0);
+    // natural-order position (row r, col k) <- zigzag index: build inverse on the fly
+    int v[8], o[8];
+    // gather column k: natural index r*8 + k; find zigzag position by scanning the small table
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = 0;
+    for (int z = 0; z < 64; z++) { uint32_t nat = zz[z]; if ((nat & 7) == k) v[nat >> 3] = (int)c[z] * (int)q[z]; }
+    idct8(v, o, true);
+#pragma unroll
+    for (int r = 0; r < 8; r++) ws[lb][r * 8 + k] = o[r];
+  }
+  __syncthreads();
+  if (act) {
+    int v[8], o[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) v[c] = ws[lb][k * 8 + c];
+    idct8(v, o, false);
+    uint8_t *Y, *Cb, *Cr; uint32_t YW, CW;
+    dec_plane_ptrs(f, Y, Cb, Cr, YW, CW);
+    const uint32_t mx = mcu % f.mcu_w, my = mcu / f.mcu_w;
+    uint8_t *dst;
+    if (blk < 4) dst = Y + (size_t)(my * 16 + (blk >> 1) * 8 + k) * YW + mx * 16 + (blk & 1) * 8;
+    else dst = (blk == 4 ? Cb : Cr) + (size_t)(my * 8 + k) * CW + mx * 8;
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) { lo |= (uint32_t)jpeg_range_limit(o[c]) << (8 * c); hi |= (uint32_t)jpeg_range_limit(o[4 + c]) << (8 * c); }
+    *(uint2 *)dst = make_uint2(lo, hi);
+  }
+}
+
+// ---- stage 4: expand bottom-level branches into leaves (chained scan of popcounts) and write the points
+#define NODE_THREADS 256
+__device__ __forceinline__ uint32_t dec_color(const DecFrame &f, uint32_t i) {
+  if (!f.data_with_color) return 0x00FFFFFFu;                 // [PCL] setDefaultColor (white, alpha 0)
+  if (f.cct != 1) {
+    if (3ull * i + 2 >= f.ncol) return 0;
+    const uint32_t red = f.cct == 0 ? 8 - f.color_bits : 0;
+    const uint8_t *c = f.col + 3ull * i;
+    return (((uint32_t)c[0] << red) & 255) | ((((uint32_t)c[1] << red) & 255) << 8) | ((((uint32_t)c[2] << red) & 255) << 16);
+  }
+  const uint32_t w = f.img_w, h = f.img_h;
+  if (i >= w * h) return 0;
+  const uint32_t off = snake_forward_256(i, h), x = off & 255, y = off >> 8;
+  uint8_t *Y, *Cb, *Cr; uint32_t YW, CW;
+  dec_plane_ptrs(f, Y, Cb, Cr, YW, CW);
+  const uint32_t cw = (w + 1) >> 1, ch = (h + 1) >> 1, cx = x >> 1, cy = y >> 1;
+  const uint32_t oy = (y & 1) ? min(cy + 1, ch - 1) : (cy > 0 ? cy - 1 : 0);
+  int cc[2];
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const uint8_t *P = c ? Cr : Cb;
+    int cs = 3 * P[(size_t)cy * CW + cx] + P[(size_t)oy * CW + cx], o;
+    if (!(x & 1)) { if (cx == 0) o = (4 * cs + 8) >> 4; else { int l = 3 * P[(size_t)cy * CW + cx - 1] + P[(size_t)oy * CW + cx - 1]; o = (3 * cs + l + 8) >> 4; } }
+    else { if (cx == cw - 1) o = (4 * cs + 7) >> 4; else { int r = 3 * P[(size_t)cy * CW + cx + 1] + P[(size_t)oy * CW + cx + 1]; o = (3 * cs + r + 7) >> 4; } }
+    cc[c] = o - 128;
+  }
+  const int yy = Y[(size_t)y * YW + x];
+  int R = yy + ((91881 * cc[1] + 32768) >> 16), B = yy + ((116130 * cc[0] + 32768) >> 16), G = yy + ((-22554 * cc[0] - 46802 * cc[1] + 32768) >> 16);
+  R = min(255, max(0, R)); G = min(255, max(0, G)); B = min(255, max(0, B));
+  return (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
+}
+
+__global__ void __launch_bounds__(NODE_THREADS) dec_points_kernel(DecFrame *frames) {
+  DecFrame &f = frames[blockIdx.y];
+  const uint32_t nb = f.n_bottom;
+  const uint32_t ntiles = (nb + NODE_THREADS - 1) / NODE_THREADS;
+  if (f.error || blockIdx.x >= ntiles) return;
+  __shared__ uint32_t s_tile; __shared__ uint64_t s_scan[33]; __shared__ uint64_t s_excl;
+  if (threadIdx.x == 0) s_tile = atomicAdd(&f.ticket[TK_NODES], 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile, g = tile * NODE_THREADS + threadIdx.x;
+  uint32_t byte = 0; uint64_t prefix = 0;
+  if (g < nb) { byte = f.node_byte[g]; prefix = f.node_prefix[g]; }
+  const uint32_t cnt = __popc(byte);
+  uint64_t tot;
+  uint64_t excl = block_excl_scan_u64(cnt, &tot, s_scan);
+  if (threadIdx.x < 32) { uint64_t e = scan_lookback(f.scan_status, tile, tot); if (threadIdx.x == 0) s_excl = e; }
+  __syncthreads();
+  excl += s_excl;
+  if (g >= nb) return;
+  if (g == nb - 1) { uint64_t V = excl + cnt; f.V = (uint32_t)V; if (V != f.point_count || V > f.out_cap) atomicOr(&f.error, FERR_BAD_STREAM); }
+  const double res = f.res;
+  uint32_t i = (uint32_t)excl;
+  while (byte) {
+    const uint32_t c = __ffs(byte) - 1; byte &= byte - 1;
+    if (i >= f.out_cap) break;
+    const uint64_t key = (prefix << 3) | c;
+    const uint32_t k3[3] = { compact3(key >> 2), compact3(key >> 1), compact3(key) };
+    float xyz[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      if (f.do_centroid) {                                  // pcv2.h:103-118
+        double corner = __dadd_rn(__dmul_rn((double)k3[a], res), f.bmin[a]);
+        uint32_t q = (3ull * i + a) < f.ncen ? f.cen[3ull * i + a] : 0;
+        xyz[a] = (float)__dadd_rn(corner, (double)__fmul_rn((float)q, 0.001f));
+      } else xyz[a] = (float)__dadd_rn(__dmul_rn(__dadd_rn((double)k3[a], 0.5), res), f.bmin[a]);   // impl.hpp:1630-1632
+    }
+    const uint32_t rgba = dec_color(f, i);
+    uint4 *o = (uint4 *)(f.out_pts + 32ull * i);
+    o[0] = make_uint4(__float_as_uint(xyz[0]), __float_as_uint(xyz[1]), __float_as_uint(xyz[2]), 0x3F800000u);
+    o[1] = make_uint4(rgba, 0, 0, 0);
+    i++;
+  }
+}

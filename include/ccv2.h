@@ -1,0 +1,125 @@
+/*
+ * ccv2.h -- C ABI of the B200-native cloud_codec_v2 intra encode/decode hot path (libccv2.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry point names the
+ * reference interface it replaces (paths relative to the cwi-dis/cwi-pcl-codec tree):
+ *   codec.h  = cloud_codec_v2/include/pcl/cloud_codec_v2/point_cloud_codec_v2.h
+ *   impl.hpp = cloud_codec_v2/include/pcl/cloud_codec_v2/impl/point_cloud_codec_v2_impl.hpp
+ *   eval.hpp = apps/evaluate_compression/include/pcl/apps/evaluate_compression/impl/evaluate_compression_impl.hpp
+ *
+ * Points are PCL's 32-byte PointXYZRGB records: x,y,z float32 at 0/4/8, data[3] at 12, b,g,r,a uint8 at
+ * 16..19, padding to 32 (the struct the reference instantiates, cloud_codec_v2/src/point_cloud_codec_v2.cpp:45).
+ * Every data pointer may be host (pageable or pinned) or device memory of the codec's device; the library
+ * detects which.  All functions return 0 on success or a negative ccv2_status.  No exceptions cross the ABI.
+ * A codec handle owns its CUDA streams and workspaces and is not thread-safe (like the reference object).
+ * There is no CPU fallback: without a CUDA device ccv2_create fails with CCV2_ERR_CUDA.
+ */
+#ifndef CCV2_H
+#define CCV2_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ccv2_status {
+  CCV2_OK = 0,
+  CCV2_ERR_ARG = -1,          /* bad argument */
+  CCV2_ERR_CUDA = -2,         /* CUDA runtime error / no device (see ccv2_last_error) */
+  CCV2_ERR_UNSUPPORTED = -3,  /* configuration outside the implemented scope (detail mode, profiles != MANUAL) */
+  CCV2_ERR_CAPACITY = -4,     /* caller's output buffer too small */
+  CCV2_ERR_WORKSPACE = -5,    /* internal workspace bound exceeded (tree bytes / stream arena) */
+  CCV2_ERR_STREAM = -6,       /* malformed compressed stream */
+  CCV2_ERR_DEPTH = -7         /* realised octree depth > 21 (Morton code does not fit 63 bits) */
+} ccv2_status;
+
+/* The constructor surface of OctreePointCloudCodecV2 (codec.h:108-143), argument for argument, plus the two
+ * setters evaluate_compression calls right after construction (eval.hpp:415-417). */
+typedef struct ccv2_params {
+  int32_t profile;                 /* compression_Profiles_e; only MANUAL_CONFIGURATION (= 12) is implemented */
+  int32_t show_statistics;         /* showStatistics_arg (accepted, ignored: PCL_INFO printing is not reproduced) */
+  double point_resolution;         /* pointResolution_arg   (eval.hpp:381: 2^-(octree_bits+enh_bits)) */
+  double octree_resolution;        /* octreeResolution_arg  (eval.hpp:383: 2^-octree_bits) */
+  int32_t do_voxel_grid_downsampling; /* doVoxelGridDownDownSampling_arg (eval.hpp:385 passes true; only true is implemented) */
+  uint32_t i_frame_rate;           /* iFrameRate_arg (eval.hpp:386 passes 0: every frame is an I frame) */
+  int32_t do_color_encoding;       /* doColorEncoding_arg */
+  uint8_t color_bit_resolution;    /* colorBitResolution_arg */
+  uint8_t color_coding_type;       /* colorCodingType_arg: 0 PCL average, 1 JPEG snake, 2 JPEG lines, 3 raw grid */
+  uint8_t _pad0[2];
+  int32_t do_voxel_grid_centroid;  /* doVoxelGridCentroid_arg (keep_centroid) */
+  int32_t create_scalable_stream;  /* createScalableStream_arg (header only) */
+  int32_t code_connectivity;       /* codeConnectivity_arg (header only) */
+  int32_t jpeg_quality;            /* jpeg_quality_arg */
+  int32_t num_threads;             /* num_threads_arg (only used by the inter-frame predictor; ignored) */
+  int32_t macroblock_size;         /* setMacroblockSize (codec.h:149-152); header field, default 16 */
+  int32_t do_icp_color_offset;     /* setDoICPColorOffset (codec.h:164-167); header field, default 0 */
+} ccv2_params;
+
+#define CCV2_MANUAL_CONFIGURATION 12   /* pcl::io::MANUAL_CONFIGURATION */
+
+typedef struct ccv2_codec ccv2_codec;
+
+/* Fills the values evaluate_compression uses with parameter_config.txt (octree_bits 11, colour type 1, jpeg 85). */
+void ccv2_default_params(ccv2_params *p);
+
+/* Replaces: OctreePointCloudCodecV2 constructor (codec.h:108-143). device = CUDA ordinal. */
+int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out);
+/* Replaces: ~OctreePointCloudCodecV2 (codec.h:146). */
+void ccv2_destroy(ccv2_codec *c);
+
+/* Upper bound of the compressed size of a frame of npts points (for sizing `out` buffers). */
+size_t ccv2_max_compressed_size(size_t npts);
+
+/* Replaces: encodePointCloud(const PointCloudConstPtr&, std::ostream&) (codec.h:174-175, impl.hpp:80-213) for
+ * `nframes` independent frames in one call (the throughput path; nframes = 1 is the reference's call).
+ * pts[i]: npts[i] x 32-byte records.  out[i]: buffer of out_cap[i] bytes; out_len[i] receives the stream
+ * length, 0 for an empty / all-non-finite cloud (the reference writes nothing, impl.hpp:206-212).
+ * Frame ids continue the codec's counter exactly as repeated encodePointCloud calls would (impl.hpp:133). */
+int ccv2_encode_batch(ccv2_codec *c, int nframes, const void *const *pts, const size_t *npts,
+                      void *const *out, const size_t *out_cap, size_t *out_len);
+
+/* Replaces: decodePointCloud(std::istream&, PointCloudPtr&) (codec.h:177-178, impl.hpp:224-310).
+ * in[i]: one compressed frame of in_len[i] bytes (one frame per stream, like the reference: impl.hpp:1802-1806).
+ * pts_out[i]: buffer for pts_cap[i] points (32 bytes each); npts_out[i] receives the decoded count. */
+int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const size_t *in_len,
+                      void *const *pts_out, const size_t *pts_cap, size_t *npts_out);
+
+/* Reads point_count from a frame header in HOST memory (SURVEY App. A offset 55) so a caller can size
+ * pts_out before decoding.  Replaces nothing in the reference (its decoder grows a std::vector). */
+int ccv2_peek_point_count(const void *in_host, size_t len, uint64_t *npts);
+
+/* Replaces: getPerformanceMetrics() (codec.h:193-197): coded bytes of {octree, centroid, colour} layers of
+ * the LAST frame encoded or decoded (impl.hpp:1697,1710,1723). */
+int ccv2_get_metrics(ccv2_codec *c, uint64_t m[3]);
+
+/* frame_ID_ accessors (state that reaches the bitstream, impl.hpp:133). */
+int ccv2_set_frame_id(ccv2_codec *c, uint32_t next_minus_one);
+uint32_t ccv2_get_frame_id(const ccv2_codec *c);
+
+/* Number of kernel launches issued by the last encode/decode batch call (bench.py's gpu_launches). */
+uint64_t ccv2_last_launch_count(const ccv2_codec *c);
+/* Device time of the last batch call's kernel region (CUDA events on the codec's stream), milliseconds. */
+float ccv2_last_device_ms(const ccv2_codec *c);
+
+/* Text of the last error on this codec (or of ccv2_create when c == NULL). */
+const char *ccv2_last_error(const ccv2_codec *c);
+const char *ccv2_status_string(int status);
+
+/* Pinned host memory helpers (cudaMallocHost / cudaFreeHost) for callers that want full-speed PCIe copies. */
+void *ccv2_host_alloc(size_t bytes);
+void ccv2_host_free(void *p);
+
+/* Test hook: copies an intermediate of frame `frame` of the last encode batch to host.
+ * what: 0 leaf Morton codes (u64 x V), 1 tree bytes (B), 2 average colours (3V), 3 colour payload (J),
+ *       4 sorted point indices (u32 x n_finite), 5 frame info (ccv2_frame_info). */
+typedef struct ccv2_frame_info {
+  uint32_t depth, n_finite, n_leaves, n_tree_bytes, n_color_bytes, error;
+  double bb_min[3], bb_max[3];
+  uint64_t coded[3];
+} ccv2_frame_info;
+int ccv2_debug_fetch(ccv2_codec *c, int frame, int what, void *host_buf, size_t cap, size_t *len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
