@@ -1,0 +1,301 @@
+"""bench.py -- Mpoints/s encode+decode @ depth-11 intra on synthetic 1M-point XYZRGB frames (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithm (the oracle port, all host cores)
+
+A "step" is one pass of the hot path over one batch of F frames: ccv2_encode_batch over the F clouds followed by
+ccv2_decode_batch over the F streams it produced.  `value` is measured with the clouds already resident in HBM
+(device pointers in, device pointers out); `e2e` is the same step through the same C-ABI calls with pinned HOST
+buffers, so the host->device copy of every cloud / stream and the device->host copy of every stream / decoded
+cloud are inside the timed region.  For N > 1 the frames are sharded over the ranks (no data-path collective:
+intra frames are independent); timing is bracketed by barrier + synchronize and reduced with MAX.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpoints/s encode+decode @ depth-11 intra; bitstream bit-exact vs ref"
+
+
+def shard_frames(n_frames_per_rank, rank, world):
+    """Seeds of the frames rank `rank` owns (weak scaling: every rank processes n_frames_per_rank distinct frames)."""
+    return [rank * n_frames_per_rank + i for i in range(n_frames_per_rank)]
+
+
+def reduce_max(value, dist=None, device=None):
+    """MAX over ranks of a python float (torch.distributed all_reduce when initialised)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gen_frames(kind, n, seeds):
+    from concurrent.futures import ThreadPoolExecutor
+    from cwi_pcl_codec_b200 import synth
+    gen = synth.gen_surface if kind == "surf" else synth.gen_uniform
+    with ThreadPoolExecutor(max_workers=min(len(seeds), os.cpu_count() or 1)) as ex:
+        return list(ex.map(lambda s: gen(n, s), seeds))
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_run(frames, bits, threads):
+    """encode+decode every frame with the oracle on `threads` host threads; returns (seconds, total points)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    p = O.default_params(octree_bits=bits)
+
+    def one(f):
+        data, _ = O.encode(f, p, frame_id=1)
+        O.decode(data)
+        return f.shape[0]
+    t = time.perf_counter()
+    if threads <= 1:
+        pts = sum(one(f) for f in frames)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            pts = sum(ex.map(one, frames))
+    return time.perf_counter() - t, pts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    per_step = max(2, min(2 * cores, 64))
+    frames = gen_frames(args.kind, args.points, list(range(min(per_step, 16))))
+    frames = [frames[i % len(frames)] for i in range(per_step)]
+    for _ in range(args.warmup):
+        cpu_oracle_run(frames[:cores], args.bits, cores)
+    tot_t, tot_p = 0.0, 0
+    for _ in range(args.steps):
+        t, p = cpu_oracle_run(frames, args.bits, cores)
+        tot_t += t; tot_p += p
+    v = tot_p / tot_t / 1e6
+    sample = "%d frames of %d points per step, oracle port (restated reference algorithm, gcc -O3), %d host threads" % (per_step, args.points, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mpoints/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/f64 (integer codec, FP64 keys)",
+            "data": "synthetic", "config": workload_config(args, per_step),
+            "cpu_baseline": {"value": v, "unit": "Mpoints/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, frames):
+    return {"workload": "BASELINE.json configs[1]: %d-point synthetic XYZRGB frames (G-%s, SURVEY 8d), intra, octree_bits %d (realised depth 12-13), colour JPEG snake Q85"
+            % (args.points, args.kind, args.bits), "frames_per_step_per_gpu": frames, "points_per_frame": args.points,
+            "cache": "inputs (%.0f MB per step per GPU) are larger than the 126 MB L2; no flush needed" % (frames * args.points * 32 / 1e6)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--frames", type=int, default=int(os.environ.get("BENCH_FRAMES", "64")), help="frames per step per GPU")
+    ap.add_argument("--points", type=int, default=1000000)
+    ap.add_argument("--bits", type=int, default=11)
+    ap.add_argument("--kind", default="surf", choices=["surf", "unif"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from cwi_pcl_codec_b200 import codec as K
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    F, NP = args.frames, args.points
+    frames = gen_frames(args.kind, NP, shard_frames(F, rank, world))
+    codec = K.Codec(K.default_params(octree_bits=args.bits), device=local)
+    lib = K.load_library()
+
+    # ---- device-resident buffers (value) ----
+    d_in = [torch.from_numpy(f.view(np.uint8).reshape(-1)).to(dev) for f in frames]
+    cap = 4 * NP + (1 << 16)
+    d_str = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(F)]
+    d_out = [torch.empty(NP * 32, dtype=torch.uint8, device=dev) for _ in range(F)]
+    in_ptrs = [t.data_ptr() for t in d_in]; str_ptrs = [t.data_ptr() for t in d_str]; out_ptrs = [t.data_ptr() for t in d_out]
+
+    def step_device():
+        lens = codec.encode_batch_raw(in_ptrs, [NP] * F, str_ptrs, [cap] * F)
+        ms, launches = codec.last_device_ms, codec.last_launch_count
+        ns = codec.decode_batch_raw(str_ptrs, lens, out_ptrs, [NP] * F)
+        return ms + codec.last_device_ms, launches + codec.last_launch_count, lens, ns
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        _, _, lens, ns = step_device()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        ms, l, lens, ns = step_device()
+        dev_ms += ms; launches += l
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    # device time: CUDA events recorded by the library on its own streams around each call's GPU work (max over ranks)
+    t_dev = reduce_max(dev_ms / 1e3, dist if world > 1 else None, dev)
+    t_wall = reduce_max(wall, dist if world > 1 else None, dev)
+    value = world * F * NP * args.steps / t_dev / 1e6
+
+    # ---- bit-exactness spot check against the oracle (outside the timed region, rank 0, first frame) ----
+    bit_exact = None
+    if rank == 0:
+        from oracle import oracle as O
+        ref, info = O.encode(frames[0], O.default_params(octree_bits=args.bits), frame_id=1)
+        got = d_str[0][:lens[0]].cpu().numpy().tobytes()
+        bit_exact = (got[:48] == ref[:48] and got[52:] == ref[52:])          # frame_ID (bytes 48..51) advances with every step
+        rdec, _ = O.decode(ref)
+        bit_exact = bool(bit_exact and np.array_equal(d_out[0][:ns[0] * 32].cpu().numpy().reshape(-1, 32), rdec))
+    S = float(np.mean(lens)); V = float(np.mean(ns))
+    alg_bytes_frame = 32 * NP + 32 * V + 2 * S                                # encode+decode, per frame
+
+    # ---- e2e: same calls with pinned host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        h_in = [K.PinnedBuffer(NP * 32) for _ in range(F)]
+        for hb, f in zip(h_in, frames):
+            hb.array[:] = f.view(np.uint8).reshape(-1)
+        h_str = [K.PinnedBuffer(cap) for _ in range(F)]
+        h_out = [K.PinnedBuffer(NP * 32) for _ in range(F)]
+        hi = [b.ptr for b in h_in]; hs = [b.ptr for b in h_str]; ho = [b.ptr for b in h_out]
+
+        def step_host():
+            l2 = codec.encode_batch_raw(hi, [NP] * F, hs, [cap] * F)
+            n2 = codec.decode_batch_raw(hs, l2, ho, [NP] * F)
+            return l2, n2
+        for _ in range(2):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            l2, n2 = step_host()
+        barrier()
+        t_e2e = reduce_max(time.perf_counter() - t0, dist if world > 1 else None, dev)
+        e2e = {"value": world * F * NP * args.steps / t_e2e / 1e6, "unit": "Mpoints/s",
+               "h2d_bytes_per_step": int(F * NP * 32 + sum(l2)), "d2h_bytes_per_step": int(sum(l2) + 32 * sum(n2)),
+               "timing": "wall clock around the C-ABI calls (synchronous), max over ranks"}
+        for b in h_in + h_str + h_out:
+            b.close()
+
+    # ---- per-kernel profile (one extra, untimed, single-stream step over one group) -> roofline of the dominant kernel ----
+    roofline = None
+    if rank == 0 and hasattr(lib, "ccv2_set_profiling"):
+        roofline = profile_roofline(K, lib, args, frames, alg_bytes_frame)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        nb = min(F, 16)
+        t, p = cpu_oracle_run(frames[:nb], args.bits, 1)
+        cpu_baseline = {"value": p / t / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "port",
+                        "sample": "%d of the step's %d frames, encode+decode, oracle port single thread (the reference's intra path is single-threaded)" % (nb, F)}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t_dev / args.steps * 1e3, "wall_ms_per_step": t_wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8/u32/f64 (integer codec, FP64 keys)", "data": "synthetic",
+                "config": workload_config(args, F), "bit_exact_vs_oracle": bit_exact, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "stream_bytes_per_frame": S, "voxels_per_frame": V}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def profile_roofline(K, lib, args, frames, alg_bytes_frame):
+    """Runs one encode+decode of one group on a single stream with CUDA events around every kernel (inside the
+    library, on the launching stream) and reports the dominant kernel against the measured HBM peak."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    which = "measured (MEASURED_PEAKS.json, copy kernel)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    prof = K.profile_step(frames[:min(len(frames), 8)], args.bits)
+    if not prof:
+        return None
+    name, tot_ms, count, frames_per_launch = max(prof, key=lambda r: r[1])
+    avg_s = tot_ms / count / 1e3
+    achieved = alg_bytes_frame * frames_per_launch / avg_s / 1e9
+    total_ms = sum(r[1] for r in prof)
+    return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": which, "avg_launch_ms": avg_s * 1e3, "frames_per_launch": frames_per_launch,
+            "algorithmic_bytes_per_frame": alg_bytes_frame, "share_of_step": tot_ms / total_ms,
+            "kernels_ms": {r[0]: round(r[1], 4) for r in prof}}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -78,6 +78,8 @@ def load_library():
     L.ccv2_host_free.argtypes = [C.c_void_p]
     L.ccv2_host_free.restype = None
     L.ccv2_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, szp]
+    L.ccv2_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.ccv2_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -85,7 +87,8 @@ def load_library():
 EXPORTED_SYMBOLS = ["ccv2_default_params", "ccv2_create", "ccv2_destroy", "ccv2_max_compressed_size",
                     "ccv2_encode_batch", "ccv2_decode_batch", "ccv2_peek_point_count", "ccv2_get_metrics",
                     "ccv2_set_frame_id", "ccv2_get_frame_id", "ccv2_last_launch_count", "ccv2_last_device_ms",
-                    "ccv2_last_error", "ccv2_status_string", "ccv2_host_alloc", "ccv2_host_free", "ccv2_debug_fetch"]
+                    "ccv2_last_error", "ccv2_status_string", "ccv2_host_alloc", "ccv2_host_free", "ccv2_debug_fetch",
+                    "ccv2_set_profiling", "ccv2_get_profile"]
 
 
 def _status_string(s):
@@ -266,6 +269,19 @@ class Codec:
     def last_device_ms(self):
         return float(self._L.ccv2_last_device_ms(self._h))
 
+    def set_profiling(self, on):
+        self._check(self._L.ccv2_set_profiling(self._h, int(on)))
+
+    def profile(self):
+        """[(kernel name, total ms, launches)] of the last batch call made with profiling on."""
+        out, i = [], 0
+        while True:
+            name, ms, n = C.c_char_p(), C.c_float(), C.c_int()
+            if self._L.ccv2_get_profile(self._h, i, C.byref(name), C.byref(ms), C.byref(n)):
+                return out
+            out.append((name.value.decode(), float(ms.value), int(n.value)))
+            i += 1
+
     def debug_fetch(self, frame, what):
         """Test hook: 0 leaf codes (u64), 1 tree bytes, 2 avg colours, 3 colour payload, 4 sorted indices, 5 info."""
         ln = C.c_size_t()
@@ -330,3 +346,19 @@ class OctreePointCloudCodecV2:
 
     def getPerformanceMetrics(self):
         return self._codec.metrics()
+
+
+def profile_step(clouds, octree_bits=11, device=0):
+    """One encode+decode of `clouds` as a single group on one stream with CUDA events around every kernel.
+    Returns [(kernel, total_ms, launches, frames_per_launch)] (bench.py's roofline leg)."""
+    c = Codec(default_params(octree_bits=octree_bits), device)
+    try:
+        c.encode_batch(clouds)                      # warm-up (allocations)
+        c.set_profiling(True)
+        streams = c.encode_batch(clouds)
+        prof = c.profile()
+        c.decode_batch(streams)
+        prof += c.profile()
+        return [(n, ms, k, len(clouds)) for n, ms, k in prof]
+    finally:
+        c.close()

@@ -88,11 +88,42 @@ struct ccv2_codec {
   uint64_t launches = 0;
   float device_ms = 0.f;
   std::string err;
+  // profiling hook: events around every kernel launch (single stream)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_pool; size_t prof_used = 0;
+  struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  struct ProfSum { std::string name; float ms; int launches; };
+  std::vector<ProfSum> prof_sum;
 };
 
 namespace {
 
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e__); return CCV2_ERR_CUDA; } } while (0)
+
+cudaEvent_t prof_event(ccv2_codec *c) {
+  if (c->prof_used == c->prof_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); c->prof_pool.push_back(e); }
+  return c->prof_pool[c->prof_used++];
+}
+void prof_begin(ccv2_codec *c, cudaStream_t st, const char *name) {
+  if (!c->profiling) return;
+  ccv2_codec::ProfRec r; r.name = name; r.e0 = prof_event(c); r.e1 = prof_event(c);
+  cudaEventRecord(r.e0, st);
+  c->prof_recs.push_back(r);
+}
+void prof_end(ccv2_codec *c, cudaStream_t st) { if (c->profiling) cudaEventRecord(c->prof_recs.back().e1, st); }
+void prof_collect(ccv2_codec *c) {
+  if (!c->profiling) return;
+  c->prof_sum.clear();
+  for (auto &r : c->prof_recs) {
+    float ms = 0; cudaEventElapsedTime(&ms, r.e0, r.e1);
+    bool found = false;
+    for (auto &q : c->prof_sum) if (q.name == r.name) { q.ms += ms; q.launches++; found = true; break; }
+    if (!found) c->prof_sum.push_back({r.name, ms, 1});
+  }
+  c->prof_recs.clear(); c->prof_used = 0;
+}
+#define LAUNCH(name, ...) do { prof_begin(c, st, name); __VA_ARGS__; prof_end(c, st); launches++; } while (0)
 
 bool is_device_ptr(const void *p) {
   cudaPointerAttributes a;
@@ -305,6 +336,7 @@ void ccv2_destroy(ccv2_codec *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (auto ev : c->ev_group) cudaEventDestroy(ev);
+  for (auto ev : c->prof_pool) cudaEventDestroy(ev);
   if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -335,6 +367,15 @@ uint32_t ccv2_get_frame_id(const ccv2_codec *c) { return c ? c->frame_id : 0; }
 uint64_t ccv2_last_launch_count(const ccv2_codec *c) { return c ? c->launches : 0; }
 float ccv2_last_device_ms(const ccv2_codec *c) { return c ? c->device_ms : 0.f; }
 
+int ccv2_set_profiling(ccv2_codec *c, int on) { if (!c) return CCV2_ERR_ARG; c->profiling = on != 0; c->prof_sum.clear(); return CCV2_OK; }
+int ccv2_get_profile(const ccv2_codec *c, int idx, const char **name, float *total_ms, int *launches) {
+  if (!c || idx < 0 || idx >= (int)c->prof_sum.size()) return CCV2_ERR_ARG;
+  if (name) *name = c->prof_sum[idx].name.c_str();
+  if (total_ms) *total_ms = c->prof_sum[idx].ms;
+  if (launches) *launches = c->prof_sum[idx].launches;
+  return CCV2_OK;
+}
+
 int ccv2_peek_point_count(const void *in_host, size_t len, uint64_t *npts) {
   if (!in_host || !npts || len < FRAME_HDR_BYTES) return CCV2_ERR_ARG;
   const uint8_t *b = (const uint8_t *)in_host;
@@ -352,7 +393,7 @@ int ccv2_encode_batch(ccv2_codec *c, int nframes, const void *const *pts, const 
   CU(cudaSetDevice(c->device));
   const ccv2_params &prm = c->prm;
   const bool cen = prm.do_voxel_grid_centroid != 0, color = prm.do_color_encoding != 0;
-  const int G = c->group, NS = c->n_streams;
+  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : c->group, NS = c->profiling ? 1 : c->n_streams;
   const int ngroups = (nframes + G - 1) / G;
   size_t nmax = 1;
   for (int i = 0; i < nframes; i++) { if (npts[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; } if (npts[i] && !pts[i]) return CCV2_ERR_ARG; nmax = std::max(nmax, npts[i]); }
@@ -426,34 +467,30 @@ int ccv2_encode_batch(ccv2_codec *c, int nframes, const void *const *pts, const 
       CU(cudaMemsetAsync((uint8_t *)c->enc_slots.p + slot_bytes * slot + zoff, 0, zbytes, st));
     }
     const unsigned gx256 = (unsigned)((gn + 255) / 256), gtiles = (unsigned)((gn + SORT_TILE - 1) / SORT_TILE);
-    bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 0);
-    bbox_fixup_kernel<<<gf, 32, 0, st>>>(dg, P);
-    keygen_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P, 0);
-    bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 1);
-    keygen_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P, 1);
+    LAUNCH("bbox_kernel", bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 0));
+    LAUNCH("bbox_fixup_kernel", bbox_fixup_kernel<<<gf, 32, 0, st>>>(dg, P));
+    LAUNCH("keygen_kernel", keygen_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P, 0));
+    LAUNCH("bbox_kernel(slow path)", bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 1));
+    LAUNCH("keygen_kernel(rekey)", keygen_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P, 1));
     // frame ids are sequential over the batch: group g's setup needs group g-1's setup kernel to have run
     if (g > 0) CU(cudaStreamWaitEvent(st, c->ev_group[g - 1], 0));
-    frame_setup_kernel<<<1, 32, 0, st>>>(dg, gf, counter);
+    LAUNCH("frame_setup_kernel", frame_setup_kernel<<<1, 32, 0, st>>>(dg, gf, counter));
     CU(cudaEventRecord(c->ev_group[g], st));
-    sort_hist_kernel<<<dim3(gtiles, gf), 256, 0, st>>>(dg);
-    launches += 7;
-    for (int p = 0; p < 8; p++) { sort_pass_kernel<<<dim3(gtiles, gf), SORT_THREADS, 0, st>>>(dg, p); launches++; }
-    leaf_scan_kernel<<<dim3((unsigned)((gn + LEAF_TILE - 1) / LEAF_TILE), gf), LEAF_THREADS, 0, st>>>(dg);
-    leaf_emit_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P);
-    launches += 2;
+    LAUNCH("sort_hist_kernel", sort_hist_kernel<<<dim3(gtiles, gf), 256, 0, st>>>(dg));
+    for (int p = 0; p < 8; p++) LAUNCH("sort_pass_kernel", sort_pass_kernel<<<dim3(gtiles, gf), SORT_THREADS, 0, st>>>(dg, p));
+    LAUNCH("leaf_scan_kernel", leaf_scan_kernel<<<dim3((unsigned)((gn + LEAF_TILE - 1) / LEAF_TILE), gf), LEAF_THREADS, 0, st>>>(dg));
+    LAUNCH("leaf_emit_kernel", leaf_emit_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P));
     if (color && prm.color_coding_type == 1) {
       const size_t img_h = gn / 256 + 1, mcu_h = (img_h + 15) / 16, nblk = mcu_h * 16 * 6;
-      jpeg_mcu_kernel<<<dim3((unsigned)(mcu_h * 16), gf), 256, 0, st>>>(dg, c->d_tables);
-      jpeg_huff_kernel<<<dim3((unsigned)((nblk + HUFF_THREADS - 1) / HUFF_THREADS), gf), HUFF_THREADS, 0, st>>>(dg, c->d_tables);
+      LAUNCH("jpeg_mcu_kernel", jpeg_mcu_kernel<<<dim3((unsigned)(mcu_h * 16), gf), 256, 0, st>>>(dg, c->d_tables));
+      LAUNCH("jpeg_huff_kernel", jpeg_huff_kernel<<<dim3((unsigned)((nblk + HUFF_THREADS - 1) / HUFF_THREADS), gf), HUFF_THREADS, 0, st>>>(dg, c->d_tables));
       const size_t jb = 4 * gn + 8192;
-      jpeg_stuff_kernel<<<dim3((unsigned)((jb + STUFF_THREADS * STUFF_BYTES - 1) / (STUFF_THREADS * STUFF_BYTES)), gf), STUFF_THREADS, 0, st>>>(dg, c->d_tables);
-      launches += 3;
+      LAUNCH("jpeg_stuff_kernel", jpeg_stuff_kernel<<<dim3((unsigned)((jb + STUFF_THREADS * STUFF_BYTES - 1) / (STUFF_THREADS * STUFF_BYTES)), gf), STUFF_THREADS, 0, st>>>(dg, c->d_tables));
     }
     const size_t hmax = std::max(tree_cap_for(gn), cpay_cap_for(gn));
-    hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), 3, gf), 256, 0, st>>>(dg);
-    rc_encode_kernel<<<dim3(3, gf), 32, 0, st>>>(dg, cen, color);
-    assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H);
-    launches += 3;
+    LAUNCH("hist_kernel", hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), 3, gf), 256, 0, st>>>(dg));
+    LAUNCH("rc_encode_kernel", rc_encode_kernel<<<dim3(3, gf), 32, 0, st>>>(dg, cen, color));
+    LAUNCH("assemble_kernel", assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H));
     CU(cudaMemcpyAsync(hf + f0, dg, sizeof(EncFrame) * gf, cudaMemcpyDeviceToHost, st));
     CU(cudaGetLastError());
   }
@@ -488,6 +525,7 @@ int ccv2_encode_batch(ccv2_codec *c, int nframes, const void *const *pts, const 
   CU(cudaEventSynchronize(c->ev_end));
   CU(cudaEventElapsedTime(&c->device_ms, c->ev_start, c->ev_end));
   CU(cudaMemcpy(&c->frame_id, counter, 4, cudaMemcpyDeviceToHost));
+  prof_collect(c);
   c->launches = launches;
   c->enc_host.assign(hf, hf + nframes);
   for (int i = nframes - 1; i >= 0; i--) if (hf[i].out_len) { for (int k = 0; k < 3; k++) c->metrics[k] = hf[i].coded[k]; break; }
@@ -555,7 +593,7 @@ int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const s
   c->err.clear(); c->launches = 0; c->device_ms = 0;
   if (nframes == 0) return CCV2_OK;
   CU(cudaSetDevice(c->device));
-  const int G = c->group, NS = c->n_streams;
+  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : c->group, NS = c->profiling ? 1 : c->n_streams;
   const int ngroups = (nframes + G - 1) / G;
   std::vector<size_t> work_off(nframes + 1, 0), input_off(nframes + 1, 0), output_off(nframes + 1, 0), zb(nframes, 0);
   std::vector<char> in_dev(nframes), out_dev(nframes);
@@ -604,12 +642,11 @@ int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const s
       if (!in_dev[k] && in_len[k]) CU(cudaMemcpyAsync((void *)hf[k].in, in[k], in_len[k], cudaMemcpyHostToDevice, st));
       CU(cudaMemsetAsync((uint8_t *)c->dec_work.p + work_off[k], 0, zb[k], st));
     }
-    dec_entropy_kernel<<<gf, 32, 0, st>>>(dg);
-    dec_serial_kernel<<<dim3(2, gf), 32, 0, st>>>(dg);
+    LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<gf, 32, 0, st>>>(dg));
+    LAUNCH("dec_serial_kernel", dec_serial_kernel<<<dim3(2, gf), 32, 0, st>>>(dg));
     const size_t img_h = pmax / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
-    jpeg_idct_kernel<<<dim3((unsigned)((nblocks + 31) / 32), gf), 256, 0, st>>>(dg, c->d_tables);
-    dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg);
-    launches += 4;
+    LAUNCH("jpeg_idct_kernel", jpeg_idct_kernel<<<dim3((unsigned)((nblocks + 31) / 32), gf), 256, 0, st>>>(dg, c->d_tables));
+    LAUNCH("dec_points_kernel", dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg));
     CU(cudaMemcpyAsync(hf + f0, dg, sizeof(DecFrame) * gf, cudaMemcpyDeviceToHost, st));
     CU(cudaGetLastError());
   }
@@ -641,6 +678,7 @@ int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const s
   CU(cudaEventRecord(c->ev_end, ms));
   CU(cudaEventSynchronize(c->ev_end));
   CU(cudaEventElapsedTime(&c->device_ms, c->ev_start, c->ev_end));
+  prof_collect(c);
   c->launches = launches;
   for (int i = nframes - 1; i >= 0; i--) if (!hf[i].error) { for (int k = 0; k < 3; k++) c->metrics[k] = hf[i].coded[k]; c->frame_id = hf[i].frame_id; break; }
   return rc;

@@ -101,6 +101,13 @@ uint64_t ccv2_last_launch_count(const ccv2_codec *c);
 /* Device time of the last batch call's kernel region (CUDA events on the codec's stream), milliseconds. */
 float ccv2_last_device_ms(const ccv2_codec *c);
 
+/* Profiling hook used by bench.py's roofline leg: when on, a batch call runs all its frames as one group on ONE
+ * stream and the library brackets every kernel launch with CUDA events on that stream; afterwards
+ * ccv2_get_profile(idx) returns per kernel name the summed device time and launch count of the last call
+ * (CCV2_ERR_ARG once idx runs past the last kernel). */
+int ccv2_set_profiling(ccv2_codec *c, int on);
+int ccv2_get_profile(const ccv2_codec *c, int idx, const char **name, float *total_ms, int *launches);
+
 /* Text of the last error on this codec (or of ccv2_create when c == NULL). */
 const char *ccv2_last_error(const ccv2_codec *c);
 const char *ccv2_status_string(int status);

@@ -1,0 +1,207 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (libccv2.so), against the CPU oracle on the
+same seeded inputs -- bit-exact streams, bit-exact decoded clouds -- plus the committed golden hashes, the
+edge cases the format has (empty / non-finite / single-point / late bbox growth), batches spanning several
+stream groups, device-pointer I/O and error behaviour."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cwi_pcl_codec_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    from cwi_pcl_codec_b200 import codec
+    codec.load_library()
+    return codec
+
+
+def oparams(O, kp):
+    return O.default_params(octree_resolution=kp.octree_resolution, point_resolution=kp.point_resolution,
+                            do_color=kp.do_color_encoding, color_bit_resolution=kp.color_bit_resolution,
+                            color_coding_type=kp.color_coding_type, do_centroid=kp.do_voxel_grid_centroid,
+                            jpeg_quality=kp.jpeg_quality)
+
+
+def check_batch(K, O, clouds, kp):
+    c = K.Codec(kp)
+    try:
+        streams = c.encode_batch(clouds)
+        op = oparams(O, kp)
+        fid = 0
+        refs = []
+        for i, cl in enumerate(clouds):
+            ref, info = O.encode(cl, op, frame_id=fid + 1)
+            if ref:
+                fid += 1
+            refs.append(ref)
+            assert streams[i] == ref, "frame %d: GPU stream (%d B) != oracle stream (%d B)" % (i, len(streams[i]), len(ref))
+        assert c.frame_id == fid
+        live = [s for s in refs if s]
+        if live:
+            dec = c.decode_batch(live)
+            for s, d in zip(live, dec):
+                rd, _ = O.decode(s)
+                assert d.shape == rd.shape and np.array_equal(d, rd)
+            m = c.metrics()
+            assert m[0] > 1028
+        return streams
+    finally:
+        c.close()
+
+
+CASES = {
+    "surf10k_b8": (lambda: [synth.gen_surface(10000, 0)], dict(octree_bits=8)),                      # BASELINE configs[0] shape
+    "unif2k_b6": (lambda: [synth.gen_uniform(2000, 1)], dict(octree_bits=6)),
+    "surf100k_b10_x3": (lambda: [synth.gen_surface(100000, s) for s in (1, 2, 3)], dict(octree_bits=10)),
+    "unif100k_b11": (lambda: [synth.gen_uniform(100000, 4)], dict(octree_bits=11)),
+    "tiny": (lambda: [synth.gen_uniform(1, 5), synth.gen_uniform(2, 6), synth.gen_uniform(255, 7), synth.gen_uniform(256, 17), synth.gen_uniform(257, 7), synth.gen_uniform(513, 8)], dict(octree_bits=7)),
+    "raw_type3": (lambda: [synth.gen_surface(20000, 9)], dict(octree_bits=9, color_coding_type=3)),
+    "pcl_type0_6bit": (lambda: [synth.gen_surface(20000, 10)], dict(octree_bits=9, color_coding_type=0, color_bits=6)),
+    "nocolor": (lambda: [synth.gen_surface(20000, 11)], dict(octree_bits=9, color_bits=0)),
+    "centroid": (lambda: [synth.gen_surface(30000, 12)], dict(octree_bits=7, keep_centroid=1)),
+    "q50": (lambda: [synth.gen_surface(50000, 13)], dict(octree_bits=10, jpeg_quality=50)),
+    "q100_random_colour": (lambda: [synth.gen_uniform(30000, 14)], dict(octree_bits=9, jpeg_quality=100)),
+    "duplicates_one_voxel": (lambda: [np.repeat(synth.gen_surface(7, 15), 3000)], dict(octree_bits=5)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_stream_and_decode_bit_exact(K, oracle, name):
+    make, kw = CASES[name]
+    check_batch(K, oracle, make(), K.default_params(**kw))
+
+
+def test_nonfinite_points_and_late_bbox_growth(K, oracle):
+    a = synth.gen_surface(40000, 14)
+    a["x"][100] = np.nan
+    a["y"][20000] = np.inf
+    b = synth.gen_surface(60000, 15)      # violators far beyond the exact 16k prefix: exercises the slow sequential path
+    b["x"][50000] = 7.5
+    b["z"][55000] = -3.25
+    lead_nan = synth.gen_surface(30000, 16)
+    lead_nan["x"][:20000] = np.nan        # no finite point inside the prefix at all
+    check_batch(K, oracle, [a, b, lead_nan], K.default_params(octree_bits=9))
+
+
+def test_empty_and_all_nonfinite_frames_write_nothing_and_keep_frame_ids(K, oracle):
+    nanf = np.zeros(3, synth.POINT_DTYPE)
+    nanf["y"] = np.nan
+    clouds = [np.zeros(0, synth.POINT_DTYPE), synth.gen_surface(5000, 16), nanf, synth.gen_surface(3000, 17)]
+    streams = check_batch(K, oracle, clouds, K.default_params(octree_bits=8))
+    assert streams[0] == b"" and streams[2] == b""
+    assert int.from_bytes(streams[1][48:52], "little") == 1 and int.from_bytes(streams[3][48:52], "little") == 2
+
+
+def test_batch_spanning_groups_and_streams_matches_one_by_one(K, oracle):
+    clouds = [synth.gen_surface(3000 + 500 * i, 100 + i) for i in range(37)]   # > group size * streams mix
+    kp = K.default_params(octree_bits=8)
+    streams = check_batch(K, oracle, clouds, kp)
+    c = K.Codec(kp)
+    one = [c.encode_batch([cl])[0] for cl in clouds]
+    c.close()
+    assert one == streams
+
+
+def test_golden_stream_hashes_full_size(K, golden_dir):
+    """BASELINE configs[1] size (1M points, depth 11, Q85): GPU streams against the committed SHA-256."""
+    table = json.load(open(os.path.join(golden_dir, "stream_hashes.json")))
+    c = K.Codec(K.default_params(octree_bits=11))
+    checked = 0
+    for name in ("surf1M_b11_snake85", "unif1M_b11_snake85"):
+        e = table[name]
+        pts = getattr(synth, e["gen"])(e["n"], e["seed"])
+        if hashlib.sha256(pts.tobytes()).hexdigest() != e["input_sha256"]:
+            continue
+        c.frame_id = 0
+        s = c.encode_batch([pts])[0]
+        assert len(s) == e["stream_bytes"] and hashlib.sha256(s).hexdigest() == e["stream_sha256"], name
+        d = c.decode_batch([s])[0]
+        assert hashlib.sha256(d.tobytes()).hexdigest() == e["decoded_sha256"], name
+        checked += 1
+    c.close()
+    if not checked:
+        pytest.skip("synthetic generator differs on this machine")
+
+
+def test_full_size_against_oracle_and_roundtrip_properties(K, oracle):
+    pts = synth.gen_surface(1000000, 21)
+    kp = K.default_params(octree_bits=11)
+    s = check_batch(K, oracle, [pts], kp)[0]
+    c = K.Codec(kp)
+    d = c.decode_batch([s])[0]
+    # size-independent properties: count == header point_count; positions are voxel centres of the bbox grid; sorted in
+    # Morton (DFS) order; every input point lies in exactly one decoded voxel
+    assert d.shape[0] == int.from_bytes(s[55:63], "little")
+    bmin = np.frombuffer(s[80:104], "<f8")
+    xyz = d[:, :12].copy().view(np.float32).reshape(-1, 3).astype(np.float64)
+    k = (xyz - bmin) * 2048.0 - 0.5
+    assert np.array_equal(k, np.round(k))
+    kin = np.floor((np.stack([pts["x"], pts["y"], pts["z"]], 1).astype(np.float64) - bmin) * 2048.0).astype(np.int64)
+    assert np.array_equal(np.unique(kin, axis=0), np.unique(k.astype(np.int64), axis=0))
+    c.close()
+
+
+def test_device_pointer_io(K, oracle):
+    torch = pytest.importorskip("torch")
+    clouds = [synth.gen_surface(50000, 30 + i) for i in range(3)]
+    kp = K.default_params(octree_bits=10)
+    c = K.Codec(kp)
+    d_in = [torch.from_numpy(cl.view(np.uint8).reshape(-1)).cuda() for cl in clouds]
+    cap = 6 * 50000 + 65536
+    d_str = [torch.empty(cap, dtype=torch.uint8, device="cuda") for _ in clouds]
+    lens = c.encode_batch_raw([t.data_ptr() for t in d_in], [50000] * 3, [t.data_ptr() for t in d_str], [cap] * 3)
+    d_out = [torch.empty(50000 * 32, dtype=torch.uint8, device="cuda") for _ in clouds]
+    ns = c.decode_batch_raw([t.data_ptr() for t in d_str], lens, [t.data_ptr() for t in d_out], [50000] * 3)
+    op = oparams(oracle, kp)
+    for i, cl in enumerate(clouds):
+        ref, _ = oracle.encode(cl, op, frame_id=i + 1)
+        assert d_str[i][:lens[i]].cpu().numpy().tobytes() == ref
+        rd, _ = oracle.decode(ref)
+        assert np.array_equal(d_out[i][:ns[i] * 32].cpu().numpy().reshape(-1, 32), rd)
+    assert c.last_launch_count > 0
+    c.close()
+
+
+def test_error_behaviour(K, oracle):
+    c = K.Codec(K.default_params(octree_bits=8))
+    cl = synth.gen_surface(5000, 40)
+    a = np.ascontiguousarray(cl)
+    small = np.zeros(100, np.uint8)
+    with pytest.raises(K.Ccv2Error) as ei:
+        c.encode_batch_raw([a.ctypes.data], [5000], [small.ctypes.data], [100])
+    assert ei.value.status == -4                                   # CCV2_ERR_CAPACITY
+    s = c.encode_batch([cl])[0]
+    junk = bytes(300)
+    out = np.zeros((10, 32), np.uint8)
+    jb = np.frombuffer(junk, np.uint8)
+    with pytest.raises(K.Ccv2Error) as ei:
+        c.decode_batch_raw([jb.ctypes.data], [300], [out.ctypes.data], [10])
+    assert ei.value.status == -6                                   # CCV2_ERR_STREAM (no frame header)
+    trunc = np.frombuffer(s[:len(s) // 2], np.uint8)
+    big = np.zeros((5000, 32), np.uint8)
+    with pytest.raises(K.Ccv2Error):
+        c.decode_batch_raw([trunc.ctypes.data], [trunc.size], [big.ctypes.data], [5000])
+    sb = np.frombuffer(s, np.uint8)
+    with pytest.raises(K.Ccv2Error) as ei:
+        c.decode_batch_raw([sb.ctypes.data], [sb.size], [out.ctypes.data], [10])
+    assert ei.value.status == -4                                   # caller's point buffer too small
+    # the codec is still usable afterwards
+    assert c.decode_batch([s])[0].shape[0] == int.from_bytes(s[55:63], "little")
+    c.close()
+
+
+def test_reference_facade(K, oracle):
+    cdc = K.OctreePointCloudCodecV2(K.MANUAL_CONFIGURATION, False, 2.0 ** -9, 2.0 ** -9, True, 0, True, 8, 1, False, False, False, 85, 1)
+    cl = synth.gen_surface(8000, 50)
+    s = cdc.encodePointCloud(cl)
+    ref, _ = oracle.encode(cl, oracle.default_params(octree_bits=9), frame_id=1)
+    assert s == ref
+    assert np.array_equal(cdc.decodePointCloud(s), oracle.decode(ref)[0])
+    assert cdc.decodePointCloud(b"garbage" * 20).shape[0] == 0
+    assert cdc.getPerformanceMetrics()[0] > 0
