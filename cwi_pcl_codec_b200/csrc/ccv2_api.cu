@@ -69,7 +69,8 @@ constexpr int MAX_STREAMS = 16;
 struct ccv2_codec {
   ccv2_params prm;
   int device = 0;
-  int n_streams = 8, group = 8;
+  int n_sm = 148;
+  int n_streams = 8, group = 0;           // group 0 = auto: spread the batch over all streams
   cudaStream_t main_stream = nullptr;
   cudaStream_t streams[MAX_STREAMS] = {};
   cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_fork = nullptr;
@@ -314,9 +315,10 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   ccv2_codec *c = new ccv2_codec();
   c->prm = *p; c->device = device;
   if (const char *s = getenv("CCV2_STREAMS")) c->n_streams = std::max(1, std::min(MAX_STREAMS, atoi(s)));
-  if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(1, std::min(64, atoi(s)));
+  if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(64, atoi(s)));
   auto fail = [&](cudaError_t ee, const char *what) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ee); ccv2_destroy(c); return CCV2_ERR_CUDA; };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+  if ((e = cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail(e, "cudaDeviceGetAttribute");
   if ((e = cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
   for (int i = 0; i < c->n_streams; i++) if ((e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
   if ((e = cudaEventCreate(&c->ev_start)) != cudaSuccess) return fail(e, "cudaEventCreate");
@@ -393,7 +395,8 @@ int ccv2_encode_batch(ccv2_codec *c, int nframes, const void *const *pts, const 
   CU(cudaSetDevice(c->device));
   const ccv2_params &prm = c->prm;
   const bool cen = prm.do_voxel_grid_centroid != 0, color = prm.do_color_encoding != 0;
-  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : c->group, NS = c->profiling ? 1 : c->n_streams;
+  const int NS = c->profiling ? 1 : c->n_streams;
+  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(64, (nframes + NS - 1) / NS)));
   const int ngroups = (nframes + G - 1) / G;
   size_t nmax = 1;
   for (int i = 0; i < nframes; i++) { if (npts[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; } if (npts[i] && !pts[i]) return CCV2_ERR_ARG; nmax = std::max(nmax, npts[i]); }
@@ -489,7 +492,7 @@ int ccv2_encode_batch(ccv2_codec *c, int nframes, const void *const *pts, const 
     }
     const size_t hmax = std::max(tree_cap_for(gn), cpay_cap_for(gn));
     LAUNCH("hist_kernel", hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), 3, gf), 256, 0, st>>>(dg));
-    LAUNCH("rc_encode_kernel", rc_encode_kernel<<<dim3(3, gf), 32, 0, st>>>(dg, cen, color));
+    LAUNCH("rc_encode_kernel", rc_encode_kernel<<<c->n_sm, 96, 0, st>>>(dg, f0, gf, cen, color));
     LAUNCH("assemble_kernel", assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H));
     CU(cudaMemcpyAsync(hf + f0, dg, sizeof(EncFrame) * gf, cudaMemcpyDeviceToHost, st));
     CU(cudaGetLastError());
@@ -575,12 +578,13 @@ static size_t carve_dec(uint8_t *base, size_t pcap, DecFrame *f, size_t *zero_of
   uint8_t *node_byte = cv.take<uint8_t>(pcap + 8);
   uint8_t *planes = cv.take<uint8_t>(mcu_h * 16 * 256 * 3 / 2 + 256);
   uint16_t *qt = cv.take<uint16_t>(128);
+  uint8_t *scan = cv.take<uint8_t>(cpay_cap_for(pcap));
   if (f) {
     f->scan_status = scan_status; f->scan_tiles_max = scan_tiles; f->coef = coef; f->coef_cap_blocks = (uint32_t)nblocks;
     f->tree = tree; f->tree_cap = (uint32_t)tree_cap_for(pcap) - 64; f->cen = cen; f->cen_cap = (uint32_t)cen_cap_for(pcap) - 64;
     f->col = col; f->col_cap = (uint32_t)cpay_cap_for(pcap) - 64;
     f->node_prefix = node_prefix; f->node_byte = node_byte; f->node_cap = (uint32_t)pcap;
-    f->planes = planes; f->planes_cap = (uint32_t)(mcu_h * 16 * 256 * 3 / 2); f->qt = qt;
+    f->planes = planes; f->planes_cap = (uint32_t)(mcu_h * 16 * 256 * 3 / 2); f->qt = qt; f->scan = scan;
   }
   if (zero_off) *zero_off = 0;
   if (zero_bytes) *zero_bytes = z1;
@@ -593,7 +597,8 @@ int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const s
   c->err.clear(); c->launches = 0; c->device_ms = 0;
   if (nframes == 0) return CCV2_OK;
   CU(cudaSetDevice(c->device));
-  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : c->group, NS = c->profiling ? 1 : c->n_streams;
+  const int NS = c->profiling ? 1 : c->n_streams;
+  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(64, (nframes + NS - 1) / NS)));
   const int ngroups = (nframes + G - 1) / G;
   std::vector<size_t> work_off(nframes + 1, 0), input_off(nframes + 1, 0), output_off(nframes + 1, 0), zb(nframes, 0);
   std::vector<char> in_dev(nframes), out_dev(nframes);
@@ -642,8 +647,9 @@ int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const s
       if (!in_dev[k] && in_len[k]) CU(cudaMemcpyAsync((void *)hf[k].in, in[k], in_len[k], cudaMemcpyHostToDevice, st));
       CU(cudaMemsetAsync((uint8_t *)c->dec_work.p + work_off[k], 0, zb[k], st));
     }
-    LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<gf, 32, 0, st>>>(dg));
-    LAUNCH("dec_serial_kernel", dec_serial_kernel<<<dim3(2, gf), 32, 0, st>>>(dg));
+    LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf));
+    LAUNCH("jpeg_destuff_kernel", jpeg_destuff_kernel<<<gf, 1024, 0, st>>>(dg));
+    LAUNCH("dec_serial_kernel", dec_serial_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf));
     const size_t img_h = pmax / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
     LAUNCH("jpeg_idct_kernel", jpeg_idct_kernel<<<dim3((unsigned)((nblocks + 31) / 32), gf), 256, 0, st>>>(dg, c->d_tables));
     LAUNCH("dec_points_kernel", dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg));

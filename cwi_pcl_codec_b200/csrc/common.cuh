@@ -88,6 +88,7 @@ struct DecFrame {
   uint32_t data_with_color, do_centroid, color_bits;
   uint32_t B, ncen, ncol;
   uint32_t n_bottom, V;
+  uint32_t walk_done, _padw;                     // DFS walk already done by the pipelined walker warp
   uint32_t img_w, img_h, mcu_w, mcu_h, n_blocks;
   uint32_t ticket[TK_COUNT];
   uint32_t error, _pad0;
@@ -99,7 +100,9 @@ struct DecFrame {
   uint64_t *node_prefix; uint8_t *node_byte; uint32_t node_cap, _pad4;
   int16_t *coef; uint32_t coef_cap_blocks, _pad5;
   uint8_t *planes; uint32_t planes_cap, _pad6;   // Y | Cb | Cr
-  uint16_t *qt;                                  // [2][64] natural order, written by the huffman stage
+  uint16_t *qt;                                  // [2][64] zigzag order, written by the jpeg header parse
+  uint8_t *scan; uint32_t scan_start, scan_len;  // de-stuffed entropy-coded segment of the jpeg
+  uint32_t dht_off[4], dht_n[4];                 // offsets of the DHT bits[16] (values follow) inside col: dc0 dc1 ac0 ac1
   uint64_t *scan_status; uint32_t scan_tiles_max, _pad7;
 };
 
@@ -196,6 +199,16 @@ __device__ __forceinline__ uint64_t scan_lookback(uint64_t *status, uint32_t til
   }
   if (lane == 0) *(volatile uint64_t *)&status[tile] = SCAN_FLAG_P | (excl + aggregate);
   return excl;
+}
+
+// The serial one-warp-per-stream kernels are launched with one block per SM (gridDim.x = SM count); the block that
+// serves frame f of a group is (first_slot + f) mod gridDim.x, where first_slot is the group's first frame index in
+// the batch.  The first wave of a classic launch maps block ids to SMs deterministically, so frames of different
+// groups running concurrently on different streams land on different SMs instead of piling onto the same few.
+__device__ __forceinline__ int steered_frame(uint32_t first_slot, uint32_t group_frames) {
+  const uint32_t g = gridDim.x;
+  const uint32_t f = (blockIdx.x + g - first_slot % g) % g;
+  return f < group_frames ? (int)f : -1;
 }
 
 // Granlund-Montgomery division of a 32-bit value by an invariant d (2 <= d < 2^31): q = n / d exactly.

@@ -11,17 +11,29 @@ __device__ __forceinline__ double ld_f64_unaligned(const uint8_t *p) { uint64_t 
 __device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t *p) { uint64_t v = 0; for (int k = 7; k >= 0; k--) v = (v << 8) | p[k]; return v; }
 __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 
-// ---- stage 1: header + entropy decoding of the layers (impl.hpp:231-261, 1766-1835). grid (frames), 32 threads
-__global__ void __launch_bounds__(32) dec_entropy_kernel(DecFrame *frames) {
-  DecFrame &f = frames[blockIdx.x];
+__device__ inline void jpeg_parse_header(DecFrame &f);
+
+__device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg);
+
+// ---- stage 1: header + entropy decoding of the layers (impl.hpp:231-261, 1766-1835), one block per frame (steered):
+// warp 0 parses the header and range-decodes tree -> [centroid] -> colour (serially dependent: no stored lengths);
+// warp 1 walks the occupancy bytes out of a shared-memory ring while warp 0 is still producing them.
+__global__ void __launch_bounds__(64) dec_entropy_kernel(DecFrame *frames, int first_slot, int group_frames) {
+  const int fi = steered_frame(first_slot, group_frames);
+  if (fi < 0) return;
+  DecFrame &f = frames[fi];
   __shared__ uint32_t freq[257];
+  __shared__ WalkRing rg;
   const uint32_t lane = lane_id();
+  const bool decoder = threadIdx.x < 32;
   const uint8_t *in = f.in;
   const uint64_t len = f.in_len;
-  uint32_t err = 0;
-  // syncToHeader: the reference scans for the magic (impl.hpp:1660-1676); we require it at offset 0 or scan forward
-  uint64_t pos = 0;
-  {
+  uint32_t err = f.error;
+  uint64_t pos = 0, B = 0;
+  uint32_t do_centroid = 0, data_with_color = 0, cct = 0, depth = 0;
+  if (threadIdx.x == 0) { rg.prod = 0; rg.cons = 0; rg.done = 0; rg.dead = 0; rg.go = 0; }
+  if (decoder && !err) {
+    // syncToHeader: scan for the two magics like the reference (impl.hpp:1660-1676)
     const char id2[] = "<PCL-OCT-CODECV2-COMPRESSED>", id1[] = "<PCL-OCT-COMPRESSED>";
     uint32_t hp = 0; bool ok = true;
     while (hp < 28) {
@@ -37,63 +49,75 @@ __global__ void __launch_bounds__(32) dec_entropy_kernel(DecFrame *frames) {
       if (c != (uint8_t)id1[hp++]) hp = ((uint8_t)id1[0] == c) ? 1 : 0;
     }
     if (!ok || pos + 92 + 8 > len) err = FERR_BAD_STREAM;
+    if (!err) {
+      const uint8_t *h = in + pos;
+      const uint32_t frame_id = ld_u32_unaligned(h);
+      data_with_color = h[6];
+      const uint64_t point_count = ld_u64_unaligned(h + 7);
+      const double res = ld_f64_unaligned(h + 15);
+      const uint8_t color_bits = h[23];
+      double bmin[3], bmax[3];
+      for (int a = 0; a < 3; a++) { bmin[a] = ld_f64_unaligned(h + 32 + 8 * a); bmax[a] = ld_f64_unaligned(h + 56 + 8 * a); }
+      do_centroid = h[80];
+      cct = ld_u32_unaligned(h + 83);
+      pos += 92;
+      // [PCL] readFrameHeader -> defineBoundingBox -> getKeyBitSize
+      const double eps = 1.1920928955078125e-07;
+      uint32_t mk = 2;
+      for (int a = 0; a < 3; a++) {
+        double t = ceil(__ddiv_rn(__dsub_rn(__dsub_rn(bmax[a], bmin[a]), eps), res));
+        uint32_t k = (t >= 4294967295.0 || !(t == t)) ? 0xFFFFFFFFu : (t > 0 ? (uint32_t)t : 0u);
+        if (k > mk) mk = k;
+      }
+      while ((1ull << depth) < mk) depth++;
+      if (depth > CCV2_MAX_DEPTH || !(res > 0)) err |= FERR_DEPTH;
+      if (point_count > f.out_cap) err |= FERR_OUT_CAP;
+      B = ld_u64_unaligned(in + pos); pos += 8;
+      if (B > f.tree_cap) err |= FERR_TREE_CAP;
+      if (lane == 0) {
+        f.frame_id = frame_id; f.data_with_color = data_with_color; f.point_count = point_count; f.res = res; f.color_bits = color_bits;
+        for (int a = 0; a < 3; a++) { f.bmin[a] = bmin[a]; f.bmax[a] = bmax[a]; }
+        f.do_centroid = do_centroid; f.cct = cct; f.depth = depth;
+      }
+    }
+    if (lane == 0) { rg.B = (uint32_t)B; rg.depth = depth; rg.go = (!err && B > 0 && depth >= 1 && depth <= 17) ? 1u : 0u; }
   }
-  if (err) { if (lane == 0) { f.error |= err; f.V = 0; f.B = 0; f.point_count = 0; } return; }
-  const uint8_t *h = in + pos;
-  const uint32_t frame_id = ld_u32_unaligned(h);
-  const uint8_t data_with_color = h[6];
-  const uint64_t point_count = ld_u64_unaligned(h + 7);
-  const double res = ld_f64_unaligned(h + 15);
-  const uint8_t color_bits = h[23];
-  double bmin[3], bmax[3];
-  for (int a = 0; a < 3; a++) { bmin[a] = ld_f64_unaligned(h + 32 + 8 * a); bmax[a] = ld_f64_unaligned(h + 56 + 8 * a); }
-  const uint8_t do_centroid = h[80];
-  const uint32_t cct = ld_u32_unaligned(h + 83);
-  pos += 92;
-  // [PCL] readFrameHeader -> defineBoundingBox -> getKeyBitSize
-  const double eps = 1.1920928955078125e-07;
-  uint32_t mk = 2;
-  for (int a = 0; a < 3; a++) {
-    double t = ceil(__ddiv_rn(__dsub_rn(__dsub_rn(bmax[a], bmin[a]), eps), res));
-    uint32_t k = (t >= 4294967295.0 || !(t == t)) ? 0xFFFFFFFFu : (t > 0 ? (uint32_t)t : 0u);
-    if (k > mk) mk = k;
+  __syncthreads();
+  const bool ring = rg.go != 0;
+  if (!decoder) {                                           // walker warp: lane 0 walks, the other lanes retire
+    if (lane == 0 && ring) dfs_walk_ring(f, &rg);
+    return;
   }
-  uint32_t depth = 0; while ((1ull << depth) < mk) depth++;
-  if (depth > CCV2_MAX_DEPTH || !(res > 0)) err = FERR_DEPTH;
-  if (point_count > f.out_cap) err |= FERR_OUT_CAP;
-  const uint64_t B = ld_u64_unaligned(in + pos); pos += 8;
-  if (B > f.tree_cap) err |= FERR_TREE_CAP;
-  if (lane == 0) {
-    f.frame_id = frame_id; f.data_with_color = data_with_color; f.point_count = point_count; f.res = res; f.color_bits = color_bits;
-    for (int a = 0; a < 3; a++) { f.bmin[a] = bmin[a]; f.bmax[a] = bmax[a]; }
-    f.do_centroid = do_centroid; f.cct = cct; f.depth = depth;
-  }
-  if (err) { if (lane == 0) { f.error |= err; f.V = 0; f.B = 0; } return; }
-  ByteFeed feed; feed.init(in, len, pos);
+  if (err) { if (lane == 0) { f.error |= err; f.V = 0; f.B = 0; f.point_count = 0; rg.dead = 1; rg.done = 1; } return; }
   uint64_t coded[3] = { 0, 0, 0 };
-  bool ok = rc_decode_layer(feed, f.tree, (uint32_t)B, freq, &coded[0]);
+  bool ok = ring ? rc_decode_layer<true>(in, len, pos, f.tree, (uint32_t)B, freq, &coded[0], &rg)
+                 : rc_decode_layer<false>(in, len, pos, f.tree, (uint32_t)B, freq, &coded[0]);
+  if (!ok && lane == 0) { rg.dead = 1; rg.done = 1; }      // releases a waiting walker
   uint32_t ncen = 0, ncol = 0;
   if (ok && do_centroid) {
-    if (feed.pos + 4 > len) ok = false;
+    if (pos + 4 > len) ok = false;
     else {
-      ncen = ld_u32_unaligned(in + feed.pos); feed.pos += 4; feed.wbase = ~0ull;
+      ncen = ld_u32_unaligned(in + pos); pos += 4;
       if (ncen > f.cen_cap) { ok = false; err |= FERR_TREE_CAP; }
-      else ok = rc_decode_layer(feed, f.cen, ncen, freq, &coded[1]);
+      else ok = rc_decode_layer<false>(in, len, pos, f.cen, ncen, freq, &coded[1]);
     }
   }
   if (ok && data_with_color) {
-    if (feed.pos + 8 > len) ok = false;
+    if (pos + 8 > len) ok = false;
     else {
-      uint64_t nc = ld_u64_unaligned(in + feed.pos); feed.pos += 8; feed.wbase = ~0ull;
+      uint64_t nc = ld_u64_unaligned(in + pos); pos += 8;
       if (nc > f.col_cap) { ok = false; err |= FERR_JPEG_CAP; }
-      else { ncol = (uint32_t)nc; ok = rc_decode_layer(feed, f.col, ncol, freq, &coded[2]); }
+      else { ncol = (uint32_t)nc; ok = rc_decode_layer<false>(in, len, pos, f.col, ncol, freq, &coded[2]); }
     }
   }
   // trailing bytes would switch the reference into detail mode (impl.hpp:1802-1806): outside the implemented scope
-  if (ok && feed.pos != len) { ok = false; err |= FERR_UNSUPPORTED; }
+  if (ok && pos != len) { ok = false; err |= FERR_UNSUPPORTED; }
   if (lane == 0) {
-    if (!ok) { f.error |= err ? err : FERR_BAD_STREAM; f.B = 0; f.V = 0; }
-    else { f.B = (uint32_t)B; f.ncen = ncen; f.ncol = ncol; f.coded[0] = coded[0]; f.coded[1] = coded[1]; f.coded[2] = coded[2]; }
+    if (!ok) { atomicOr(&f.error, err ? err : FERR_BAD_STREAM); f.B = 0; f.V = 0; }
+    else {
+      f.B = (uint32_t)B; f.ncen = ncen; f.ncol = ncol; f.coded[0] = coded[0]; f.coded[1] = coded[1]; f.coded[2] = coded[2];
+      if (data_with_color && cct == 1) jpeg_parse_header(f);
+    }
   }
 }
 
@@ -112,6 +136,108 @@ struct SeqBytes {
     return v;
   }
 };
+// Fast walk for depth <= 17: the child masks of the open branches live in two 64-bit registers (8 bits per level),
+// the stream is consumed through a 64-bit window, and the children of a level depth-2 branch (all bottom-level
+// nodes, contiguous in the stream) are drained in a tight loop.
+__device__ inline void dfs_walk_fast(DecFrame &f) {
+  const uint32_t B = f.B, d = f.depth;
+  const uint64_t *src = (const uint64_t *)f.tree;          // 8-byte aligned, padded
+  uint32_t pos = 0; uint64_t win = src[0]; uint32_t wleft = 8; uint64_t nextw = src[1]; uint32_t wi = 2;
+  const uint32_t nwords = (B + 7) / 8 + 1;
+#define NEXT_BYTE(dst) do { dst = (uint32_t)win & 255u; win >>= 8; pos++; if (--wleft == 0) { win = nextw; wleft = 8; nextw = wi < nwords ? src[wi] : 0; wi++; } } while (0)
+  uint32_t nb = 0; const uint32_t cap = f.node_cap;
+  uint64_t *np = f.node_prefix; uint8_t *nby = f.node_byte;
+  bool bad = false;
+  uint32_t m; NEXT_BYTE(m);
+  if (d == 1) { np[0] = 0; nby[0] = (uint8_t)m; nb = 1; }
+  else {
+    uint64_t s0 = 0, s1 = 0, prefix = 0; uint32_t L = 0;
+    for (;;) {
+      if (m == 0) {
+        if (L == 0) break;
+        L--; prefix >>= 3;
+        m = (uint32_t)((L < 8 ? s0 >> (8 * L) : s1 >> (8 * (L - 8))) & 255u);
+        continue;
+      }
+      if (L + 2 == d) {                                   // children are bottom-level branches: one byte each
+        const uint32_t k = __popc(m);
+        if (pos + k > B || nb + k > cap) { bad = true; break; }
+        const uint64_t pre = prefix << 3;
+        do {
+          const uint32_t c = __ffs(m) - 1; m &= m - 1;
+          uint32_t byte; NEXT_BYTE(byte);
+          np[nb] = pre | c; nby[nb] = (uint8_t)byte; nb++;
+        } while (m);
+        continue;                                          // m == 0: pop
+      }
+      const uint32_t c = __ffs(m) - 1; m &= m - 1;
+      if (pos >= B) { bad = true; break; }
+      if (L < 8) { const uint32_t sh = 8 * L; s0 = (s0 & ~(255ull << sh)) | ((uint64_t)m << sh); }
+      else { const uint32_t sh = 8 * (L - 8); s1 = (s1 & ~(255ull << sh)) | ((uint64_t)m << sh); }
+      prefix = (prefix << 3) | c; L++;
+      NEXT_BYTE(m);
+    }
+  }
+#undef NEXT_BYTE
+  if (pos != B) bad = true;
+  if (bad) { f.error |= FERR_BAD_STREAM; nb = 0; }
+  f.n_bottom = nb;
+}
+
+// The same walk fed from the shared-memory ring the range decoder fills (dec_entropy_kernel).
+__device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg) {
+  const uint32_t B = rg->B, d = rg->depth;
+  uint32_t pos = 0, wpos = 0, win = 0, wleft = 0, avail = 0;
+  bool bad = false;
+#define NEXT_BYTE(dst) do { if (wleft == 0) { \
+      while (wpos >= avail) { avail = rg->prod; if (rg->dead) { bad = true; break; } } \
+      if (bad) break; \
+      win = rg->ring[wpos & (RING_WORDS - 1)]; wpos++; wleft = 4; if ((wpos & 15) == 0) rg->cons = wpos; } \
+    dst = win & 255u; win >>= 8; wleft--; pos++; } while (0)
+  uint32_t nb = 0; const uint32_t cap = f.node_cap;
+  uint64_t *np = f.node_prefix; uint8_t *nby = f.node_byte;
+  uint32_t m = 0;
+  do {
+    NEXT_BYTE(m);
+    if (bad) break;
+    if (d == 1) { np[0] = 0; nby[0] = (uint8_t)m; nb = 1; break; }
+    uint64_t s0 = 0, s1 = 0, prefix = 0; uint32_t L = 0;
+    for (;;) {
+      if (m == 0) {
+        if (L == 0) break;
+        L--; prefix >>= 3;
+        m = (uint32_t)((L < 8 ? s0 >> (8 * L) : s1 >> (8 * (L - 8))) & 255u);
+        continue;
+      }
+      if (L + 2 == d) {                                   // children are bottom-level branches: one byte each
+        const uint32_t k = __popc(m);
+        if (pos + k > B || nb + k > cap) { bad = true; break; }
+        const uint64_t pre = prefix << 3;
+        do {
+          const uint32_t c = __ffs(m) - 1; m &= m - 1;
+          uint32_t byte = 0; NEXT_BYTE(byte);
+          np[nb] = pre | c; nby[nb] = (uint8_t)byte; nb++;
+        } while (m && !bad);
+        if (bad) break;
+        continue;                                          // m == 0: pop
+      }
+      const uint32_t c = __ffs(m) - 1; m &= m - 1;
+      if (pos >= B) { bad = true; break; }
+      if (L < 8) { const uint32_t sh = 8 * L; s0 = (s0 & ~(255ull << sh)) | ((uint64_t)m << sh); }
+      else { const uint32_t sh = 8 * (L - 8); s1 = (s1 & ~(255ull << sh)) | ((uint64_t)m << sh); }
+      prefix = (prefix << 3) | c; L++;
+      NEXT_BYTE(m);
+      if (bad) break;
+    }
+  } while (0);
+#undef NEXT_BYTE
+  rg->dead = 1;                                            // the decoder must never wait for a walker that has left
+  if (pos != B) bad = true;
+  if (bad) { atomicOr(&f.error, FERR_BAD_STREAM); nb = 0; }
+  f.n_bottom = nb;
+  f.walk_done = 1;
+}
+
 __device__ inline void dfs_walk(DecFrame &f) {
   const uint32_t B = f.B, d = f.depth;
   if (B == 0 || d == 0) { f.n_bottom = 0; return; }
@@ -147,26 +273,90 @@ __device__ inline void dfs_walk(DecFrame &f) {
   f.n_bottom = nb;
 }
 
-// ---- stage 2b: JPEG marker parse + Huffman decode of the single SNAKE image (serial; no restart markers)
-struct HuffDec { int mincode[17]; int maxcode[17]; int valptr[17]; uint8_t vals[256]; uint16_t look[512]; };   // look: (len << 8) | sym for codes <= 9 bits
-struct JBits {
-  const uint8_t *p; uint32_t n, pos; uint64_t acc; int nb; bool marker;
-  __device__ __forceinline__ void fill() {
-    while (nb <= 48) {
-      uint32_t c = 0;
-      if (!marker && pos < n) {
-        c = p[pos];
-        if (c == 0xFF) { if (pos + 1 < n && p[pos + 1] == 0) pos += 2; else { marker = true; c = 0; } }
-        else pos++;
+// ---- stage 2b: JPEG of the single SNAKE image: marker parse (serial, short), parallel de-stuffing of the
+// entropy-coded segment, serial Huffman decode (no restart markers => one dependent bit stream per image)
+__device__ inline void jpeg_parse_header(DecFrame &f) {
+  const uint8_t *in = f.col; const uint32_t len = f.ncol;
+  bool bad = false;
+  uint32_t w = 0, h = 0, scan = 0, have = 0;
+  if (len < 4 || in[0] != 0xFF || in[1] != 0xD8) bad = true;
+  uint32_t pos = 2;
+  while (!bad && pos + 4 <= len) {
+    if (in[pos] != 0xFF) { bad = true; break; }
+    uint32_t m = in[pos + 1], L = ((uint32_t)in[pos + 2] << 8) | in[pos + 3];
+    const uint8_t *s = in + pos + 4;
+    if (L < 2 || pos + 2 + L > len) { bad = true; break; }
+    if (m == 0xDB) {
+      uint32_t o = 0;
+      while (o + 65 <= L - 2) { uint32_t t = s[o] & 15; if ((s[o] >> 4) || t > 1) { bad = true; break; } for (int i = 0; i < 64; i++) f.qt[t * 64 + i] = s[o + 1 + i]; have |= 1u << t; o += 65; }   // zigzag order kept
+    } else if (m == 0xC0) {
+      if (L < 17) { bad = true; break; }
+      h = ((uint32_t)s[1] << 8) | s[2]; w = ((uint32_t)s[3] << 8) | s[4];
+      if (s[0] != 8 || s[5] != 3 || s[7] != 0x22 || s[10] != 0x11 || s[13] != 0x11 || s[8] != 0 || s[11] != 1 || s[14] != 1) bad = true;
+    } else if (m == 0xC4) {
+      uint32_t o = 0;
+      while (o + 17 <= L - 2) {
+        uint32_t tc = s[o] >> 4, th = s[o] & 15, nv = 0;
+        if (tc > 1 || th > 1) { bad = true; break; }
+        for (int i = 0; i < 16; i++) nv += s[o + 1 + i];
+        if (nv > 256 || o + 17 + nv > L - 2) { bad = true; break; }
+        f.dht_off[tc * 2 + th] = pos + 4 + o + 1; f.dht_n[tc * 2 + th] = nv;
+        have |= 4u << (tc * 2 + th);
+        o += 17 + nv;
       }
-      acc = (acc << 8) | c; nb += 8;
-    }
+    } else if (m == 0xDA) { scan = pos + 2 + L; break; }
+    else if (m == 0xC2 || m == 0xDD) { bad = true; break; }      // progressive / restart intervals: libjpeg as driven by jpeg_io never emits them
+    pos += 2 + L;
   }
-  __device__ __forceinline__ uint32_t peek(int k) { return (uint32_t)(acc >> (nb - k)) & ((1u << k) - 1); }
-  __device__ __forceinline__ void skip(int k) { nb -= k; }
+  if (!scan || w != 256 || h == 0 || have != 0x3F) bad = true;  // SNAKE images are 256 wide (cjpeg.h:197)
+  const uint32_t mcu_w = (w + 15) / 16, mcu_h = (h + 15) / 16, nblocks = mcu_w * mcu_h * 6;
+  if (!bad && nblocks > f.coef_cap_blocks) { bad = true; f.error |= FERR_JPEG_CAP; }
+  if (bad) { f.error |= FERR_BAD_STREAM; f.img_w = f.img_h = f.mcu_w = f.mcu_h = f.n_blocks = 0; f.scan_start = f.scan_len = 0; return; }
+  f.img_w = w; f.img_h = h; f.mcu_w = mcu_w; f.mcu_h = mcu_h; f.n_blocks = nblocks; f.scan_start = scan;
+}
+
+// removes the 0x00 stuffed after every 0xFF of the entropy-coded segment; one CTA per frame, chunks in order
+__global__ void __launch_bounds__(1024) jpeg_destuff_kernel(DecFrame *frames) {
+  DecFrame &f = frames[blockIdx.x];
+  if (f.error || !f.data_with_color || f.cct != 1 || f.n_blocks == 0) return;
+  const uint8_t *in = f.col + f.scan_start;
+  uint32_t n = f.ncol - f.scan_start;
+  if (n >= 2 && in[n - 2] == 0xFF && in[n - 1] == 0xD9) n -= 2;     // EOI
+  __shared__ uint64_t s_scan[33];
+  __shared__ uint8_t s_last[1024];
+  uint32_t obase = 0; uint32_t carry = 0;                            // last byte of the previous chunk
+  for (uint32_t c0 = 0; c0 < n; c0 += 1024 * 16) {
+    const uint32_t b0 = c0 + threadIdx.x * 16;
+    uint8_t by[16]; uint32_t nv = 0;
+    if (b0 < n) { nv = min(16u, n - b0); for (uint32_t k = 0; k < nv; k++) by[k] = in[b0 + k]; }
+    s_last[threadIdx.x] = nv ? by[nv - 1] : 0;
+    __syncthreads();
+    uint32_t prev = threadIdx.x ? s_last[threadIdx.x - 1] : carry;
+    const uint32_t chunk_last = s_last[1023];
+    uint32_t keep = 0, cnt = 0;
+    for (uint32_t k = 0; k < nv; k++) { bool kp = !(by[k] == 0 && prev == 0xFF); keep |= (uint32_t)kp << k; cnt += kp; prev = by[k]; }
+    uint64_t tot;
+    uint64_t excl = block_excl_scan_u64(cnt, &tot, s_scan);
+    uint32_t o = obase + (uint32_t)excl;
+    for (uint32_t k = 0; k < nv; k++) if (keep >> k & 1) f.scan[o++] = by[k];
+    obase += (uint32_t)tot; carry = chunk_last;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) f.scan_len = obase;
+}
+
+struct HuffDec { int mincode[17]; int maxcode[17]; int valptr[17]; uint8_t vals[256]; uint16_t look[512]; };   // look: (len << 8) | sym for codes <= 9 bits
+struct JBits {               // MSB-first bit reader over the de-stuffed segment, 32-bit big-endian refills, next word prefetched
+  const uint32_t *w; uint32_t nwords, wi; uint64_t acc; uint32_t nb; uint32_t nxt;
+  __device__ __forceinline__ uint32_t fetch(uint32_t i) const { return i < nwords ? __byte_perm(w[i], 0, 0x0123) : 0u; }
+  __device__ __forceinline__ void init(const uint8_t *p, uint32_t nbytes) {
+    w = (const uint32_t *)p; nwords = (nbytes + 3) / 4;
+    acc = ((uint64_t)fetch(0) << 32) | fetch(1); nb = 64; nxt = fetch(2); wi = 3;
+  }
+  __device__ __forceinline__ uint32_t peek(uint32_t k) const { return (uint32_t)(acc >> (64 - k)); }          // 1 <= k <= 32
+  __device__ __forceinline__ void skip(uint32_t k) { acc <<= k; nb -= k; if (nb <= 32) { acc |= (uint64_t)nxt << (32 - nb); nb += 32; nxt = fetch(wi); wi++; } }
 };
 __device__ inline int huff_sym(JBits &b, const HuffDec &h) {
-  b.fill();
   uint32_t e = h.look[b.peek(9)];
   if (e) { b.skip(e >> 8); return e & 255; }
   for (int l = 10; l <= 16; l++) {
@@ -194,71 +384,41 @@ __device__ inline void huff_build(HuffDec &h, const uint8_t *bits, const uint8_t
 __device__ __forceinline__ int jextend(int v, int n) { return n == 0 ? 0 : (v < (1 << (n - 1)) ? v - (1 << n) + 1 : v); }
 
 __device__ inline void jpeg_huff_decode(DecFrame &f, HuffDec *hd /* smem[4]: dc0 dc1 ac0 ac1 */) {
-  const uint8_t *in = f.col; const uint32_t len = f.ncol;
-  bool bad = false;
-  uint32_t w = 0, h = 0, scan = 0;
-  uint32_t have = 0;
-  if (len < 4 || in[0] != 0xFF || in[1] != 0xD8) bad = true;
-  uint32_t pos = 2;
-  while (!bad && pos + 4 <= len) {
-    if (in[pos] != 0xFF) { bad = true; break; }
-    uint32_t m = in[pos + 1], L = ((uint32_t)in[pos + 2] << 8) | in[pos + 3];
-    const uint8_t *s = in + pos + 4;
-    if (L < 2 || pos + 2 + L > len) { bad = true; break; }
-    if (m == 0xDB) {
-      uint32_t o = 0;
-      while (o + 65 <= L - 2) { uint32_t t = s[o] & 15; if ((s[o] >> 4) || t > 1) { bad = true; break; } for (int i = 0; i < 64; i++) f.qt[t * 64 + i] = s[o + 1 + i]; have |= 1u << t; o += 65; }   // zigzag order kept
-    } else if (m == 0xC0) {
-      h = ((uint32_t)s[1] << 8) | s[2]; w = ((uint32_t)s[3] << 8) | s[4];
-      if (s[0] != 8 || s[5] != 3 || s[7] != 0x22 || s[10] != 0x11 || s[13] != 0x11 || s[8] != 0 || s[11] != 1 || s[14] != 1) bad = true;
-    } else if (m == 0xC4) {
-      uint32_t o = 0;
-      while (o + 17 <= L - 2) {
-        uint32_t tc = s[o] >> 4, th = s[o] & 15, nv = 0;
-        if (tc > 1 || th > 1) { bad = true; break; }
-        for (int i = 0; i < 16; i++) nv += s[o + 1 + i];
-        if (nv > 256 || o + 17 + nv > L - 2) { bad = true; break; }
-        huff_build(hd[tc * 2 + th], s + o + 1, s + o + 17, (int)nv);
-        have |= 4u << (tc * 2 + th);
-        o += 17 + nv;
-      }
-    } else if (m == 0xDA) { scan = pos + 2 + L; break; }
-    else if (m == 0xC2 || m == 0xDD) { bad = true; break; }      // progressive / restart intervals: libjpeg as driven by jpeg_io never emits them
-    pos += 2 + L;
-  }
-  if (!scan || w != 256 || h == 0 || have != 0x3F) bad = true;  // SNAKE images are 256 wide (cjpeg.h:197)
-  const uint32_t mcu_w = (w + 15) / 16, mcu_h = (h + 15) / 16, nblocks = mcu_w * mcu_h * 6;
-  if (!bad && nblocks > f.coef_cap_blocks) { bad = true; f.error |= FERR_JPEG_CAP; }
-  if (bad) { f.error |= FERR_BAD_STREAM; f.img_w = f.img_h = f.mcu_w = f.mcu_h = f.n_blocks = 0; return; }
-  f.img_w = w; f.img_h = h; f.mcu_w = mcu_w; f.mcu_h = mcu_h; f.n_blocks = nblocks;
-  JBits br; br.p = in; br.n = len; br.pos = scan; br.acc = 0; br.nb = 0; br.marker = false;
+  const uint32_t nblocks = f.n_blocks;
+  if (nblocks == 0) return;
+  for (int t = 0; t < 4; t++) huff_build(hd[t], f.col + f.dht_off[t], f.col + f.dht_off[t] + 16, (int)f.dht_n[t]);
+  JBits br; br.init(f.scan, f.scan_len);
   int pred[3] = { 0, 0, 0 };
   short *coef = f.coef;                                   // pre-zeroed; zigzag order, quantised
+  uint32_t blk = 0;
   for (uint32_t g = 0; g < nblocks; g++) {
-    const uint32_t blk = g % 6; const int comp = blk < 4 ? 0 : (int)blk - 3; const int ts = comp ? 1 : 0;
+    const int comp = blk < 4 ? 0 : (int)blk - 3; const int ts = comp ? 1 : 0;
     short *c = coef + (size_t)g * 64;
     int n = huff_sym(br, hd[ts]);
-    br.fill();
-    int diff = n ? jextend((int)br.peek(n), n) : 0; br.skip(n);
+    int diff = 0;
+    if (n) { diff = jextend((int)br.peek(n), n); br.skip(n); }
     pred[comp] += diff; c[0] = (short)pred[comp];
     for (int k = 1; k < 64; k++) {
       int rs = huff_sym(br, hd[2 + ts]), r = rs >> 4, s = rs & 15;
       if (s == 0) { if (r == 15) { k += 15; continue; } break; }
       k += r;
-      br.fill();
       int v = jextend((int)br.peek(s), s); br.skip(s);
       if (k > 63) break;
       c[k] = (short)v;
     }
+    blk = blk == 5 ? 0 : blk + 1;
   }
 }
 
-__global__ void __launch_bounds__(32) dec_serial_kernel(DecFrame *frames) {
-  DecFrame &f = frames[blockIdx.y];
+__global__ void __launch_bounds__(64) dec_serial_kernel(DecFrame *frames, int first_slot, int group_frames) {
+  const int fi = steered_frame(first_slot, group_frames);
+  if (fi < 0) return;
+  DecFrame &f = frames[fi];
   __shared__ HuffDec hd[4];
-  if (threadIdx.x != 0) return;
-  if (f.error) { if (blockIdx.x == 0) f.n_bottom = 0; else { f.n_blocks = 0; } return; }
-  if (blockIdx.x == 0) dfs_walk(f);
+  if (lane_id() != 0) return;
+  const int role = threadIdx.x >> 5;                       // warp 0: DFS walk, warp 1: JPEG Huffman decode
+  if (f.error) { if (role == 0) f.n_bottom = 0; else f.n_blocks = 0; return; }
+  if (role == 0) { if (f.walk_done) return; if (f.depth >= 1 && f.depth <= 17 && f.B > 0) dfs_walk_fast(f); else dfs_walk(f); }
   else if (f.data_with_color && f.cct == 1) jpeg_huff_decode(f, hd);
 }
 

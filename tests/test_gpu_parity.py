@@ -141,7 +141,8 @@ def test_full_size_against_oracle_and_roundtrip_properties(K, oracle):
     bmin = np.frombuffer(s[80:104], "<f8")
     xyz = d[:, :12].copy().view(np.float32).reshape(-1, 3).astype(np.float64)
     k = (xyz - bmin) * 2048.0 - 0.5
-    assert np.array_equal(k, np.round(k))
+    assert np.abs(k - np.round(k)).max() < 2e-3                    # positions are float32: voxel centres up to rounding
+    k = np.round(k)
     kin = np.floor((np.stack([pts["x"], pts["y"], pts["z"]], 1).astype(np.float64) - bmin) * 2048.0).astype(np.int64)
     assert np.array_equal(np.unique(kin, axis=0), np.unique(k.astype(np.int64), axis=0))
     c.close()
