@@ -204,34 +204,36 @@ __global__ void __launch_bounds__(256) assemble_kernel(EncFrame *frames, HeaderP
 // ================================================================================================
 // decode side
 // ================================================================================================
-// Sequential input for the warp-uniform range decoder: a 64-bit big-endian look-ahead register refilled from
-// aligned 32-bit words, the next word prefetched one refill ahead so its latency stays off the serial chain.
-struct WordFeed {
-  const uint32_t *w; uint32_t last, wi; uint64_t la; uint32_t nla; uint32_t nxt; uint32_t consumed;
-  __device__ __forceinline__ uint32_t fetch(uint32_t i) const { return __byte_perm(w[min(i, last)], 0, 0x0123); }
+// Sequential input for the warp-uniform range decoder: a 64-bit big-endian window W over the stream, rebuilt from
+// three cached aligned 64-bit words (A, B and the prefetched C) whenever whole bytes have been consumed.  The fast
+// path consumes at most one byte per symbol, so the window is rebuilt once per 8 symbols, off the per-symbol path.
+struct WindowFeed {
+  const uint64_t *w; uint32_t last, widx, sbyte, ubits, consumed; uint64_t A, B, C, W;
+  __device__ __forceinline__ uint64_t fetch(uint32_t i) const {
+    const uint64_t v = w[min(i, last)];
+    return ((uint64_t)__byte_perm((uint32_t)v, 0, 0x0123) << 32) | __byte_perm((uint32_t)(v >> 32), 0, 0x0123);
+  }
+  __device__ __forceinline__ void rebuild() { W = sbyte ? (A << (8 * sbyte)) | (B >> (64 - 8 * sbyte)) : A; }
   __device__ __forceinline__ void init(const uint8_t *base, uint64_t len, uint64_t pos) {
     const uintptr_t a = (uintptr_t)(base + pos);
-    const uint32_t skip = (uint32_t)(a & 3);
-    w = (const uint32_t *)(a - skip);
-    const uintptr_t end = ((uintptr_t)(base + len) + 3) & ~(uintptr_t)3;
-    last = (uint32_t)((end - (a - skip)) / 4) - 1;          // reads past the end repeat the last word (PCL would read EOF garbage)
-    la = ((uint64_t)fetch(0) << 32) | fetch(1);
-    la <<= 8 * skip; nla = 8 - skip;
-    wi = 3; nxt = fetch(2); consumed = 0;
+    sbyte = (uint32_t)(a & 7);
+    w = (const uint64_t *)(a - sbyte);
+    const uintptr_t end = ((uintptr_t)(base + len) + 7) & ~(uintptr_t)7;
+    last = (uint32_t)((end - (a - sbyte)) / 8) - 1;        // reads past the end repeat the last word (PCL would read EOF garbage)
+    widx = 0; A = fetch(0); B = fetch(1); C = fetch(2); ubits = 0; consumed = 0;
+    rebuild();
   }
-  __device__ __forceinline__ void refill() { if (nla <= 4) { la |= (uint64_t)nxt << (32 - 8 * nla); nla += 4; nxt = fetch(wi); wi++; } }
-  // take sh bits (0, 8, 16 or 24) from the front of the stream
-  __device__ __forceinline__ uint32_t take(uint32_t sh) {
-    const uint32_t v = __funnelshift_l((uint32_t)(la >> 32), 0, sh);
-    la <<= sh; nla -= sh >> 3; consumed += sh >> 3;
-    refill();
-    return v;
+  // whole bytes consumed since the last rebuild are in ubits (multiple of 8, <= 64)
+  __device__ __forceinline__ void advance() {
+    consumed += ubits >> 3; sbyte += ubits >> 3; ubits = 0;
+    while (sbyte >= 8) { sbyte -= 8; A = B; B = C; widx++; C = fetch(widx + 2); }
+    rebuild();
   }
-  __device__ __forceinline__ uint32_t take32() {
-    const uint32_t v = (uint32_t)(la >> 32);
-    la <<= 32; nla -= 4; consumed += 4;
-    refill();
-    return v;
+  __device__ __forceinline__ uint32_t take_byte() {        // generic path: any number of bytes
+    if (ubits == 64) advance();                             // the window may have been drained by the fast path
+    const uint32_t b = (uint32_t)(W >> 56);
+    W <<= 8; ubits += 8;
+    return b;
   }
 };
 
@@ -267,8 +269,10 @@ __device__ inline bool rc_decode_layer(const uint8_t *base, uint64_t len, uint64
   if (__any_sync(FULL_MASK, bad) || freq_s[0] != 0 || total >= RC_BOTTOM) return false;
   __syncwarp();
   const FastDiv fd = fastdiv_make(total);
-  WordFeed in; in.init(base, len, pos + 1028);
-  uint32_t code = in.take32(), low = 0, range = 0xFFFFFFFFu;
+  WindowFeed in; in.init(base, len, pos + 1028);
+  uint32_t code = 0, low = 0, range = 0xFFFFFFFFu;
+  for (int k = 0; k < 4; k++) code = (code << 8) | in.take_byte();
+  in.advance();
   uint32_t osym = 0;
   uint32_t *out32 = (uint32_t *)out;
   const uint32_t sym_base = 8 * lane;
@@ -276,8 +280,8 @@ __device__ inline bool rc_decode_layer(const uint8_t *base, uint64_t len, uint64
   // One symbol.  r = range / total; lane-local boundaries t_k = freq[8*lane+k] * r against v = code - low.  The
   // predicates are monotone (true...true false...false) so a 3-level select tree finds the last true one; the
   // owner lane (first boundary <= v < first boundary of the next lane) broadcasts its (cum,width) and symbol through
-  // REDUX.MAX (every other lane contributes 0) -- ~23 cycles instead of VOTE + FLO + SHFL (~85).
-#define RC_DEC_CORE() \
+  // REDUX.MAX (every other lane contributes 0) -- ~20 cycles instead of VOTE + FLO + SHFL (~85).
+#define RC_DEC_MAP() \
     const uint32_t r_ = fastdiv(range, fd); const uint32_t v_ = code - low; \
     const bool p0 = c[0] * r_ <= v_, p1 = c[1] * r_ <= v_, p2 = c[2] * r_ <= v_, p3 = c[3] * r_ <= v_; \
     const bool p4 = c[4] * r_ <= v_, p5 = c[5] * r_ <= v_, p6 = c[6] * r_ <= v_, p7 = c[7] * r_ <= v_; \
@@ -289,18 +293,22 @@ __device__ inline bool rc_decode_layer(const uint8_t *base, uint64_t len, uint64
     const uint32_t pk_ = __reduce_max_sync(FULL_MASK, own_ ? (p4 ? a47 : a03) : 0u); \
     const uint32_t sym_ = __reduce_max_sync(FULL_MASK, own_ ? sym_base + (p4 ? i47 : i03) : 0u); \
     osym = (osym >> 8) | (sym_ << 24); \
-    low += (pk_ >> 16) * r_; range = r_ * (pk_ & 0xFFFFu); \
-    const uint32_t sh_ = rc_equal_bits(low ^ (low + range));   /* same closed-form renormalisation as the encoder */ \
-    code = (code << sh_) | in.take(sh_); low <<= sh_; range <<= sh_;
-#define RC_DEC_UNDERFLOW() do { \
-      range = (0u - low) & (RC_BOTTOM - 1); code = (code << 8) | in.take(8); low <<= 8; range <<= 8; \
-      const uint32_t s2_ = rc_equal_bits(low ^ (low + range)); \
-      code = (code << s2_) | in.take(s2_); low <<= s2_; range <<= s2_; } while (range < RC_BOTTOM)
+    low += (pk_ >> 16) * r_; range = r_ * (pk_ & 0xFFFFu);
+  // PCL's literal renormalisation loop (any number of bytes, underflow included)
+#define RC_DEC_RENORM_GENERIC() do { for (;;) { \
+      if ((low ^ (low + range)) >= RC_TOP) { if (range >= RC_BOTTOM) break; range = (0u - low) & (RC_BOTTOM - 1); } \
+      code = (code << 8) | in.take_byte(); low <<= 8; range <<= 8; } } while (0)
 #define RC_DEC_STORE(I) do { if (((I) & 3) == 3) { out32[(I) >> 2] = osym; if (RING) rg->ring[((I) >> 2) & (RING_WORDS - 1)] = osym; } } while (0)
-#define RC_DEC_FAST(K) do { RC_DEC_CORE() if (__builtin_expect(range < RC_BOTTOM, 0)) { kk = (K); goto slow_path; } \
+  // fast path: the symbol shifts in 0, 1 or 2 bytes (99.9 % of symbols), does not underflow, and the window still
+  // holds the bytes; anything else takes PCL's literal loop and then resumes the fast path at the next symbol.
+#define RC_DEC_FAST(K) do { RC_DEC_MAP() \
+    const uint32_t x_ = low ^ (low + range); \
+    const uint32_t sh_ = x_ < RC_BOTTOM ? 16u : (x_ < RC_TOP ? 8u : 0u); \
+    const uint32_t rs_ = range << sh_; \
+    if (__builtin_expect((x_ < 256u) | (rs_ < RC_BOTTOM) | (in.ubits > 48u), 0)) { kk = (K); goto slow_path; } \
+    code = __funnelshift_l((uint32_t)(in.W >> 32), code, sh_); in.W <<= sh_; in.ubits += sh_; low <<= sh_; range = rs_; \
     RC_DEC_STORE(i0 + (K)); } while (0)
-#define RC_DEC_SYMBOL(I) do { RC_DEC_CORE() if (__builtin_expect(range < RC_BOTTOM, 0)) RC_DEC_UNDERFLOW(); \
-    RC_DEC_STORE(I); } while (0)
+#define RC_DEC_SYMBOL(I) do { RC_DEC_MAP() RC_DEC_RENORM_GENERIC(); RC_DEC_STORE(I); } while (0)
   const uint32_t n8 = n & ~7u;
   for (uint32_t i0 = 0; i0 < n8; i0 += 8) {
     uint32_t kk;
@@ -309,19 +317,23 @@ __device__ inline bool rc_decode_layer(const uint8_t *base, uint64_t len, uint64
       rg->prod = i0 >> 2;
       while (!rg->dead && (i0 >> 2) - rg->cons > RING_WORDS - 64) { }
     }
-    RC_DEC_FAST(0); RC_DEC_FAST(1); RC_DEC_FAST(2); RC_DEC_FAST(3); RC_DEC_FAST(4); RC_DEC_FAST(5); RC_DEC_FAST(6); RC_DEC_FAST(7);
+    RC_DEC_FAST(0); resume1: RC_DEC_FAST(1); resume2: RC_DEC_FAST(2); resume3: RC_DEC_FAST(3);
+    resume4: RC_DEC_FAST(4); resume5: RC_DEC_FAST(5); resume6: RC_DEC_FAST(6); resume7: RC_DEC_FAST(7);
+    resume8: in.advance();
     continue;
-  slow_path:                                                         // rare: finish symbol kk's underflow, then the rest of the batch
-    RC_DEC_UNDERFLOW();
+  slow_path:                                                         // symbol kk is mapped but not renormalised yet
+    RC_DEC_RENORM_GENERIC();
     RC_DEC_STORE(i0 + kk);
-    for (uint32_t i = i0 + kk + 1; i < i0 + 8; i++) RC_DEC_SYMBOL(i);
+    switch (kk) { case 0: goto resume1; case 1: goto resume2; case 2: goto resume3; case 3: goto resume4;
+                  case 4: goto resume5; case 5: goto resume6; case 6: goto resume7; default: goto resume8; }
   }
   for (uint32_t i = n8; i < n; i++) RC_DEC_SYMBOL(i);
-#undef RC_DEC_STORE
+  in.advance();
 #undef RC_DEC_FAST
 #undef RC_DEC_SYMBOL
-#undef RC_DEC_UNDERFLOW
-#undef RC_DEC_CORE
+#undef RC_DEC_STORE
+#undef RC_DEC_RENORM_GENERIC
+#undef RC_DEC_MAP
   if (n & 3) {
     const uint32_t rem = n & 3; osym >>= 8 * (4 - rem);
     for (uint32_t k = 0; k < rem; k++) out[(n & ~3u) + k] = (uint8_t)(osym >> (8 * k));
