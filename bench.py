@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--frames", type=int, default=int(os.environ.get("BENCH_FRAMES", "64")), help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=int(os.environ.get("BENCH_FRAMES", "512")), help="frames per step per GPU")
     ap.add_argument("--points", type=int, default=1000000)
     ap.add_argument("--bits", type=int, default=11)
     ap.add_argument("--kind", default="surf", choices=["surf", "unif"])
@@ -291,7 +291,13 @@ def profile_roofline(K, lib, args, frames, alg_bytes_frame):
     avg_s = tot_ms / count / 1e3
     achieved = alg_bytes_frame * frames_per_launch / avg_s / 1e9
     total_ms = sum(r[1] for r in prof)
-    return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    try:                                                        # dram bytes per launch from the committed ncu --set full capture
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+        traffic = int(t[name]) * frames_per_launch if name in t else None
+    except Exception:
+        pass
+    return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": which, "avg_launch_ms": avg_s * 1e3, "frames_per_launch": frames_per_launch,
             "algorithmic_bytes_per_frame": alg_bytes_frame, "share_of_step": tot_ms / total_ms,
             "kernels_ms": {r[0]: round(r[1], 4) for r in prof}}

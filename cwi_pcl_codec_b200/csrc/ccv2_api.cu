@@ -70,6 +70,7 @@ struct ccv2_codec {
   ccv2_params prm;
   int device = 0;
   int n_sm = 148;
+  int use_ring = 1;                       // pipeline the DFS walk behind the range decoder (CCV2_NO_RING=1 disables: debugging)
   int n_streams = 8, group = 0;           // group 0 = auto: spread the batch over all streams
   cudaStream_t main_stream = nullptr;
   cudaStream_t streams[MAX_STREAMS] = {};
@@ -314,6 +315,7 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   }
   ccv2_codec *c = new ccv2_codec();
   c->prm = *p; c->device = device;
+  if (const char *s = getenv("CCV2_NO_RING")) c->use_ring = atoi(s) ? 0 : 1;
   if (const char *s = getenv("CCV2_STREAMS")) c->n_streams = std::max(1, std::min(MAX_STREAMS, atoi(s)));
   if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(64, atoi(s)));
   auto fail = [&](cudaError_t ee, const char *what) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ee); ccv2_destroy(c); return CCV2_ERR_CUDA; };
@@ -568,7 +570,7 @@ static size_t carve_dec(uint8_t *base, size_t pcap, DecFrame *f, size_t *zero_of
   Carver cv(base);
   const size_t img_h = pcap / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
   const uint32_t scan_tiles = (uint32_t)(pcap / NODE_THREADS) + 8;
-  uint64_t *scan_status = cv.take<uint64_t>(scan_tiles);
+  uint64_t *scan_status = cv.take<uint64_t>(2 * (size_t)scan_tiles);
   int16_t *coef = cv.take<int16_t>(nblocks * 64 + 64);
   size_t z1 = (cv.off + 255) & ~size_t(255);
   uint8_t *tree = cv.take<uint8_t>(tree_cap_for(pcap));
@@ -576,6 +578,9 @@ static size_t carve_dec(uint8_t *base, size_t pcap, DecFrame *f, size_t *zero_of
   uint8_t *col = cv.take<uint8_t>(cpay_cap_for(pcap));
   uint64_t *node_prefix = cv.take<uint64_t>(pcap + 8);
   uint8_t *node_byte = cv.take<uint8_t>(pcap + 8);
+  uint64_t *l2_prefix = cv.take<uint64_t>(pcap + 8);
+  uint8_t *l2_mask = cv.take<uint8_t>(pcap + 8);
+  uint32_t *l2_off = cv.take<uint32_t>(pcap + 8);
   uint8_t *planes = cv.take<uint8_t>(mcu_h * 16 * 256 * 3 / 2 + 256);
   uint16_t *qt = cv.take<uint16_t>(128);
   uint8_t *scan = cv.take<uint8_t>(cpay_cap_for(pcap));
@@ -584,6 +589,7 @@ static size_t carve_dec(uint8_t *base, size_t pcap, DecFrame *f, size_t *zero_of
     f->tree = tree; f->tree_cap = (uint32_t)tree_cap_for(pcap) - 64; f->cen = cen; f->cen_cap = (uint32_t)cen_cap_for(pcap) - 64;
     f->col = col; f->col_cap = (uint32_t)cpay_cap_for(pcap) - 64;
     f->node_prefix = node_prefix; f->node_byte = node_byte; f->node_cap = (uint32_t)pcap;
+    f->l2_prefix = l2_prefix; f->l2_mask = l2_mask; f->l2_off = l2_off;
     f->planes = planes; f->planes_cap = (uint32_t)(mcu_h * 16 * 256 * 3 / 2); f->qt = qt; f->scan = scan;
   }
   if (zero_off) *zero_off = 0;
@@ -647,7 +653,8 @@ int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const s
       if (!in_dev[k] && in_len[k]) CU(cudaMemcpyAsync((void *)hf[k].in, in[k], in_len[k], cudaMemcpyHostToDevice, st));
       CU(cudaMemsetAsync((uint8_t *)c->dec_work.p + work_off[k], 0, zb[k], st));
     }
-    LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf));
+    LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf, c->use_ring));
+    LAUNCH("dec_expand_kernel", dec_expand_kernel<<<dim3((unsigned)((pmax + 255) / 256), gf), 256, 0, st>>>(dg));
     LAUNCH("jpeg_destuff_kernel", jpeg_destuff_kernel<<<gf, 1024, 0, st>>>(dg));
     LAUNCH("dec_serial_kernel", dec_serial_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf));
     const size_t img_h = pmax / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;

@@ -22,7 +22,7 @@ enum : uint32_t {
   FERR_UNSUPPORTED = 1u << 6, // decoder: stream uses a mode outside the implemented scope
 };
 
-enum : int { TK_SORT0 = 0, TK_LEAF = 8, TK_HUFF = 9, TK_STUFF = 10, TK_NODES = 11, TK_COUNT = 16 };
+enum : int { TK_SORT0 = 0, TK_LEAF = 8, TK_HUFF = 9, TK_STUFF = 10, TK_NODES = 11, TK_EXPAND = 12, TK_COUNT = 16 };
 
 struct __align__(16) JpegTables {   // per codec, device resident
   uint16_t q[2][64];           // quant tables, natural order (lum, chroma)
@@ -97,7 +97,9 @@ struct DecFrame {
   uint8_t *tree; uint32_t tree_cap, _pad1;
   uint8_t *cen; uint32_t cen_cap, _pad2;
   uint8_t *col; uint32_t col_cap, _pad3;
-  uint64_t *node_prefix; uint8_t *node_byte; uint32_t node_cap, _pad4;
+  uint64_t *node_prefix; uint8_t *node_byte; uint32_t node_cap, _pad4;   // bottom-level branches (level depth-1)
+  uint64_t *l2_prefix; uint8_t *l2_mask; uint32_t *l2_off;                 // level depth-2 branches recorded by the pipelined walker
+  uint32_t n_l2, l2_valid;
   int16_t *coef; uint32_t coef_cap_blocks, _pad5;
   uint8_t *planes; uint32_t planes_cap, _pad6;   // Y | Cb | Cr
   uint16_t *qt;                                  // [2][64] zigzag order, written by the jpeg header parse

@@ -13,17 +13,19 @@ __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p) { return 
 
 __device__ inline void jpeg_parse_header(DecFrame &f);
 
-__device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg);
+__device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *lut);
 
 // ---- stage 1: header + entropy decoding of the layers (impl.hpp:231-261, 1766-1835), one block per frame (steered):
 // warp 0 parses the header and range-decodes tree -> [centroid] -> colour (serially dependent: no stored lengths);
 // warp 1 walks the occupancy bytes out of a shared-memory ring while warp 0 is still producing them.
-__global__ void __launch_bounds__(64) dec_entropy_kernel(DecFrame *frames, int first_slot, int group_frames) {
+__global__ void __launch_bounds__(64) dec_entropy_kernel(DecFrame *frames, int first_slot, int group_frames, int use_ring) {
   const int fi = steered_frame(first_slot, group_frames);
   if (fi < 0) return;
   DecFrame &f = frames[fi];
   __shared__ uint32_t freq[257];
   __shared__ WalkRing rg;
+  __shared__ uint32_t lut[256];                            // per 8-bit child mask: popcount << 16 | mask without its lowest bit << 8 | index of the lowest bit
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = ((uint32_t)__popc(i) << 16) | ((i & (i - 1)) << 8) | (i ? (uint32_t)(__ffs(i) - 1) : 0u);
   const uint32_t lane = lane_id();
   const bool decoder = threadIdx.x < 32;
   const uint8_t *in = f.in;
@@ -80,12 +82,12 @@ __global__ void __launch_bounds__(64) dec_entropy_kernel(DecFrame *frames, int f
         f.do_centroid = do_centroid; f.cct = cct; f.depth = depth;
       }
     }
-    if (lane == 0) { rg.B = (uint32_t)B; rg.depth = depth; rg.go = (!err && B > 0 && depth >= 1 && depth <= 17) ? 1u : 0u; }
+    if (lane == 0) { rg.B = (uint32_t)B; rg.depth = depth; rg.go = (use_ring && !err && B > 0 && depth >= 1 && depth <= 17) ? 1u : 0u; }
   }
   __syncthreads();
   const bool ring = rg.go != 0;
   if (!decoder) {                                           // walker warp: lane 0 walks, the other lanes retire
-    if (lane == 0 && ring) dfs_walk_ring(f, &rg);
+    if (lane == 0 && ring) dfs_walk_ring(f, &rg, lut);
     return;
   }
   if (err) { if (lane == 0) { f.error |= err; f.V = 0; f.B = 0; f.point_count = 0; rg.dead = 1; rg.done = 1; } return; }
@@ -184,58 +186,86 @@ __device__ inline void dfs_walk_fast(DecFrame &f) {
   f.n_bottom = nb;
 }
 
-// The same walk fed from the shared-memory ring the range decoder fills (dec_entropy_kernel).
-__device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg) {
+// The pipelined walker (warp 1 of dec_entropy_kernel): reads the occupancy bytes out of the shared-memory ring
+// while the range decoder is still producing them.  It only has to visit the branches above the bottom level: for
+// a branch at level depth-2 it records (prefix, child mask, stream offset of the first child) and skips the child
+// bytes -- dec_expand_kernel turns those records into bottom-level records in parallel afterwards.
+__device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *lut) {
   const uint32_t B = rg->B, d = rg->depth;
-  uint32_t pos = 0, wpos = 0, win = 0, wleft = 0, avail = 0;
+  uint32_t pos = 0, cw = NONE_U32, win = 0, avail = 0, pub = 0;
   bool bad = false;
-#define NEXT_BYTE(dst) do { if (wleft == 0) { \
-      while (wpos >= avail) { avail = rg->prod; if (rg->dead) { bad = true; break; } } \
-      if (bad) break; \
-      win = rg->ring[wpos & (RING_WORDS - 1)]; wpos++; wleft = 4; if ((wpos & 15) == 0) rg->cons = wpos; } \
-    dst = win & 255u; win >>= 8; wleft--; pos++; } while (0)
-  uint32_t nb = 0; const uint32_t cap = f.node_cap;
-  uint64_t *np = f.node_prefix; uint8_t *nby = f.node_byte;
-  uint32_t m = 0;
-  do {
-    NEXT_BYTE(m);
-    if (bad) break;
-    if (d == 1) { np[0] = 0; nby[0] = (uint8_t)m; nb = 1; break; }
+  auto read_byte = [&](uint32_t &dst) -> bool {             // byte at stream offset pos; false when the producer died
+    const uint32_t wi = pos >> 2;
+    if (wi != cw) {
+      while (wi >= avail) { avail = rg->prod; if (rg->dead) return false; }
+      win = rg->ring[wi & (RING_WORDS - 1)]; cw = wi;
+      if ((wi >> 4) != pub) { pub = wi >> 4; rg->cons = wi; }
+    }
+    dst = (win >> (8 * (pos & 3))) & 255u; pos++;
+    return true;
+  };
+  uint32_t m = 0, n2 = 0, nb = 0;
+  const uint32_t cap = f.node_cap;
+  if (!read_byte(m)) bad = true;
+  else if (d == 1) { f.node_prefix[0] = 0; f.node_byte[0] = (uint8_t)m; nb = 1; }
+  else {
     uint64_t s0 = 0, s1 = 0, prefix = 0; uint32_t L = 0;
     for (;;) {
-      if (m == 0) {
-        if (L == 0) break;
+      if (L + 2 == d) {                                     // children are bottom-level branches: record and skip them
+        const uint32_t k = lut[m] >> 16;
+        if (pos + k > B || n2 >= cap) { bad = true; break; }
+        f.l2_prefix[n2] = prefix; f.l2_mask[n2] = (uint8_t)m; f.l2_off[n2] = pos; n2++;
+        pos += k; m = 0;
+      }
+      bool done = false;
+      while (m == 0) {                                      // pop exhausted branches
+        if (L == 0) { done = true; break; }
         L--; prefix >>= 3;
         m = (uint32_t)((L < 8 ? s0 >> (8 * L) : s1 >> (8 * (L - 8))) & 255u);
-        continue;
       }
-      if (L + 2 == d) {                                   // children are bottom-level branches: one byte each
-        const uint32_t k = __popc(m);
-        if (pos + k > B || nb + k > cap) { bad = true; break; }
-        const uint64_t pre = prefix << 3;
-        do {
-          const uint32_t c = __ffs(m) - 1; m &= m - 1;
-          uint32_t byte = 0; NEXT_BYTE(byte);
-          np[nb] = pre | c; nby[nb] = (uint8_t)byte; nb++;
-        } while (m && !bad);
-        if (bad) break;
-        continue;                                          // m == 0: pop
-      }
-      const uint32_t c = __ffs(m) - 1; m &= m - 1;
-      if (pos >= B) { bad = true; break; }
-      if (L < 8) { const uint32_t sh = 8 * L; s0 = (s0 & ~(255ull << sh)) | ((uint64_t)m << sh); }
-      else { const uint32_t sh = 8 * (L - 8); s1 = (s1 & ~(255ull << sh)) | ((uint64_t)m << sh); }
+      if (done) break;
+      const uint32_t e = lut[m], c = e & 7u, mn = (e >> 8) & 255u;   // descend into the next child
+      if (L < 8) { const uint32_t sh = 8 * L; s0 = (s0 & ~(255ull << sh)) | ((uint64_t)mn << sh); }
+      else { const uint32_t sh = 8 * (L - 8); s1 = (s1 & ~(255ull << sh)) | ((uint64_t)mn << sh); }
       prefix = (prefix << 3) | c; L++;
-      NEXT_BYTE(m);
-      if (bad) break;
+      if (pos >= B) { bad = true; break; }
+      if (!read_byte(m)) { bad = true; break; }
     }
-  } while (0);
-#undef NEXT_BYTE
+  }
   rg->dead = 1;                                            // the decoder must never wait for a walker that has left
   if (pos != B) bad = true;
-  if (bad) { atomicOr(&f.error, FERR_BAD_STREAM); nb = 0; }
-  f.n_bottom = nb;
+  if (bad) { atomicOr(&f.error, FERR_BAD_STREAM); nb = 0; n2 = 0; }
+  f.n_bottom = nb; f.n_l2 = n2; f.l2_valid = (d >= 2 && !bad) ? 1u : 0u;
   f.walk_done = 1;
+}
+
+// Expands the level depth-2 records of the pipelined walker into bottom-level records (chained scan of popcounts).
+__global__ void __launch_bounds__(256) dec_expand_kernel(DecFrame *frames) {
+  DecFrame &f = frames[blockIdx.y];
+  if (f.error || !f.l2_valid) return;
+  const uint32_t n2 = f.n_l2;
+  const uint32_t ntiles = (n2 + 255) / 256;
+  if (blockIdx.x >= ntiles) return;
+  __shared__ uint32_t s_tile; __shared__ uint64_t s_scan[33]; __shared__ uint64_t s_excl;
+  if (threadIdx.x == 0) s_tile = atomicAdd(&f.ticket[TK_EXPAND], 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile, g = tile * 256 + threadIdx.x;
+  uint32_t mask = 0, off = 0; uint64_t prefix = 0;
+  if (g < n2) { mask = f.l2_mask[g]; off = f.l2_off[g]; prefix = f.l2_prefix[g]; }
+  const uint32_t k = __popc(mask);
+  uint64_t tot;
+  uint64_t excl = block_excl_scan_u64(k, &tot, s_scan);
+  if (threadIdx.x < 32) { uint64_t e = scan_lookback(f.scan_status + f.scan_tiles_max, tile, tot); if (threadIdx.x == 0) s_excl = e; }
+  __syncthreads();
+  excl += s_excl;
+  if (g >= n2) return;
+  if (g == n2 - 1) { const uint64_t total = excl + k; if (total > f.node_cap) { atomicOr(&f.error, FERR_BAD_STREAM); f.n_bottom = 0; } else f.n_bottom = (uint32_t)total; }
+  uint32_t o = (uint32_t)excl, i = 0;
+  while (mask && o < f.node_cap) {
+    const uint32_t c = __ffs(mask) - 1; mask &= mask - 1;
+    f.node_prefix[o] = (prefix << 3) | c; f.node_byte[o] = f.tree[off + i];
+    o++; i++;
+  }
 }
 
 __device__ inline void dfs_walk(DecFrame &f) {

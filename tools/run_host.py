@@ -1,0 +1,24 @@
+"""Developer tool (GPU box): pinned-host encode+decode of F frames; prints wall ms of each call and PCIe copy bandwidth."""
+import os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cwi_pcl_codec_b200 import codec as K, synth
+n = int(sys.argv[1]); F = int(sys.argv[2]); reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+base = [synth.gen_surface(n, s) for s in range(min(F, 8))]
+cap = 4 * n + (1 << 16)
+h_in = [K.PinnedBuffer(n * 32) for _ in range(F)]
+for i, b in enumerate(h_in): b.array[:] = base[i % len(base)].view(np.uint8).reshape(-1)
+h_str = [K.PinnedBuffer(cap) for _ in range(F)]
+h_out = [K.PinnedBuffer(n * 32) for _ in range(F)]
+# raw PCIe bandwidth with torch
+x = torch.empty(1 << 30, dtype=torch.uint8).pin_memory(); y = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+for name, a, b in (("H2D", x, y), ("D2H", y, x)):
+    torch.cuda.synchronize(); t = time.time()
+    for _ in range(4): b.copy_(a, non_blocking=True)
+    torch.cuda.synchronize(); print("%s %.1f GB/s" % (name, 4 * (1 << 30) / (time.time() - t) / 1e9))
+c = K.Codec(K.default_params(octree_bits=11))
+ip = [b.ptr for b in h_in]; sp = [b.ptr for b in h_str]; op = [b.ptr for b in h_out]
+for r in range(reps):
+    t = time.time(); lens = c.encode_batch_raw(ip, [n] * F, sp, [cap] * F); te = time.time() - t; de = c.last_device_ms
+    t = time.time(); ns = c.decode_batch_raw(sp, lens, op, [n] * F); td = time.time() - t; dd = c.last_device_ms
+print("F=%d host pinned: encode wall %.1f dev %.1f ms | decode wall %.1f dev %.1f ms | %.1f Mpts/s e2e" % (F, te * 1e3, de, td * 1e3, dd, n * F / (te + td) / 1e6))
