@@ -14,6 +14,7 @@ import argparse
 import ctypes as C
 import json
 import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: see csrc/ccv2_api.cu (stream -> hardware queue aliasing)
 import subprocess
 import sys
 import threading
@@ -284,7 +285,7 @@ def profile_roofline(K, lib, args, frames, alg_bytes_frame):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     which = "measured (MEASURED_PEAKS.json, copy kernel)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    prof = K.profile_step(frames[:min(len(frames), 8)], args.bits)
+    prof = K.profile_step(frames[:min(len(frames), 32)], args.bits)
     if not prof:
         return None
     name, tot_ms, count, frames_per_launch = max(prof, key=lambda r: r[1])

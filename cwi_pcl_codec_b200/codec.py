@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libccv2.so")
 
-MANUAL_CONFIGURATION = 12  # pcl::io::compression_Profiles_e
+MANUAL_CONFIGURATION = 13  # pcl::io::compression_Profiles_e (12 profiles, COMPRESSION_PROFILE_COUNT, MANUAL_CONFIGURATION)
 
 
 class Ccv2Error(RuntimeError):
@@ -60,6 +60,7 @@ def load_library():
     L.ccv2_max_compressed_size.restype = C.c_size_t
     L.ccv2_encode_batch.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, szp]
     L.ccv2_decode_batch.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, szp]
+    L.ccv2_roundtrip_batch.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, szp, vpp, szp, szp]
     L.ccv2_peek_point_count.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
     L.ccv2_get_metrics.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.ccv2_set_frame_id.argtypes = [C.c_void_p, C.c_uint32]
@@ -85,7 +86,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ["ccv2_default_params", "ccv2_create", "ccv2_destroy", "ccv2_max_compressed_size",
-                    "ccv2_encode_batch", "ccv2_decode_batch", "ccv2_peek_point_count", "ccv2_get_metrics",
+                    "ccv2_encode_batch", "ccv2_decode_batch", "ccv2_roundtrip_batch", "ccv2_peek_point_count", "ccv2_get_metrics",
                     "ccv2_set_frame_id", "ccv2_get_frame_id", "ccv2_last_launch_count", "ccv2_last_device_ms",
                     "ccv2_last_error", "ccv2_status_string", "ccv2_host_alloc", "ccv2_host_free", "ccv2_debug_fetch",
                     "ccv2_set_profiling", "ccv2_get_profile"]
@@ -209,6 +210,21 @@ class Codec:
         rc = self._L.ccv2_decode_batch(self._h, n, a_in, a_n, a_out, a_cap, a_len)
         self._check(rc)
         return list(a_len)
+
+    def roundtrip_batch_raw(self, in_ptrs, npts, str_ptrs, str_caps, out_ptrs, out_caps):
+        """encode -> decode in one pipelined call; returns (stream lengths, decoded point counts)."""
+        n = len(in_ptrs)
+        a_in = (C.c_void_p * n)(*in_ptrs)
+        a_n = (C.c_size_t * n)(*npts)
+        a_str = (C.c_void_p * n)(*str_ptrs) if str_ptrs is not None else None
+        a_scap = (C.c_size_t * n)(*(str_caps if str_caps is not None else [0] * n))
+        a_slen = (C.c_size_t * n)()
+        a_out = (C.c_void_p * n)(*out_ptrs)
+        a_cap = (C.c_size_t * n)(*out_caps)
+        a_np = (C.c_size_t * n)()
+        rc = self._L.ccv2_roundtrip_batch(self._h, n, a_in, a_n, a_str, a_scap, a_slen, a_out, a_cap, a_np)
+        self._check(rc)
+        return list(a_slen), list(a_np)
 
     # ---- numpy convenience API
     def encode_batch(self, clouds):

@@ -24,6 +24,13 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// The batch driver keeps 9 streams busy (8 group streams + 1 control stream).  CUDA maps streams onto
+// CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue serialise behind each other's
+// long serial kernels (measured: 2x on the round trip).  Ask for more queues unless the user already chose -- this only
+// takes effect if it happens before the process creates its CUDA context, so hosts that initialise CUDA first
+// (e.g. import torch; torch.cuda.init()) should export the variable themselves (bench.py and tests/conftest.py do).
+struct EnvInit { EnvInit() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); } } g_env_init;
+
 struct DevBuf {
   void *p = nullptr; size_t cap = 0;
   cudaError_t ensure(size_t bytes) {
@@ -388,184 +395,6 @@ int ccv2_peek_point_count(const void *in_host, size_t len, uint64_t *npts) {
   return CCV2_OK;
 }
 
-// ================================================================================================ encode
-int ccv2_encode_batch(ccv2_codec *c, int nframes, const void *const *pts, const size_t *npts,
-                      void *const *out, const size_t *out_cap, size_t *out_len) {
-  if (!c || nframes < 0 || (nframes && (!pts || !npts || !out || !out_cap || !out_len))) return CCV2_ERR_ARG;
-  c->err.clear(); c->launches = 0; c->device_ms = 0;
-  if (nframes == 0) return CCV2_OK;
-  CU(cudaSetDevice(c->device));
-  const ccv2_params &prm = c->prm;
-  const bool cen = prm.do_voxel_grid_centroid != 0, color = prm.do_color_encoding != 0;
-  const int NS = c->profiling ? 1 : c->n_streams;
-  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(64, (nframes + NS - 1) / NS)));
-  const int ngroups = (nframes + G - 1) / G;
-  size_t nmax = 1;
-  for (int i = 0; i < nframes; i++) { if (npts[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; } if (npts[i] && !pts[i]) return CCV2_ERR_ARG; nmax = std::max(nmax, npts[i]); }
-
-  // ---- workspaces. Slots: one per (stream, frame-in-group); persist + input staging: one per frame of the batch
-  size_t zoff = 0, zbytes = 0;
-  const size_t slot_bytes = carve_enc_slot(nullptr, nmax, nullptr, prm, &zoff, &zbytes);
-  const int nslots = std::min(ngroups, NS) * G;
-  CU(c->enc_slots.ensure(slot_bytes * nslots));
-  std::vector<size_t> persist_off(nframes + 1, 0), input_off(nframes + 1, 0);
-  std::vector<char> in_dev(nframes), out_dev(nframes);
-  for (int i = 0; i < nframes; i++) {
-    persist_off[i + 1] = persist_off[i] + carve_enc_persist(nullptr, npts[i], nullptr, cen);
-    in_dev[i] = npts[i] ? is_device_ptr(pts[i]) : 1;
-    out_dev[i] = out[i] ? is_device_ptr(out[i]) : 0;
-    input_off[i + 1] = input_off[i] + (in_dev[i] ? 0 : ((32 * npts[i] + 255) & ~size_t(255)));
-  }
-  CU(c->enc_persist.ensure(persist_off[nframes]));
-  CU(c->enc_input.ensure(input_off[nframes] + 256));
-  const size_t frames_bytes = (sizeof(EncFrame) * nframes + 255) & ~size_t(255);
-  CU(c->enc_frames.ensure(frames_bytes + (size_t)nframes * 3 * 256 * 4));
-  CU(c->h_frames.ensure(sizeof(EncFrame) * nframes));
-  while ((int)c->ev_group.size() < ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_group.push_back(ev); }
-
-  EncFrame *hf = (EncFrame *)c->h_frames.p;
-  EncFrame *df = (EncFrame *)c->enc_frames.p;
-  memset(hf, 0, sizeof(EncFrame) * nframes);
-  for (int i = 0; i < nframes; i++) {
-    EncFrame &f = hf[i];
-    const int g = i / G, slot = (g % NS) * G + (i % G);
-    f.pts = in_dev[i] ? (const uint8_t *)pts[i] : (const uint8_t *)c->enc_input.p + input_off[i];
-    f.n = (uint32_t)npts[i];
-    f.violator = NONE_U32;
-    carve_enc_slot((uint8_t *)c->enc_slots.p + slot_bytes * slot, nmax, &f, prm, nullptr, nullptr);
-    carve_enc_persist((uint8_t *)c->enc_persist.p + persist_off[i], npts[i], &f, cen);
-    f.hist = (uint32_t *)((uint8_t *)c->enc_frames.p + frames_bytes) + (size_t)i * 3 * 256;
-    if (color && prm.color_coding_type != 1) f.avg = f.cpay;       // raw averages are the colour payload (types 0, 3)
-  }
-
-  EncParams P;
-  P.res = prm.octree_resolution;
-  { int ex; double m = frexp(P.res, &ex); P.res_pow2 = (m == 0.5); P.inv_res = P.res_pow2 ? 1.0 / P.res : 0.0; }
-  P.do_color = color; P.color_type = prm.color_coding_type; P.do_centroid = cen;
-  P.color_reduction = (prm.color_coding_type == 0) ? std::max(0, 8 - (int)prm.color_bit_resolution) : 0;   // jp_color_coder_ is never configured
-  P.prefix_len = 16384;
-  HeaderParams H;
-  H.octree_res = prm.octree_resolution; H.point_res = (double)(float)prm.point_resolution;
-  H.do_voxel_grid = 1; H.with_color = color; H.color_bits = prm.color_bit_resolution; H.do_centroid = cen;
-  H.connectivity = prm.code_connectivity != 0; H.scalable = prm.create_scalable_stream != 0; H.icp_offset = prm.do_icp_color_offset != 0; H._p = 0;
-  H.color_type = prm.color_coding_type; H.macroblock = prm.macroblock_size;
-
-  cudaStream_t ms = c->main_stream;
-  CU(cudaEventRecord(c->ev_start, ms));
-  CU(cudaMemcpyAsync(df, hf, sizeof(EncFrame) * nframes, cudaMemcpyHostToDevice, ms));
-  CU(cudaMemsetAsync((uint8_t *)c->enc_frames.p + frames_bytes, 0, (size_t)nframes * 3 * 256 * 4, ms));
-  cudaEvent_t ev_setup = c->ev_fork;
-  CU(cudaEventRecord(ev_setup, ms));
-
-  uint64_t launches = 0;
-  uint32_t *counter = c->d_frame_counter;
-  for (int g = 0; g < ngroups; g++) {
-    cudaStream_t st = c->streams[g % NS];
-    const int f0 = g * G, gf = std::min(G, nframes - f0);
-    EncFrame *dg = df + f0;
-    CU(cudaStreamWaitEvent(st, ev_setup, 0));
-    size_t gn = 1;
-    for (int i = 0; i < gf; i++) {
-      gn = std::max(gn, npts[f0 + i]);
-      if (!in_dev[f0 + i] && npts[f0 + i]) CU(cudaMemcpyAsync((void *)hf[f0 + i].pts, pts[f0 + i], 32 * npts[f0 + i], cudaMemcpyHostToDevice, st));
-      const int slot = (g % NS) * G + i;
-      CU(cudaMemsetAsync((uint8_t *)c->enc_slots.p + slot_bytes * slot + zoff, 0, zbytes, st));
-    }
-    const unsigned gx256 = (unsigned)((gn + 255) / 256), gtiles = (unsigned)((gn + SORT_TILE - 1) / SORT_TILE);
-    LAUNCH("bbox_kernel", bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 0));
-    LAUNCH("bbox_fixup_kernel", bbox_fixup_kernel<<<gf, 32, 0, st>>>(dg, P));
-    LAUNCH("keygen_kernel", keygen_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P, 0));
-    LAUNCH("bbox_kernel(slow path)", bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 1));
-    LAUNCH("keygen_kernel(rekey)", keygen_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P, 1));
-    // frame ids are sequential over the batch: group g's setup needs group g-1's setup kernel to have run
-    if (g > 0) CU(cudaStreamWaitEvent(st, c->ev_group[g - 1], 0));
-    LAUNCH("frame_setup_kernel", frame_setup_kernel<<<1, 32, 0, st>>>(dg, gf, counter));
-    CU(cudaEventRecord(c->ev_group[g], st));
-    LAUNCH("sort_hist_kernel", sort_hist_kernel<<<dim3(gtiles, gf), 256, 0, st>>>(dg));
-    for (int p = 0; p < 8; p++) LAUNCH("sort_pass_kernel", sort_pass_kernel<<<dim3(gtiles, gf), SORT_THREADS, 0, st>>>(dg, p));
-    LAUNCH("leaf_scan_kernel", leaf_scan_kernel<<<dim3((unsigned)((gn + LEAF_TILE - 1) / LEAF_TILE), gf), LEAF_THREADS, 0, st>>>(dg));
-    LAUNCH("leaf_emit_kernel", leaf_emit_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P));
-    if (color && prm.color_coding_type == 1) {
-      const size_t img_h = gn / 256 + 1, mcu_h = (img_h + 15) / 16, nblk = mcu_h * 16 * 6;
-      LAUNCH("jpeg_mcu_kernel", jpeg_mcu_kernel<<<dim3((unsigned)(mcu_h * 16), gf), 256, 0, st>>>(dg, c->d_tables));
-      LAUNCH("jpeg_huff_kernel", jpeg_huff_kernel<<<dim3((unsigned)((nblk + HUFF_THREADS - 1) / HUFF_THREADS), gf), HUFF_THREADS, 0, st>>>(dg, c->d_tables));
-      const size_t jb = 4 * gn + 8192;
-      LAUNCH("jpeg_stuff_kernel", jpeg_stuff_kernel<<<dim3((unsigned)((jb + STUFF_THREADS * STUFF_BYTES - 1) / (STUFF_THREADS * STUFF_BYTES)), gf), STUFF_THREADS, 0, st>>>(dg, c->d_tables));
-    }
-    const size_t hmax = std::max(tree_cap_for(gn), cpay_cap_for(gn));
-    LAUNCH("hist_kernel", hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), 3, gf), 256, 0, st>>>(dg));
-    LAUNCH("rc_encode_kernel", rc_encode_kernel<<<c->n_sm, 96, 0, st>>>(dg, f0, gf, cen, color));
-    LAUNCH("assemble_kernel", assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H));
-    CU(cudaMemcpyAsync(hf + f0, dg, sizeof(EncFrame) * gf, cudaMemcpyDeviceToHost, st));
-    CU(cudaGetLastError());
-  }
-  // ---- collect: per group wait for its record copy, then move the streams out with exact sizes
-  int rc = CCV2_OK;
-  for (int g = 0; g < ngroups; g++) {
-    cudaStream_t st = c->streams[g % NS];
-    // the D2H of the records is the last op queued on st for this group so far
-    cudaEvent_t ev = c->ev_group[g];
-    CU(cudaEventRecord(ev, st));
-    CU(cudaEventSynchronize(ev));
-    const int f0 = g * G, gf = std::min(G, nframes - f0);
-    for (int i = 0; i < gf; i++) {
-      EncFrame &f = hf[f0 + i];
-      out_len[f0 + i] = 0;
-      if (f.error) {
-        if (rc == CCV2_OK) {
-          rc = (f.error & FERR_DEPTH) ? CCV2_ERR_DEPTH : CCV2_ERR_WORKSPACE;
-          char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x", f0 + i, f.error); c->err = b;
-        }
-        continue;
-      }
-      if (f.out_len == 0) continue;
-      if (f.out_len > out_cap[f0 + i] || !out[f0 + i]) { if (rc == CCV2_OK) { rc = CCV2_ERR_CAPACITY; c->err = "output buffer too small"; } continue; }
-      CU(cudaMemcpyAsync(out[f0 + i], f.stream, f.out_len, out_dev[f0 + i] ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-      out_len[f0 + i] = f.out_len;
-    }
-    CU(cudaEventRecord(ev, st));
-    CU(cudaStreamWaitEvent(ms, ev, 0));
-  }
-  CU(cudaEventRecord(c->ev_end, ms));
-  CU(cudaEventSynchronize(c->ev_end));
-  CU(cudaEventElapsedTime(&c->device_ms, c->ev_start, c->ev_end));
-  CU(cudaMemcpy(&c->frame_id, counter, 4, cudaMemcpyDeviceToHost));
-  prof_collect(c);
-  c->launches = launches;
-  c->enc_host.assign(hf, hf + nframes);
-  for (int i = nframes - 1; i >= 0; i--) if (hf[i].out_len) { for (int k = 0; k < 3; k++) c->metrics[k] = hf[i].coded[k]; break; }
-  return rc;
-}
-
-int ccv2_debug_fetch(ccv2_codec *c, int frame, int what, void *host_buf, size_t cap, size_t *len) {
-  if (!c || frame < 0 || frame >= (int)c->enc_host.size() || !len) return CCV2_ERR_ARG;
-  CU(cudaSetDevice(c->device));
-  const EncFrame &f = c->enc_host[frame];
-  const void *src = nullptr; size_t n = 0;
-  ccv2_frame_info info;
-  switch (what) {
-    case 0: src = f.leaf_key; n = (size_t)f.V * 8; break;
-    case 1: src = f.tree; n = f.B; break;
-    case 2: src = f.avg; n = (size_t)f.V * 3; break;
-    case 3: src = f.cpay; n = f.ncolor; break;
-    case 4: src = f.vals[f.npasses & 1]; n = (size_t)f.n_finite * 4; break;
-    case 5:
-      memset(&info, 0, sizeof info);
-      info.depth = f.depth; info.n_finite = f.n_finite; info.n_leaves = f.V; info.n_tree_bytes = f.B; info.n_color_bytes = f.ncolor; info.error = f.error;
-      for (int a = 0; a < 3; a++) { info.bb_min[a] = f.bmin[a]; info.bb_max[a] = f.bmax[a]; info.coded[a] = f.coded[a]; }
-      *len = sizeof info;
-      if (cap < sizeof info || !host_buf) return CCV2_ERR_CAPACITY;
-      memcpy(host_buf, &info, sizeof info);
-      return CCV2_OK;
-    default: return CCV2_ERR_ARG;
-  }
-  *len = n;
-  if (n > cap || !host_buf) return CCV2_ERR_CAPACITY;
-  if (n) CU(cudaMemcpy(host_buf, src, n, cudaMemcpyDeviceToHost));
-  return CCV2_OK;
-}
-
-// ================================================================================================ decode
 static size_t carve_dec(uint8_t *base, size_t pcap, DecFrame *f, size_t *zero_off, size_t *zero_bytes) {
   Carver cv(base);
   const size_t img_h = pcap / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
@@ -597,93 +426,228 @@ static size_t carve_dec(uint8_t *base, size_t pcap, DecFrame *f, size_t *zero_of
   return (cv.off + 255) & ~size_t(255);
 }
 
-int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const size_t *in_len,
-                      void *const *pts_out, const size_t *pts_cap, size_t *npts_out) {
-  if (!c || nframes < 0 || (nframes && (!in || !in_len || !pts_out || !pts_cap || !npts_out))) return CCV2_ERR_ARG;
+// ================================================================================================ batch driver
+// mode 0: encode, 1: decode, 2: encode -> decode round trip (decode reads the encoder's device-resident streams, so the
+// host->device copies of later groups overlap the device->host copies of earlier ones: both PCIe directions busy).
+static int run_batch(ccv2_codec *c, int mode, int nframes,
+                     const void *const *pts, const size_t *npts, void *const *out, const size_t *out_cap, size_t *out_len,
+                     const void *const *in, const size_t *in_len, void *const *pts_out, const size_t *pts_cap, size_t *npts_out) {
+  const bool do_enc = mode != 1, do_dec = mode != 0, rt = mode == 2;
   c->err.clear(); c->launches = 0; c->device_ms = 0;
   if (nframes == 0) return CCV2_OK;
   CU(cudaSetDevice(c->device));
+  const ccv2_params &prm = c->prm;
+  const bool cen = prm.do_voxel_grid_centroid != 0, color = prm.do_color_encoding != 0;
   const int NS = c->profiling ? 1 : c->n_streams;
   const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(64, (nframes + NS - 1) / NS)));
   const int ngroups = (nframes + G - 1) / G;
-  std::vector<size_t> work_off(nframes + 1, 0), input_off(nframes + 1, 0), output_off(nframes + 1, 0), zb(nframes, 0);
-  std::vector<char> in_dev(nframes), out_dev(nframes);
-  for (int i = 0; i < nframes; i++) {
-    if (pts_cap[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; }
-    if ((in_len[i] && !in[i]) || (pts_cap[i] && !pts_out[i])) return CCV2_ERR_ARG;
-    size_t zo;
-    work_off[i + 1] = work_off[i] + carve_dec(nullptr, pts_cap[i], nullptr, &zo, &zb[i]);
-    in_dev[i] = in_len[i] ? is_device_ptr(in[i]) : 1;
-    out_dev[i] = pts_cap[i] ? is_device_ptr(pts_out[i]) : 1;
-    input_off[i + 1] = input_off[i] + (in_dev[i] ? 0 : ((in_len[i] + 64 + 255) & ~size_t(255)));
-    output_off[i + 1] = output_off[i] + (out_dev[i] ? 0 : ((32 * pts_cap[i] + 255) & ~size_t(255)));
-  }
-  CU(c->dec_work.ensure(work_off[nframes]));
-  CU(c->dec_input.ensure(input_off[nframes] + 256));
-  CU(c->dec_output.ensure(output_off[nframes] + 256));
-  CU(c->dec_frames.ensure(sizeof(DecFrame) * nframes));
-  CU(c->h_dframes.ensure(sizeof(DecFrame) * nframes));
-  while ((int)c->ev_group.size() < ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_group.push_back(ev); }
-  DecFrame *hf = (DecFrame *)c->h_dframes.p, *df = (DecFrame *)c->dec_frames.p;
-  memset(hf, 0, sizeof(DecFrame) * nframes);
-  for (int i = 0; i < nframes; i++) {
-    DecFrame &f = hf[i];
-    f.in = in_dev[i] ? (const uint8_t *)in[i] : (const uint8_t *)c->dec_input.p + input_off[i];
-    f.in_len = in_len[i];
-    f.out_pts = out_dev[i] ? (uint8_t *)pts_out[i] : (uint8_t *)c->dec_output.p + output_off[i];
-    f.out_cap = pts_cap[i];
-    carve_dec((uint8_t *)c->dec_work.p + work_off[i], pts_cap[i], &f, nullptr, nullptr);
-    if (in_len[i] == 0) f.error = FERR_BAD_STREAM;
-  }
+  while ((int)c->ev_group.size() < 2 * ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_group.push_back(ev); }
   cudaStream_t ms = c->main_stream;
+
+  // ------------------------------------------------------------------ encode side set-up
+  size_t nmax = 1, zoff = 0, zbytes = 0, slot_bytes = 0, frames_bytes = 0;
+  std::vector<size_t> input_off(nframes + 1, 0);
+  std::vector<char> in_dev(nframes, 1), out_dev(nframes, 0);
+  EncFrame *hf = nullptr, *df = nullptr;
+  EncParams P; HeaderParams H;
+  memset(&P, 0, sizeof P); memset(&H, 0, sizeof H);
+  if (do_enc) {
+    for (int i = 0; i < nframes; i++) { if (npts[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; } if (npts[i] && !pts[i]) return CCV2_ERR_ARG; nmax = std::max(nmax, npts[i]); }
+    // Slots: one per (stream, frame-in-group); persist + input staging: one per frame of the batch
+    slot_bytes = carve_enc_slot(nullptr, nmax, nullptr, prm, &zoff, &zbytes);
+    const int nslots = std::min(ngroups, NS) * G;
+    CU(c->enc_slots.ensure(slot_bytes * nslots));
+    std::vector<size_t> persist_off(nframes + 1, 0);
+    for (int i = 0; i < nframes; i++) {
+      persist_off[i + 1] = persist_off[i] + carve_enc_persist(nullptr, npts[i], nullptr, cen);
+      in_dev[i] = npts[i] ? is_device_ptr(pts[i]) : 1;
+      out_dev[i] = (out && out[i]) ? is_device_ptr(out[i]) : 0;
+      input_off[i + 1] = input_off[i] + (in_dev[i] ? 0 : ((32 * npts[i] + 255) & ~size_t(255)));
+    }
+    CU(c->enc_persist.ensure(persist_off[nframes]));
+    CU(c->enc_input.ensure(input_off[nframes] + 256));
+    frames_bytes = (sizeof(EncFrame) * nframes + 255) & ~size_t(255);
+    CU(c->enc_frames.ensure(frames_bytes + (size_t)nframes * 3 * 256 * 4));
+    CU(c->h_frames.ensure(sizeof(EncFrame) * nframes));
+    hf = (EncFrame *)c->h_frames.p; df = (EncFrame *)c->enc_frames.p;
+    memset(hf, 0, sizeof(EncFrame) * nframes);
+    for (int i = 0; i < nframes; i++) {
+      EncFrame &f = hf[i];
+      const int g = i / G, slot = (g % NS) * G + (i % G);
+      f.pts = in_dev[i] ? (const uint8_t *)pts[i] : (const uint8_t *)c->enc_input.p + input_off[i];
+      f.n = (uint32_t)npts[i];
+      f.n_finite = (uint32_t)npts[i];                               // keygen subtracts the non-finite points
+      f.violator = NONE_U32;
+      carve_enc_slot((uint8_t *)c->enc_slots.p + slot_bytes * slot, nmax, &f, prm, nullptr, nullptr);
+      carve_enc_persist((uint8_t *)c->enc_persist.p + persist_off[i], npts[i], &f, cen);
+      f.hist = (uint32_t *)((uint8_t *)c->enc_frames.p + frames_bytes) + (size_t)i * 3 * 256;
+      if (color && prm.color_coding_type != 1) f.avg = f.cpay;       // raw averages are the colour payload (types 0, 3)
+    }
+    P.res = prm.octree_resolution;
+    { int ex; double m = frexp(P.res, &ex); P.res_pow2 = (m == 0.5); P.inv_res = P.res_pow2 ? 1.0 / P.res : 0.0; }
+    P.do_color = color; P.color_type = prm.color_coding_type; P.do_centroid = cen;
+    P.color_reduction = (prm.color_coding_type == 0) ? std::max(0, 8 - (int)prm.color_bit_resolution) : 0;   // jp_color_coder_ is never configured
+    P.prefix_len = 16384;
+    H.octree_res = prm.octree_resolution; H.point_res = (double)(float)prm.point_resolution;
+    H.do_voxel_grid = 1; H.with_color = color; H.color_bits = prm.color_bit_resolution; H.do_centroid = cen;
+    H.connectivity = prm.code_connectivity != 0; H.scalable = prm.create_scalable_stream != 0; H.icp_offset = prm.do_icp_color_offset != 0; H._p = 0;
+    H.color_type = prm.color_coding_type; H.macroblock = prm.macroblock_size;
+  }
+
+  // ------------------------------------------------------------------ decode side set-up
+  std::vector<size_t> work_off(nframes + 1, 0), dinput_off(nframes + 1, 0), output_off(nframes + 1, 0), zb(nframes, 0);
+  std::vector<char> din_dev(nframes, 1), dout_dev(nframes, 1);
+  DecFrame *hd = nullptr, *dd = nullptr;
+  if (do_dec) {
+    for (int i = 0; i < nframes; i++) {
+      if (pts_cap[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; }
+      if ((!rt && in_len[i] && !in[i]) || (pts_cap[i] && !pts_out[i])) return CCV2_ERR_ARG;
+      size_t zo;
+      work_off[i + 1] = work_off[i] + carve_dec(nullptr, pts_cap[i], nullptr, &zo, &zb[i]);
+      din_dev[i] = rt ? 1 : (in_len[i] ? is_device_ptr(in[i]) : 1);
+      dout_dev[i] = pts_cap[i] ? is_device_ptr(pts_out[i]) : 1;
+      dinput_off[i + 1] = dinput_off[i] + (din_dev[i] ? 0 : ((in_len[i] + 64 + 255) & ~size_t(255)));
+      output_off[i + 1] = output_off[i] + (dout_dev[i] ? 0 : ((32 * pts_cap[i] + 255) & ~size_t(255)));
+    }
+    CU(c->dec_work.ensure(work_off[nframes]));
+    CU(c->dec_input.ensure(dinput_off[nframes] + 256));
+    CU(c->dec_output.ensure(output_off[nframes] + 256));
+    CU(c->dec_frames.ensure(sizeof(DecFrame) * nframes));
+    CU(c->h_dframes.ensure(sizeof(DecFrame) * nframes));
+    hd = (DecFrame *)c->h_dframes.p; dd = (DecFrame *)c->dec_frames.p;
+    memset(hd, 0, sizeof(DecFrame) * nframes);
+    for (int i = 0; i < nframes; i++) {
+      DecFrame &f = hd[i];
+      if (rt) { f.in = hf[i].stream; f.in_len = 0; }       // length filled in on the device by link_kernel
+      else {
+        f.in = din_dev[i] ? (const uint8_t *)in[i] : (const uint8_t *)c->dec_input.p + dinput_off[i];
+        f.in_len = in_len[i];
+        if (in_len[i] == 0) f.error = FERR_BAD_STREAM;
+      }
+      f.out_pts = dout_dev[i] ? (uint8_t *)pts_out[i] : (uint8_t *)c->dec_output.p + output_off[i];
+      f.out_cap = pts_cap[i];
+      carve_dec((uint8_t *)c->dec_work.p + work_off[i], pts_cap[i], &f, nullptr, nullptr);
+    }
+  }
+
+  // ------------------------------------------------------------------ enqueue
   CU(cudaEventRecord(c->ev_start, ms));
-  CU(cudaMemcpyAsync(df, hf, sizeof(DecFrame) * nframes, cudaMemcpyHostToDevice, ms));
+  if (do_enc) {
+    CU(cudaMemcpyAsync(df, hf, sizeof(EncFrame) * nframes, cudaMemcpyHostToDevice, ms));
+    CU(cudaMemsetAsync((uint8_t *)c->enc_frames.p + frames_bytes, 0, (size_t)nframes * 3 * 256 * 4, ms));
+  }
+  if (do_dec) CU(cudaMemcpyAsync(dd, hd, sizeof(DecFrame) * nframes, cudaMemcpyHostToDevice, ms));
   cudaEvent_t ev_setup = c->ev_fork;
   CU(cudaEventRecord(ev_setup, ms));
   uint64_t launches = 0;
+  uint32_t *counter = c->d_frame_counter;
   for (int g = 0; g < ngroups; g++) {
     cudaStream_t st = c->streams[g % NS];
     const int f0 = g * G, gf = std::min(G, nframes - f0);
-    DecFrame *dg = df + f0;
     CU(cudaStreamWaitEvent(st, ev_setup, 0));
-    size_t pmax = 1;
-    for (int i = 0; i < gf; i++) {
-      const int k = f0 + i;
-      pmax = std::max(pmax, pts_cap[k]);
-      if (!in_dev[k] && in_len[k]) CU(cudaMemcpyAsync((void *)hf[k].in, in[k], in_len[k], cudaMemcpyHostToDevice, st));
-      CU(cudaMemsetAsync((uint8_t *)c->dec_work.p + work_off[k], 0, zb[k], st));
+    if (do_enc) {
+      EncFrame *dg = df + f0;
+      size_t gn = 1;
+      for (int i = 0; i < gf; i++) {
+        gn = std::max(gn, npts[f0 + i]);
+        if (!in_dev[f0 + i] && npts[f0 + i]) CU(cudaMemcpyAsync((void *)hf[f0 + i].pts, pts[f0 + i], 32 * npts[f0 + i], cudaMemcpyHostToDevice, st));
+        const int slot = (g % NS) * G + i;
+        CU(cudaMemsetAsync((uint8_t *)c->enc_slots.p + slot_bytes * slot + zoff, 0, zbytes, st));
+      }
+      const unsigned gx256 = (unsigned)((gn + 255) / 256), gtiles = (unsigned)((gn + SORT_TILE - 1) / SORT_TILE);
+      LAUNCH("bbox_kernel", bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 0));
+      LAUNCH("bbox_fixup_kernel", bbox_fixup_kernel<<<gf, 32, 0, st>>>(dg, P));
+      LAUNCH("keygen_kernel", keygen_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P, 0));
+      LAUNCH("bbox_kernel(slow path)", bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 1));
+      LAUNCH("keygen_kernel(rekey)", keygen_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P, 1));
+      // frame ids are sequential over the batch: group g's setup needs group g-1's setup kernel to have run
+      if (g > 0) CU(cudaStreamWaitEvent(st, c->ev_group[g - 1], 0));
+      LAUNCH("frame_setup_kernel", frame_setup_kernel<<<1, 32, 0, st>>>(dg, gf, counter));
+      CU(cudaEventRecord(c->ev_group[g], st));
+      LAUNCH("sort_hist_kernel", sort_hist_kernel<<<dim3(gtiles, gf), 256, 0, st>>>(dg));
+      for (int p = 0; p < 8; p++) LAUNCH("sort_pass_kernel", sort_pass_kernel<<<dim3(gtiles, gf), SORT_THREADS, 0, st>>>(dg, p));
+      LAUNCH("leaf_scan_kernel", leaf_scan_kernel<<<dim3((unsigned)((gn + LEAF_TILE - 1) / LEAF_TILE), gf), LEAF_THREADS, 0, st>>>(dg));
+      LAUNCH("leaf_emit_kernel", leaf_emit_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P));
+      if (color && prm.color_coding_type == 1) {
+        const size_t img_h = gn / 256 + 1, mcu_h = (img_h + 15) / 16, nblk = mcu_h * 16 * 6;
+        LAUNCH("jpeg_mcu_kernel", jpeg_mcu_kernel<<<dim3((unsigned)(mcu_h * 16), gf), 256, 0, st>>>(dg, c->d_tables));
+        LAUNCH("jpeg_huff_kernel", jpeg_huff_kernel<<<dim3((unsigned)((nblk + HUFF_THREADS - 1) / HUFF_THREADS), gf), HUFF_THREADS, 0, st>>>(dg, c->d_tables));
+        const size_t jb = 4 * gn + 8192;
+        LAUNCH("jpeg_stuff_kernel", jpeg_stuff_kernel<<<dim3((unsigned)((jb + STUFF_THREADS * STUFF_BYTES - 1) / (STUFF_THREADS * STUFF_BYTES)), gf), STUFF_THREADS, 0, st>>>(dg, c->d_tables));
+      }
+      const size_t hmax = std::max(tree_cap_for(gn), cpay_cap_for(gn));
+      LAUNCH("hist_kernel", hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), 3, gf), 256, 0, st>>>(dg));
+      LAUNCH("rc_encode_kernel", rc_encode_kernel<<<c->n_sm, 96, 0, st>>>(dg, f0, gf, cen, color));
+      LAUNCH("assemble_kernel", assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H));
+      CU(cudaMemcpyAsync(hf + f0, dg, sizeof(EncFrame) * gf, cudaMemcpyDeviceToHost, st));
     }
-    LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf, c->use_ring));
-    LAUNCH("dec_expand_kernel", dec_expand_kernel<<<dim3((unsigned)((pmax + 255) / 256), gf), 256, 0, st>>>(dg));
-    LAUNCH("jpeg_destuff_kernel", jpeg_destuff_kernel<<<gf, 1024, 0, st>>>(dg));
-    LAUNCH("dec_serial_kernel", dec_serial_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf));
-    const size_t img_h = pmax / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
-    LAUNCH("jpeg_idct_kernel", jpeg_idct_kernel<<<dim3((unsigned)((nblocks + 31) / 32), gf), 256, 0, st>>>(dg, c->d_tables));
-    LAUNCH("dec_points_kernel", dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg));
-    CU(cudaMemcpyAsync(hf + f0, dg, sizeof(DecFrame) * gf, cudaMemcpyDeviceToHost, st));
+    if (do_dec) {
+      DecFrame *dg = dd + f0;
+      size_t pmax = 1;
+      for (int i = 0; i < gf; i++) {
+        const int k = f0 + i;
+        pmax = std::max(pmax, pts_cap[k]);
+        if (!rt && !din_dev[k] && in_len[k]) CU(cudaMemcpyAsync((void *)hd[k].in, in[k], in_len[k], cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync((uint8_t *)c->dec_work.p + work_off[k], 0, zb[k], st));
+      }
+      if (rt) LAUNCH("link_kernel", link_kernel<<<(gf + 63) / 64, 64, 0, st>>>(df + f0, dg, gf));
+      LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf, c->use_ring));
+      LAUNCH("dec_expand_kernel", dec_expand_kernel<<<dim3((unsigned)((pmax + 255) / 256), gf), 256, 0, st>>>(dg));
+      LAUNCH("jpeg_destuff_kernel", jpeg_destuff_kernel<<<gf, 1024, 0, st>>>(dg));
+      LAUNCH("dec_serial_kernel", dec_serial_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf));
+      const size_t img_h = pmax / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
+      LAUNCH("jpeg_idct_kernel", jpeg_idct_kernel<<<dim3((unsigned)((nblocks + 31) / 32), gf), 256, 0, st>>>(dg, c->d_tables));
+      LAUNCH("dec_points_kernel", dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg));
+      CU(cudaMemcpyAsync(hd + f0, dg, sizeof(DecFrame) * gf, cudaMemcpyDeviceToHost, st));
+    }
     CU(cudaGetLastError());
   }
+
+  // ------------------------------------------------------------------ collect: per group wait for its record copies,
+  // then move the results out with exact sizes (later groups keep running meanwhile)
   int rc = CCV2_OK;
   for (int g = 0; g < ngroups; g++) {
     cudaStream_t st = c->streams[g % NS];
-    cudaEvent_t ev = c->ev_group[g];
+    cudaEvent_t ev = c->ev_group[ngroups + g];
     CU(cudaEventRecord(ev, st));
     CU(cudaEventSynchronize(ev));
     const int f0 = g * G, gf = std::min(G, nframes - f0);
     for (int i = 0; i < gf; i++) {
       const int k = f0 + i;
-      DecFrame &f = hf[k];
-      npts_out[k] = 0;
-      if (f.error) {
-        if (rc == CCV2_OK) {
-          rc = (f.error & FERR_OUT_CAP) ? CCV2_ERR_CAPACITY : (f.error & FERR_DEPTH) ? CCV2_ERR_DEPTH : (f.error & FERR_UNSUPPORTED) ? CCV2_ERR_UNSUPPORTED
-             : (f.error & (FERR_TREE_CAP | FERR_JPEG_CAP)) ? CCV2_ERR_WORKSPACE : CCV2_ERR_STREAM;
-          char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x", k, f.error); c->err = b;
-        }
-        continue;
+      bool enc_ok = true;
+      if (do_enc) {
+        EncFrame &f = hf[k];
+        if (out_len) out_len[k] = 0;
+        if (f.error) {
+          enc_ok = false;
+          if (rc == CCV2_OK) {
+            rc = (f.error & FERR_DEPTH) ? CCV2_ERR_DEPTH : CCV2_ERR_WORKSPACE;
+            char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x (encode)", k, f.error); c->err = b;
+          }
+        } else if (f.out_len && out && out[k]) {
+          if (f.out_len > out_cap[k]) { if (rc == CCV2_OK) { rc = CCV2_ERR_CAPACITY; c->err = "output buffer too small"; } }
+          else {
+            CU(cudaMemcpyAsync(out[k], f.stream, f.out_len, out_dev[k] ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+            out_len[k] = f.out_len;
+          }
+        } else if (f.out_len && !rt) { if (rc == CCV2_OK) { rc = CCV2_ERR_CAPACITY; c->err = "output buffer too small"; } }
+        else if (f.out_len && out_len) out_len[k] = f.out_len;      // round trip without a stream buffer: report the size only
       }
-      npts_out[k] = f.V;
-      if (!out_dev[k] && f.V) CU(cudaMemcpyAsync(pts_out[k], f.out_pts, 32ull * f.V, cudaMemcpyDeviceToHost, st));
+      if (do_dec) {
+        DecFrame &f = hd[k];
+        npts_out[k] = 0;
+        if (rt && (!enc_ok || hf[k].out_len == 0)) continue;       // empty frame: nothing was written, nothing to decode
+        if (f.error) {
+          if (rc == CCV2_OK) {
+            rc = (f.error & FERR_OUT_CAP) ? CCV2_ERR_CAPACITY : (f.error & FERR_DEPTH) ? CCV2_ERR_DEPTH : (f.error & FERR_UNSUPPORTED) ? CCV2_ERR_UNSUPPORTED
+               : (f.error & (FERR_TREE_CAP | FERR_JPEG_CAP)) ? CCV2_ERR_WORKSPACE : CCV2_ERR_STREAM;
+            char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x (decode)", k, f.error); c->err = b;
+          }
+          continue;
+        }
+        npts_out[k] = f.V;
+        if (!dout_dev[k] && f.V) CU(cudaMemcpyAsync(pts_out[k], f.out_pts, 32ull * f.V, cudaMemcpyDeviceToHost, st));
+      }
     }
     CU(cudaEventRecord(ev, st));
     CU(cudaStreamWaitEvent(ms, ev, 0));
@@ -693,8 +657,62 @@ int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const s
   CU(cudaEventElapsedTime(&c->device_ms, c->ev_start, c->ev_end));
   prof_collect(c);
   c->launches = launches;
-  for (int i = nframes - 1; i >= 0; i--) if (!hf[i].error) { for (int k = 0; k < 3; k++) c->metrics[k] = hf[i].coded[k]; c->frame_id = hf[i].frame_id; break; }
+  if (do_enc) {
+    CU(cudaMemcpy(&c->frame_id, counter, 4, cudaMemcpyDeviceToHost));
+    c->enc_host.assign(hf, hf + nframes);
+    for (int i = nframes - 1; i >= 0; i--) if (hf[i].out_len) { for (int k = 0; k < 3; k++) c->metrics[k] = hf[i].coded[k]; break; }
+  } else {
+    for (int i = nframes - 1; i >= 0; i--) if (!hd[i].error) { for (int k = 0; k < 3; k++) c->metrics[k] = hd[i].coded[k]; c->frame_id = hd[i].frame_id; break; }
+  }
   return rc;
+}
+
+int ccv2_encode_batch(ccv2_codec *c, int nframes, const void *const *pts, const size_t *npts,
+                      void *const *out, const size_t *out_cap, size_t *out_len) {
+  if (!c || nframes < 0 || (nframes && (!pts || !npts || !out || !out_cap || !out_len))) return CCV2_ERR_ARG;
+  return run_batch(c, 0, nframes, pts, npts, out, out_cap, out_len, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const size_t *in_len,
+                      void *const *pts_out, const size_t *pts_cap, size_t *npts_out) {
+  if (!c || nframes < 0 || (nframes && (!in || !in_len || !pts_out || !pts_cap || !npts_out))) return CCV2_ERR_ARG;
+  return run_batch(c, 1, nframes, nullptr, nullptr, nullptr, nullptr, nullptr, in, in_len, pts_out, pts_cap, npts_out);
+}
+
+int ccv2_roundtrip_batch(ccv2_codec *c, int nframes, const void *const *pts, const size_t *npts,
+                         void *const *out, const size_t *out_cap, size_t *out_len,
+                         void *const *pts_out, const size_t *pts_cap, size_t *npts_out) {
+  if (!c || nframes < 0 || (nframes && (!pts || !npts || !pts_out || !pts_cap || !npts_out))) return CCV2_ERR_ARG;
+  if (out && (!out_cap || !out_len)) return CCV2_ERR_ARG;
+  return run_batch(c, 2, nframes, pts, npts, out, out_cap, out_len, nullptr, nullptr, pts_out, pts_cap, npts_out);
+}
+
+int ccv2_debug_fetch(ccv2_codec *c, int frame, int what, void *host_buf, size_t cap, size_t *len) {
+  if (!c || frame < 0 || frame >= (int)c->enc_host.size() || !len) return CCV2_ERR_ARG;
+  CU(cudaSetDevice(c->device));
+  const EncFrame &f = c->enc_host[frame];
+  const void *src = nullptr; size_t n = 0;
+  ccv2_frame_info info;
+  switch (what) {
+    case 0: src = f.leaf_key; n = (size_t)f.V * 8; break;
+    case 1: src = f.tree; n = f.B; break;
+    case 2: src = f.avg; n = (size_t)f.V * 3; break;
+    case 3: src = f.cpay; n = f.ncolor; break;
+    case 4: src = f.vals[f.npasses & 1]; n = (size_t)f.n_finite * 4; break;
+    case 5:
+      memset(&info, 0, sizeof info);
+      info.depth = f.depth; info.n_finite = f.n_finite; info.n_leaves = f.V; info.n_tree_bytes = f.B; info.n_color_bytes = f.ncolor; info.error = f.error;
+      for (int a = 0; a < 3; a++) { info.bb_min[a] = f.bmin[a]; info.bb_max[a] = f.bmax[a]; info.coded[a] = f.coded[a]; }
+      *len = sizeof info;
+      if (cap < sizeof info || !host_buf) return CCV2_ERR_CAPACITY;
+      memcpy(host_buf, &info, sizeof info);
+      return CCV2_OK;
+    default: return CCV2_ERR_ARG;
+  }
+  *len = n;
+  if (n > cap || !host_buf) return CCV2_ERR_CAPACITY;
+  if (n) CU(cudaMemcpy(host_buf, src, n, cudaMemcpyDeviceToHost));
+  return CCV2_OK;
 }
 
 }  // extern "C"

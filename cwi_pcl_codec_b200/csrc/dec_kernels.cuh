@@ -593,3 +593,12 @@ __global__ void __launch_bounds__(NODE_THREADS) dec_points_kernel(DecFrame *fram
     i++;
   }
 }
+
+// Round trip: hands the encoder's device-resident stream of every frame of a group to the decoder's frame record.
+__global__ void link_kernel(const EncFrame *enc, DecFrame *dec, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dec[i].in = enc[i].stream;
+  dec[i].in_len = enc[i].out_len;
+  if (enc[i].error || enc[i].out_len == 0) dec[i].error = FERR_BAD_STREAM;   // empty / failed frame: the host skips it
+}

@@ -36,7 +36,7 @@ typedef enum ccv2_status {
 /* The constructor surface of OctreePointCloudCodecV2 (codec.h:108-143), argument for argument, plus the two
  * setters evaluate_compression calls right after construction (eval.hpp:415-417). */
 typedef struct ccv2_params {
-  int32_t profile;                 /* compression_Profiles_e; only MANUAL_CONFIGURATION (= 12) is implemented */
+  int32_t profile;                 /* compression_Profiles_e; only MANUAL_CONFIGURATION (= 13) is implemented */
   int32_t show_statistics;         /* showStatistics_arg (accepted, ignored: PCL_INFO printing is not reproduced) */
   double point_resolution;         /* pointResolution_arg   (eval.hpp:381: 2^-(octree_bits+enh_bits)) */
   double octree_resolution;        /* octreeResolution_arg  (eval.hpp:383: 2^-octree_bits) */
@@ -55,7 +55,7 @@ typedef struct ccv2_params {
   int32_t do_icp_color_offset;     /* setDoICPColorOffset (codec.h:164-167); header field, default 0 */
 } ccv2_params;
 
-#define CCV2_MANUAL_CONFIGURATION 12   /* pcl::io::MANUAL_CONFIGURATION */
+#define CCV2_MANUAL_CONFIGURATION 13   /* pcl::io::MANUAL_CONFIGURATION (12 profiles, COMPRESSION_PROFILE_COUNT, then MANUAL) */
 
 typedef struct ccv2_codec ccv2_codec;
 
@@ -83,6 +83,14 @@ int ccv2_encode_batch(ccv2_codec *c, int nframes, const void *const *pts, const 
  * pts_out[i]: buffer for pts_cap[i] points (32 bytes each); npts_out[i] receives the decoded count. */
 int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const size_t *in_len,
                       void *const *pts_out, const size_t *pts_cap, size_t *npts_out);
+
+/* Encode then decode every frame in one pipelined call -- what evaluate_compression does per frame (eval.hpp:818-843:
+ * do_encoding then do_decoding on the stream just produced).  The decoder reads the encoder's device-resident stream,
+ * so the host->device copies of later frames overlap the device->host copies of earlier ones.  out may be NULL (or
+ * hold NULL entries) when the caller does not want the compressed bytes back; out_len still receives the sizes. */
+int ccv2_roundtrip_batch(ccv2_codec *c, int nframes, const void *const *pts, const size_t *npts,
+                         void *const *out, const size_t *out_cap, size_t *out_len,
+                         void *const *pts_out, const size_t *pts_cap, size_t *npts_out);
 
 /* Reads point_count from a frame header in HOST memory (SURVEY App. A offset 55) so a caller can size
  * pts_out before decoding.  Replaces nothing in the reference (its decoder grows a std::vector). */

@@ -1,4 +1,5 @@
 import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: see csrc/ccv2_api.cu (stream -> hardware queue aliasing)
 import sys
 
 import pytest

@@ -206,3 +206,34 @@ def test_reference_facade(K, oracle):
     assert np.array_equal(cdc.decodePointCloud(s), oracle.decode(ref)[0])
     assert cdc.decodePointCloud(b"garbage" * 20).shape[0] == 0
     assert cdc.getPerformanceMetrics()[0] > 0
+
+
+def test_roundtrip_call_matches_separate_calls(K, oracle):
+    clouds = [synth.gen_surface(20000 + 1000 * i, 60 + i) for i in range(11)] + [np.zeros(0, synth.POINT_DTYPE)]
+    kp = K.default_params(octree_bits=9)
+    c = K.Codec(kp)
+    arrs = [np.ascontiguousarray(cl) for cl in clouds]
+    ns = [a.nbytes // 32 for a in arrs]
+    caps = [6 * n + 65536 for n in ns]
+    strs = [np.zeros(cp, np.uint8) for cp in caps]
+    outs = [np.zeros((max(1, n), 32), np.uint8) for n in ns]
+    lens, cnts = c.roundtrip_batch_raw([a.ctypes.data if a.size else None for a in arrs], ns, [s.ctypes.data for s in strs], caps,
+                                       [o.ctypes.data for o in outs], [max(1, n) for n in ns])
+    op = oparams(oracle, kp)
+    fid = 0
+    for i, cl in enumerate(clouds):
+        ref, _ = oracle.encode(cl, op, frame_id=fid + 1)
+        if ref:
+            fid += 1
+        assert strs[i][:lens[i]].tobytes() == ref
+        if ref:
+            rd, _ = oracle.decode(ref)
+            assert cnts[i] == rd.shape[0] and np.array_equal(outs[i][:cnts[i]], rd)
+        else:
+            assert cnts[i] == 0 and lens[i] == 0
+    # streams optional: sizes are still reported
+    c.frame_id = 0
+    lens2, cnts2 = c.roundtrip_batch_raw([a.ctypes.data if a.size else None for a in arrs], ns, None, None,
+                                         [o.ctypes.data for o in outs], [max(1, n) for n in ns])
+    assert lens2 == lens and cnts2 == cnts
+    c.close()

@@ -1,5 +1,6 @@
 """Developer tool (GPU box): encode+decode F frames of N points once or twice; prints device times. Used under ncu."""
 import os, sys, time
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: see csrc/ccv2_api.cu (stream -> hardware queue aliasing)
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cwi_pcl_codec_b200 import codec as K, synth

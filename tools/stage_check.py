@@ -6,6 +6,7 @@ diffs against the oracle's decoder.  Never stops at the first mismatch -- prints
 usage: python tools/stage_check.py [--big]
 """
 import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: see csrc/ccv2_api.cu (stream -> hardware queue aliasing)
 import sys
 import time
 
