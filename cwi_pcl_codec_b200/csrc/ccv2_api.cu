@@ -333,6 +333,7 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   if ((e = cudaEventCreate(&c->ev_start)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if ((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  if ((e = cudaFuncSetAttribute(sort_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_BYTES)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
   JpegTables T; build_jpeg_tables(p->jpeg_quality, T);
   if ((e = cudaMalloc(&c->d_tables, sizeof T)) != cudaSuccess) return fail(e, "cudaMalloc");
   if ((e = cudaMemcpy(c->d_tables, &T, sizeof T, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "cudaMemcpy");
@@ -565,7 +566,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       LAUNCH("frame_setup_kernel", frame_setup_kernel<<<1, 32, 0, st>>>(dg, gf, counter));
       CU(cudaEventRecord(c->ev_group[g], st));
       LAUNCH("sort_hist_kernel", sort_hist_kernel<<<dim3(gtiles, gf), 256, 0, st>>>(dg));
-      for (int p = 0; p < 8; p++) LAUNCH("sort_pass_kernel", sort_pass_kernel<<<dim3(gtiles, gf), SORT_THREADS, 0, st>>>(dg, p));
+      for (int p = 0; p < 8; p++) LAUNCH("sort_pass_kernel", sort_pass_kernel<<<dim3(gtiles, gf), SORT_THREADS, SORT_SMEM_BYTES, st>>>(dg, p));
       LAUNCH("leaf_scan_kernel", leaf_scan_kernel<<<dim3((unsigned)((gn + LEAF_TILE - 1) / LEAF_TILE), gf), LEAF_THREADS, 0, st>>>(dg));
       LAUNCH("leaf_emit_kernel", leaf_emit_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P));
       if (color && prm.color_coding_type == 1) {

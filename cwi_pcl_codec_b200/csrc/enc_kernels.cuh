@@ -200,15 +200,19 @@ __global__ void __launch_bounds__(256) sort_hist_kernel(EncFrame *frames) {
   }
 }
 
+#define SORT_SMEM_BYTES (SORT_TILE * 12)     // dynamic shared memory: the tile's keys (8 B) and values (4 B) in digit order
 __global__ void __launch_bounds__(SORT_THREADS) sort_pass_kernel(EncFrame *frames, int pass) {
   EncFrame &f = frames[blockIdx.y];
   if ((uint32_t)pass >= f.npasses) return;
   const uint32_t n = f.n;
   const uint32_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
   if (blockIdx.x >= ntiles) return;
+  extern __shared__ __align__(16) uint8_t sort_dyn[];
+  uint64_t *skey = (uint64_t *)sort_dyn;
+  uint32_t *sval = (uint32_t *)(sort_dyn + SORT_TILE * 8);
   __shared__ uint32_t s_tile;
   __shared__ uint32_t whist[SORT_THREADS / 32][256];
-  __shared__ uint32_t tile_off[256];
+  __shared__ uint32_t tile_off[256], dbase[256];
   __shared__ uint64_t s_scan[33];
   if (threadIdx.x == 0) s_tile = atomicAdd(&f.ticket[TK_SORT0 + pass], 1u);
   for (uint32_t k = threadIdx.x; k < (SORT_THREADS / 32) * 256; k += blockDim.x) (&whist[0][0])[k] = 0;
@@ -221,9 +225,9 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pass_kernel(EncFrame *frame
   uint64_t *dkeys = f.keys[(pass + 1) & 1]; uint32_t *dvals = f.vals[(pass + 1) & 1];
   const uint32_t shift = 8 * pass;
   const uint32_t wbase = tile * SORT_TILE + w * (32 * SORT_ITEMS);
-  uint64_t key[SORT_ITEMS]; uint16_t rank[SORT_ITEMS];
+  uint64_t key[SORT_ITEMS]; uint32_t val[SORT_ITEMS]; uint16_t rank[SORT_ITEMS];
 #pragma unroll
-  for (int k = 0; k < SORT_ITEMS; k++) { uint32_t i = wbase + k * 32 + lane; key[k] = i < n ? skeys[i] : ~0ull; }
+  for (int k = 0; k < SORT_ITEMS; k++) { uint32_t i = wbase + k * 32 + lane; key[k] = i < n ? skeys[i] : ~0ull; val[k] = i < n ? svals[i] : 0u; }
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; k++) {
     uint32_t i = wbase + k * 32 + lane;
@@ -258,17 +262,27 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pass_kernel(EncFrame *frame
       *(volatile uint32_t *)&st[(size_t)tile * 256] = (2u << 30) | (excl + run);
     }
     tile_off[d] = gbase + excl;
+    dbase[d] = (uint32_t)block_excl_scan_u64(run, &tot, s_scan);     // where digit d starts inside this tile
   }
   __syncthreads();
+  // stage the tile in digit order in shared memory, then write it out with consecutive threads on consecutive
+  // addresses inside every digit run (direct scatter wrote one 32-byte sector per 8-byte key)
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; k++) {
     uint32_t i = wbase + k * 32 + lane;
     if (i < n) {
       uint32_t d = (uint32_t)((key[k] >> shift) & 255);
-      uint32_t pos = tile_off[d] + whist[w][d] + rank[k];
-      dkeys[pos] = key[k];
-      dvals[pos] = svals[i];
+      uint32_t lp = dbase[d] + whist[w][d] + rank[k];
+      skey[lp] = key[k]; sval[lp] = val[k];
     }
+  }
+  __syncthreads();
+  const uint32_t tile_n = min((uint32_t)SORT_TILE, n - tile * SORT_TILE);
+  for (uint32_t idx = threadIdx.x; idx < tile_n; idx += SORT_THREADS) {
+    const uint64_t kk = skey[idx];
+    const uint32_t d = (uint32_t)((kk >> shift) & 255);
+    const uint32_t pos = tile_off[d] + (idx - dbase[d]);
+    dkeys[pos] = kk; dvals[pos] = sval[idx];
   }
 }
 
