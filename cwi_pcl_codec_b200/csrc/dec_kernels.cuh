@@ -13,7 +13,7 @@ __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p) { return 
 
 __device__ inline void jpeg_parse_header(DecFrame &f);
 
-__device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *lut);
+__device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *lut, uint32_t *stack);
 
 // ---- stage 1: header + entropy decoding of the layers (impl.hpp:231-261, 1766-1835), one block per frame (steered):
 // warp 0 parses the header and range-decodes tree -> [centroid] -> colour (serially dependent: no stored lengths);
@@ -24,8 +24,9 @@ __global__ void __launch_bounds__(64) dec_entropy_kernel(DecFrame *frames, int f
   DecFrame &f = frames[fi];
   __shared__ uint32_t freq[257];
   __shared__ WalkRing rg;
-  __shared__ uint32_t lut[256];                            // per 8-bit child mask: popcount << 16 | mask without its lowest bit << 8 | index of the lowest bit
-  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = ((uint32_t)__popc(i) << 16) | ((i & (i - 1)) << 8) | (i ? (uint32_t)(__ffs(i) - 1) : 0u);
+  __shared__ uint32_t lut[256];                            // per 8-bit child mask: popcount << 16 | index of the lowest bit << 8 | mask without its lowest bit
+  __shared__ uint32_t wstack[32];                          // walker: remaining-children mask per open level
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = ((uint32_t)__popc(i) << 16) | ((i ? (uint32_t)(__ffs(i) - 1) : 0u) << 8) | (i & (i - 1));
   const uint32_t lane = lane_id();
   const bool decoder = threadIdx.x < 32;
   const uint8_t *in = f.in;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(64) dec_entropy_kernel(DecFrame *frames, int f
   __syncthreads();
   const bool ring = rg.go != 0;
   if (!decoder) {                                           // walker warp: lane 0 walks, the other lanes retire
-    if (lane == 0 && ring) dfs_walk_ring(f, &rg, lut);
+    if (lane == 0 && ring) dfs_walk_ring(f, &rg, lut, wstack);
     return;
   }
   if (err) { if (lane == 0) { f.error |= err; f.V = 0; f.B = 0; f.point_count = 0; rg.dead = 1; rg.done = 1; } return; }
@@ -190,7 +191,7 @@ __device__ inline void dfs_walk_fast(DecFrame &f) {
 // while the range decoder is still producing them.  It only has to visit the branches above the bottom level: for
 // a branch at level depth-2 it records (prefix, child mask, stream offset of the first child) and skips the child
 // bytes -- dec_expand_kernel turns those records into bottom-level records in parallel afterwards.
-__device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *lut) {
+__device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *lut, uint32_t *stack) {
   const uint32_t B = rg->B, d = rg->depth;
   uint32_t pos = 0, cw = NONE_U32, win = 0, avail = 0, pub = 0;
   bool bad = false;
@@ -201,33 +202,28 @@ __device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *
       win = rg->ring[wi & (RING_WORDS - 1)]; cw = wi;
       if ((wi >> 4) != pub) { pub = wi >> 4; rg->cons = wi; }
     }
-    dst = (win >> (8 * (pos & 3))) & 255u; pos++;
+    dst = __byte_perm(win, 0, 0x4440u | (pos & 3u)); pos++;
     return true;
   };
   uint32_t m = 0, n2 = 0, nb = 0;
   const uint32_t cap = f.node_cap;
+  uint64_t *const l2p = f.l2_prefix; uint8_t *const l2m = f.l2_mask; uint32_t *const l2o = f.l2_off;
   if (!read_byte(m)) bad = true;
   else if (d == 1) { f.node_prefix[0] = 0; f.node_byte[0] = (uint8_t)m; nb = 1; }
   else {
-    uint64_t s0 = 0, s1 = 0, prefix = 0; uint32_t L = 0;
+    uint64_t prefix = 0; uint32_t L = 0;
+    const uint32_t Lb = d - 2;                              // branches at this level have bottom-level children
     for (;;) {
-      if (L + 2 == d) {                                     // children are bottom-level branches: record and skip them
+      if (L == Lb) {                                        // record (prefix, mask, offset of the first child) and skip the children
         const uint32_t k = lut[m] >> 16;
         if (pos + k > B || n2 >= cap) { bad = true; break; }
-        f.l2_prefix[n2] = prefix; f.l2_mask[n2] = (uint8_t)m; f.l2_off[n2] = pos; n2++;
+        l2p[n2] = prefix; l2m[n2] = (uint8_t)m; l2o[n2] = pos; n2++;
         pos += k; m = 0;
       }
-      bool done = false;
-      while (m == 0) {                                      // pop exhausted branches
-        if (L == 0) { done = true; break; }
-        L--; prefix >>= 3;
-        m = (uint32_t)((L < 8 ? s0 >> (8 * L) : s1 >> (8 * (L - 8))) & 255u);
-      }
-      if (done) break;
-      const uint32_t e = lut[m], c = e & 7u, mn = (e >> 8) & 255u;   // descend into the next child
-      if (L < 8) { const uint32_t sh = 8 * L; s0 = (s0 & ~(255ull << sh)) | ((uint64_t)mn << sh); }
-      else { const uint32_t sh = 8 * (L - 8); s1 = (s1 & ~(255ull << sh)) | ((uint64_t)mn << sh); }
-      prefix = (prefix << 3) | c; L++;
+      while (m == 0 && L) { L--; prefix >>= 3; m = stack[L]; }   // pop exhausted branches
+      if (m == 0) break;                                     // the root is exhausted: done
+      const uint32_t e = lut[m];                             // descend into the next child
+      stack[L] = e & 255u; prefix = (prefix << 3) | ((e >> 8) & 7u); L++;
       if (pos >= B) { bad = true; break; }
       if (!read_byte(m)) { bad = true; break; }
     }
