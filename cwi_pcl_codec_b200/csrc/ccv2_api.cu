@@ -592,7 +592,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
         CU(cudaMemsetAsync((uint8_t *)c->dec_work.p + work_off[k], 0, zb[k], st));
       }
       if (rt) LAUNCH("link_kernel", link_kernel<<<(gf + 63) / 64, 64, 0, st>>>(df + f0, dg, gf));
-      LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf, c->use_ring));
+      LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<c->n_sm, 96, 0, st>>>(dg, f0, gf, c->use_ring));
       LAUNCH("dec_expand_kernel", dec_expand_kernel<<<dim3((unsigned)((pmax + 255) / 256), gf), 256, 0, st>>>(dg));
       LAUNCH("jpeg_destuff_kernel", jpeg_destuff_kernel<<<gf, 1024, 0, st>>>(dg));
       LAUNCH("dec_serial_kernel", dec_serial_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf));

@@ -88,7 +88,7 @@ struct DecFrame {
   uint32_t data_with_color, do_centroid, color_bits;
   uint32_t B, ncen, ncol;
   uint32_t n_bottom, V;
-  uint32_t walk_done, _padw;                     // DFS walk already done by the pipelined walker warp
+  uint32_t walk_done, huff_done;                 // DFS walk / JPEG Huffman decode already done inside dec_entropy_kernel
   uint32_t img_w, img_h, mcu_w, mcu_h, n_blocks;
   uint32_t ticket[TK_COUNT];
   uint32_t error, _pad0;

@@ -11,30 +11,42 @@ __device__ __forceinline__ double ld_f64_unaligned(const uint8_t *p) { uint64_t 
 __device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t *p) { uint64_t v = 0; for (int k = 7; k >= 0; k--) v = (v << 8) | p[k]; return v; }
 __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 
-__device__ inline void jpeg_parse_header(DecFrame &f);
+__device__ inline uint32_t jpeg_parse_header(DecFrame &f);
+struct HuffDec { int mincode[17]; int maxcode[17]; int valptr[17]; uint8_t vals[256]; uint16_t look[512]; };   // look: (len << 8) | sym for codes <= 9 bits
+__device__ inline void jpeg_huff_decode(DecFrame &f, HuffDec *hd);
+__device__ inline void warp_destuff(DecFrame &f);
 
 __device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *lut, uint32_t *stack);
 
 // ---- stage 1: header + entropy decoding of the layers (impl.hpp:231-261, 1766-1835), one block per frame (steered):
 // warp 0 parses the header and range-decodes tree -> [centroid] -> colour (serially dependent: no stored lengths);
 // warp 1 walks the occupancy bytes out of a shared-memory ring while warp 0 is still producing them.
-__global__ void __launch_bounds__(64) dec_entropy_kernel(DecFrame *frames, int first_slot, int group_frames, int use_ring) {
+// warp 2 decodes the colour layer speculatively while warp 0 is still busy with the tree layer: the colour layer is the
+// last layer of the frame and starts with an unmistakable signature (u64 size below 2^32, then 257 strictly increasing
+// u32 below 2^16 starting at 0), so its offset can be found by scanning backwards from the end; warp 0 accepts the
+// result only if its own position after the preceding layers lands exactly there, otherwise it decodes the layer
+// itself as the reference would.
+struct SpecColour { volatile uint32_t state; uint32_t pos, ncol, coded, jerr; uint32_t with_color, cct; };
+__global__ void __launch_bounds__(96) dec_entropy_kernel(DecFrame *frames, int first_slot, int group_frames, int use_ring) {
   const int fi = steered_frame(first_slot, group_frames);
   if (fi < 0) return;
   DecFrame &f = frames[fi];
-  __shared__ uint32_t freq[257];
+  __shared__ uint32_t freq[257], freq2[257];
   __shared__ WalkRing rg;
+  __shared__ SpecColour sc;
+  __shared__ HuffDec hd[4];
   __shared__ uint32_t lut[256];                            // per 8-bit child mask: popcount << 16 | index of the lowest bit << 8 | mask without its lowest bit
   __shared__ uint32_t wstack[32];                          // walker: remaining-children mask per open level
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = ((uint32_t)__popc(i) << 16) | ((i ? (uint32_t)(__ffs(i) - 1) : 0u) << 8) | (i & (i - 1));
   const uint32_t lane = lane_id();
   const bool decoder = threadIdx.x < 32;
+  const uint32_t role = threadIdx.x >> 5;                  // 0 range decoder, 1 DFS walker, 2 speculative colour layer
   const uint8_t *in = f.in;
   const uint64_t len = f.in_len;
   uint32_t err = f.error;
   uint64_t pos = 0, B = 0;
   uint32_t do_centroid = 0, data_with_color = 0, cct = 0, depth = 0;
-  if (threadIdx.x == 0) { rg.prod = 0; rg.cons = 0; rg.done = 0; rg.dead = 0; rg.go = 0; }
+  if (threadIdx.x == 0) { rg.prod = 0; rg.cons = 0; rg.done = 0; rg.dead = 0; rg.go = 0; sc.state = 0; sc.with_color = 0; sc.cct = 0; sc.jerr = 0; }
   if (decoder && !err) {
     // syncToHeader: scan for the two magics like the reference (impl.hpp:1660-1676)
     const char id2[] = "<PCL-OCT-CODECV2-COMPRESSED>", id1[] = "<PCL-OCT-COMPRESSED>";
@@ -83,12 +95,56 @@ __global__ void __launch_bounds__(64) dec_entropy_kernel(DecFrame *frames, int f
         f.do_centroid = do_centroid; f.cct = cct; f.depth = depth;
       }
     }
-    if (lane == 0) { rg.B = (uint32_t)B; rg.depth = depth; rg.go = (use_ring && !err && B > 0 && depth >= 1 && depth <= 17) ? 1u : 0u; }
+    if (lane == 0) { rg.B = (uint32_t)B; rg.depth = depth; rg.go = (use_ring && !err && B > 0 && depth >= 1 && depth <= 17) ? 1u : 0u;
+                     sc.with_color = (use_ring && !err) ? data_with_color : 0u; sc.cct = cct; }
   }
   __syncthreads();
   const bool ring = rg.go != 0;
-  if (!decoder) {                                           // walker warp: lane 0 walks, the other lanes retire
+  if (role == 1) {                                          // walker warp: lane 0 walks, the other lanes retire
     if (lane == 0 && ring) dfs_walk_ring(f, &rg, lut, wstack);
+    return;
+  }
+  if (role == 2) {                                          // speculative colour layer (+ JPEG entropy decode)
+    uint32_t st = 2;
+    if (sc.with_color && len > FRAME_HDR_BYTES + 8 + 1032 + 8 + 1032) {
+      // backward scan for the layer signature; candidates o = offset of the u64 size word
+      const uint64_t lo_lim = FRAME_HDR_BYTES + 8 + 1032;
+      uint64_t found = 0; bool have = false;
+      for (uint64_t hi = len - 1040; !have && hi >= lo_lim; hi = hi >= 32 + lo_lim ? hi - 32 : 0) {
+        const uint64_t o = hi >= lane ? hi - lane : 0;
+        bool q = o >= lo_lim && (in[o + 4] | in[o + 5] | in[o + 6] | in[o + 7] | in[o + 8] | in[o + 9] | in[o + 10] | in[o + 11] | in[o + 14] | in[o + 15]) == 0;
+        uint32_t cand = __ballot_sync(FULL_MASK, q);
+        while (cand && !have) {                             // validate candidates from the highest offset down
+          const uint32_t l = __ffs(cand) - 1; cand &= cand - 1;
+          const uint64_t oc = hi - l;
+          bool okk = true;
+          for (uint32_t s2 = lane; s2 < 256; s2 += 32) {
+            const uint32_t a = ld_u32_unaligned(in + oc + 8 + 4 * s2), b2 = ld_u32_unaligned(in + oc + 12 + 4 * s2);
+            okk &= (b2 > a) & (b2 < RC_BOTTOM);
+          }
+          if (__all_sync(FULL_MASK, okk)) { found = oc; have = true; }
+        }
+        if (hi < 32 + lo_lim) break;
+      }
+      if (have) {
+        const uint64_t nc = ld_u64_unaligned(in + found);
+        uint64_t p2 = found + 8, cd = 0;
+        if (nc > 0 && nc <= f.col_cap && rc_decode_layer<false>(in, len, p2, f.col, (uint32_t)nc, freq2, &cd) && p2 == len) {
+          uint32_t jerr = 0;
+          if (sc.cct == 1) {
+            f.ncol = (uint32_t)nc;                          // the JPEG stages read it
+            if (lane == 0) jerr = jpeg_parse_header(f);
+            jerr = __shfl_sync(FULL_MASK, jerr, 0);
+            __syncwarp();
+            if (!jerr) { warp_destuff(f); __syncwarp(); if (lane == 0) { jpeg_huff_decode(f, hd); f.huff_done = 1; } }
+          }
+          if (lane == 0) { sc.pos = (uint32_t)found; sc.ncol = (uint32_t)nc; sc.coded = (uint32_t)cd; sc.jerr = jerr; }
+          st = 1;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); sc.state = st; }
     return;
   }
   if (err) { if (lane == 0) { f.error |= err; f.V = 0; f.B = 0; f.point_count = 0; rg.dead = 1; rg.done = 1; } return; }
@@ -105,12 +161,24 @@ __global__ void __launch_bounds__(64) dec_entropy_kernel(DecFrame *frames, int f
       else ok = rc_decode_layer<false>(in, len, pos, f.cen, ncen, freq, &coded[1]);
     }
   }
+  bool spec_used = false;
   if (ok && data_with_color) {
-    if (pos + 8 > len) ok = false;
-    else {
-      uint64_t nc = ld_u64_unaligned(in + pos); pos += 8;
-      if (nc > f.col_cap) { ok = false; err |= FERR_JPEG_CAP; }
-      else { ncol = (uint32_t)nc; ok = rc_decode_layer<false>(in, len, pos, f.col, ncol, freq, &coded[2]); }
+    while (sc.with_color && sc.state == 0) { }             // warp 2 is normally long done
+    if (sc.with_color && sc.state == 1 && sc.pos == pos) {  // speculation confirmed: the layer starts exactly where we are
+      ncol = sc.ncol; coded[2] = sc.coded; pos = len; spec_used = true;
+      if (sc.jerr) { ok = false; err |= sc.jerr; }
+    } else {
+      if (sc.with_color && sc.state == 1) {                 // mis-speculation (never observed): undo its side effects
+        for (uint32_t k = lane; k < f.coef_cap_blocks * 32; k += 32) ((uint32_t *)f.coef)[k] = 0;
+        if (lane == 0) f.huff_done = 0;
+        __syncwarp();
+      }
+      if (pos + 8 > len) ok = false;
+      else {
+        uint64_t nc = ld_u64_unaligned(in + pos); pos += 8;
+        if (nc > f.col_cap) { ok = false; err |= FERR_JPEG_CAP; }
+        else { ncol = (uint32_t)nc; ok = rc_decode_layer<false>(in, len, pos, f.col, ncol, freq, &coded[2]); }
+      }
     }
   }
   // trailing bytes would switch the reference into detail mode (impl.hpp:1802-1806): outside the implemented scope
@@ -119,7 +187,7 @@ __global__ void __launch_bounds__(64) dec_entropy_kernel(DecFrame *frames, int f
     if (!ok) { atomicOr(&f.error, err ? err : FERR_BAD_STREAM); f.B = 0; f.V = 0; }
     else {
       f.B = (uint32_t)B; f.ncen = ncen; f.ncol = ncol; f.coded[0] = coded[0]; f.coded[1] = coded[1]; f.coded[2] = coded[2];
-      if (data_with_color && cct == 1) jpeg_parse_header(f);
+      if (data_with_color && cct == 1 && !spec_used) { const uint32_t je = jpeg_parse_header(f); if (je) { atomicOr(&f.error, je); f.B = 0; f.V = 0; } }
     }
   }
 }
@@ -301,7 +369,7 @@ __device__ inline void dfs_walk(DecFrame &f) {
 
 // ---- stage 2b: JPEG of the single SNAKE image: marker parse (serial, short), parallel de-stuffing of the
 // entropy-coded segment, serial Huffman decode (no restart markers => one dependent bit stream per image)
-__device__ inline void jpeg_parse_header(DecFrame &f) {
+__device__ inline uint32_t jpeg_parse_header(DecFrame &f) {   // returns FERR_* bits (0 = ok); the caller decides whether they count
   const uint8_t *in = f.col; const uint32_t len = f.ncol;
   bool bad = false;
   uint32_t w = 0, h = 0, scan = 0, have = 0;
@@ -336,15 +404,17 @@ __device__ inline void jpeg_parse_header(DecFrame &f) {
   }
   if (!scan || w != 256 || h == 0 || have != 0x3F) bad = true;  // SNAKE images are 256 wide (cjpeg.h:197)
   const uint32_t mcu_w = (w + 15) / 16, mcu_h = (h + 15) / 16, nblocks = mcu_w * mcu_h * 6;
-  if (!bad && nblocks > f.coef_cap_blocks) { bad = true; f.error |= FERR_JPEG_CAP; }
-  if (bad) { f.error |= FERR_BAD_STREAM; f.img_w = f.img_h = f.mcu_w = f.mcu_h = f.n_blocks = 0; f.scan_start = f.scan_len = 0; return; }
+  uint32_t eb = 0;
+  if (!bad && nblocks > f.coef_cap_blocks) { bad = true; eb |= FERR_JPEG_CAP; }
+  if (bad) { f.img_w = f.img_h = f.mcu_w = f.mcu_h = f.n_blocks = 0; f.scan_start = f.scan_len = 0; return eb | FERR_BAD_STREAM; }
   f.img_w = w; f.img_h = h; f.mcu_w = mcu_w; f.mcu_h = mcu_h; f.n_blocks = nblocks; f.scan_start = scan;
+  return 0;
 }
 
 // removes the 0x00 stuffed after every 0xFF of the entropy-coded segment; one CTA per frame, chunks in order
 __global__ void __launch_bounds__(1024) jpeg_destuff_kernel(DecFrame *frames) {
   DecFrame &f = frames[blockIdx.x];
-  if (f.error || !f.data_with_color || f.cct != 1 || f.n_blocks == 0) return;
+  if (f.error || f.huff_done || !f.data_with_color || f.cct != 1 || f.n_blocks == 0) return;
   const uint8_t *in = f.col + f.scan_start;
   uint32_t n = f.ncol - f.scan_start;
   if (n >= 2 && in[n - 2] == 0xFF && in[n - 1] == 0xD9) n -= 2;     // EOI
@@ -371,7 +441,32 @@ __global__ void __launch_bounds__(1024) jpeg_destuff_kernel(DecFrame *frames) {
   if (threadIdx.x == 0) f.scan_len = obase;
 }
 
-struct HuffDec { int mincode[17]; int maxcode[17]; int valptr[17]; uint8_t vals[256]; uint16_t look[512]; };   // look: (len << 8) | sym for codes <= 9 bits
+// de-stuffing by one warp (speculative colour path inside dec_entropy_kernel): 4 bytes per lane per step
+__device__ inline void warp_destuff(DecFrame &f) {
+  const uint32_t lane = lane_id();
+  const uint8_t *in = f.col + f.scan_start;
+  uint32_t n = f.ncol - f.scan_start;
+  if (n >= 2 && in[n - 2] == 0xFF && in[n - 1] == 0xD9) n -= 2;     // EOI
+  uint32_t obase = 0, carry = 0;
+  for (uint32_t c0 = 0; c0 < n; c0 += 128) {
+    const uint32_t b0 = c0 + 4 * lane;
+    uint32_t by[4] = { 0, 0, 0, 0 }, nv = 0;
+    if (b0 < n) { nv = min(4u, n - b0); for (uint32_t k = 0; k < nv; k++) by[k] = in[b0 + k]; }
+    uint32_t prev = __shfl_up_sync(FULL_MASK, by[3], 1);
+    if (lane == 0) prev = carry;
+    uint32_t keep = 0, cnt = 0;
+    for (uint32_t k = 0; k < nv; k++) { const bool kp = !(by[k] == 0 && prev == 0xFF); keep |= (uint32_t)kp << k; cnt += kp; prev = by[k]; }
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o); if (lane >= (uint32_t)o) inc += t; }
+    uint32_t o = obase + inc - cnt;
+    for (uint32_t k = 0; k < nv; k++) if (keep >> k & 1) f.scan[o++] = (uint8_t)by[k];
+    obase += __shfl_sync(FULL_MASK, inc, 31);
+    carry = __shfl_sync(FULL_MASK, by[3], 31);
+  }
+  if (lane == 0) f.scan_len = obase;
+}
+
 struct JBits {               // MSB-first bit reader over the de-stuffed segment, 32-bit big-endian refills, next word prefetched
   const uint32_t *w; uint32_t nwords, wi; uint64_t acc; uint32_t nb; uint32_t nxt;
   __device__ __forceinline__ uint32_t fetch(uint32_t i) const { return i < nwords ? __byte_perm(w[i], 0, 0x0123) : 0u; }
@@ -445,7 +540,7 @@ __global__ void __launch_bounds__(64) dec_serial_kernel(DecFrame *frames, int fi
   const int role = threadIdx.x >> 5;                       // warp 0: DFS walk, warp 1: JPEG Huffman decode
   if (f.error) { if (role == 0) f.n_bottom = 0; else f.n_blocks = 0; return; }
   if (role == 0) { if (f.walk_done) return; if (f.depth >= 1 && f.depth <= 17 && f.B > 0) dfs_walk_fast(f); else dfs_walk(f); }
-  else if (f.data_with_color && f.cct == 1) jpeg_huff_decode(f, hd);
+  else if (f.data_with_color && f.cct == 1 && !f.huff_done) jpeg_huff_decode(f, hd);
 }
 
 // ---- stage 3: dequantise + ISLOW IDCT. 8 threads per block, 32 blocks per CTA; writes Y / Cb / Cr planes
