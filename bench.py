@@ -5,9 +5,10 @@
 
 A "step" is one pass of the hot path over one batch of F frames: ccv2_encode_batch over the F clouds followed by
 ccv2_decode_batch over the F streams it produced.  `value` is measured with the clouds already resident in HBM
-(device pointers in, device pointers out); `e2e` is the same step through the same C-ABI calls with pinned HOST
-buffers, so the host->device copy of every cloud / stream and the device->host copy of every stream / decoded
-cloud are inside the timed region.  For N > 1 the frames are sharded over the ranks (no data-path collective:
+(device pointers in, device pointers out); `e2e` is the same work through the C ABI with pinned HOST buffers
+(ccv2_roundtrip_batch: encode -> decode per frame in one pipelined call, like evaluate_compression's per-frame
+loop), so the host->device copy of every cloud and the device->host copy of every stream and decoded cloud are
+inside the timed region.  For N > 1 the frames are sharded over the ranks (no data-path collective:
 intra frames are independent); timing is bracketed by barrier + synchronize and reduced with MAX.
 """
 import argparse
@@ -154,6 +155,8 @@ def main():
     ap.add_argument("--kind", default="surf", choices=["surf", "unif"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-api", default="roundtrip", choices=["roundtrip", "separate"],
+                    help="e2e through ccv2_roundtrip_batch (default) or ccv2_encode_batch + ccv2_decode_batch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -234,6 +237,8 @@ def main():
         hi = [b.ptr for b in h_in]; hs = [b.ptr for b in h_str]; ho = [b.ptr for b in h_out]
 
         def step_host():
+            if args.e2e_api == "roundtrip":          # one pipelined call: encode -> decode per frame, streams and clouds back on the host
+                return codec.roundtrip_batch_raw(hi, [NP] * F, hs, [cap] * F, ho, [NP] * F)
             l2 = codec.encode_batch_raw(hi, [NP] * F, hs, [cap] * F)
             n2 = codec.decode_batch_raw(hs, l2, ho, [NP] * F)
             return l2, n2
@@ -247,7 +252,8 @@ def main():
         t_e2e = reduce_max(time.perf_counter() - t0, dist if world > 1 else None, dev)
         e2e = {"value": world * F * NP * args.steps / t_e2e / 1e6, "unit": "Mpoints/s",
                "h2d_bytes_per_step": int(F * NP * 32 + sum(l2)), "d2h_bytes_per_step": int(sum(l2) + 32 * sum(n2)),
-               "timing": "wall clock around the C-ABI calls (synchronous), max over ranks"}
+               "api": "ccv2_roundtrip_batch" if args.e2e_api == "roundtrip" else "ccv2_encode_batch + ccv2_decode_batch",
+               "timing": "wall clock around the C-ABI calls (synchronous), pinned host buffers in and out, max over ranks"}
         for b in h_in + h_str + h_out:
             b.close()
 

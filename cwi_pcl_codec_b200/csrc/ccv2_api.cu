@@ -77,9 +77,13 @@ struct ccv2_codec {
   ccv2_params prm;
   int device = 0;
   int n_sm = 148;
+  int trace = 0;                          // CCV2_TRACE=1: print per-group timeline (ms since batch start) to stderr
+  std::vector<cudaEvent_t> ev_trace;
   int use_ring = 1;                       // pipeline the DFS walk behind the range decoder (CCV2_NO_RING=1 disables: debugging)
   int n_streams = 8, group = 0;           // group 0 = auto: spread the batch over all streams
   cudaStream_t main_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;     // all host->device input copies, in group order (see run_batch)
+  std::vector<cudaEvent_t> ev_h2d;
   cudaStream_t streams[MAX_STREAMS] = {};
   cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_fork = nullptr;
   std::vector<cudaEvent_t> ev_group;
@@ -322,6 +326,7 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   }
   ccv2_codec *c = new ccv2_codec();
   c->prm = *p; c->device = device;
+  if (const char *s = getenv("CCV2_TRACE")) c->trace = atoi(s);
   if (const char *s = getenv("CCV2_NO_RING")) c->use_ring = atoi(s) ? 0 : 1;
   if (const char *s = getenv("CCV2_STREAMS")) c->n_streams = std::max(1, std::min(MAX_STREAMS, atoi(s)));
   if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(64, atoi(s)));
@@ -329,6 +334,7 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
   if ((e = cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail(e, "cudaDeviceGetAttribute");
   if ((e = cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+  if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
   for (int i = 0; i < c->n_streams; i++) if ((e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
   if ((e = cudaEventCreate(&c->ev_start)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if ((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) return fail(e, "cudaEventCreate");
@@ -349,11 +355,14 @@ void ccv2_destroy(ccv2_codec *c) {
   cudaDeviceSynchronize();
   for (auto ev : c->ev_group) cudaEventDestroy(ev);
   for (auto ev : c->prof_pool) cudaEventDestroy(ev);
+  for (auto ev : c->ev_trace) cudaEventDestroy(ev);
   if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (int i = 0; i < MAX_STREAMS; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
   if (c->main_stream) cudaStreamDestroy(c->main_stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (auto ev : c->ev_h2d) cudaEventDestroy(ev);
   if (c->d_tables) cudaFree(c->d_tables);
   if (c->d_frame_counter) cudaFree(c->d_frame_counter);
   c->enc_frames.release(); c->enc_slots.release(); c->enc_persist.release(); c->enc_input.release();
@@ -442,8 +451,10 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
   const int NS = c->profiling ? 1 : c->n_streams;
   const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(64, (nframes + NS - 1) / NS)));
   const int ngroups = (nframes + G - 1) / G;
+  while ((int)c->ev_h2d.size() < ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_h2d.push_back(ev); }
   while ((int)c->ev_group.size() < 2 * ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_group.push_back(ev); }
   cudaStream_t ms = c->main_stream;
+  if (c->trace) while ((int)c->ev_trace.size() < 4 * ngroups) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); c->ev_trace.push_back(ev); }
 
   // ------------------------------------------------------------------ encode side set-up
   size_t nmax = 1, zoff = 0, zbytes = 0, slot_bytes = 0, frames_bytes = 0;
@@ -549,12 +560,22 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
     if (do_enc) {
       EncFrame *dg = df + f0;
       size_t gn = 1;
+      // Host inputs go through ONE copy stream in group order: copies issued on the group streams would be
+      // interleaved by the copy engine and every group's input would land at the very end (measured), which defeats
+      // the pipeline.  This way group g can start as soon as its own clouds are on the device.
+      bool any_h2d = false;
       for (int i = 0; i < gf; i++) {
         gn = std::max(gn, npts[f0 + i]);
-        if (!in_dev[f0 + i] && npts[f0 + i]) CU(cudaMemcpyAsync((void *)hf[f0 + i].pts, pts[f0 + i], 32 * npts[f0 + i], cudaMemcpyHostToDevice, st));
+        if (!in_dev[f0 + i] && npts[f0 + i]) {
+          if (!any_h2d && g == 0) CU(cudaStreamWaitEvent(c->copy_stream, ev_setup, 0));
+          CU(cudaMemcpyAsync((void *)hf[f0 + i].pts, pts[f0 + i], 32 * npts[f0 + i], cudaMemcpyHostToDevice, c->copy_stream));
+          any_h2d = true;
+        }
         const int slot = (g % NS) * G + i;
         CU(cudaMemsetAsync((uint8_t *)c->enc_slots.p + slot_bytes * slot + zoff, 0, zbytes, st));
       }
+      if (any_h2d) { CU(cudaEventRecord(c->ev_h2d[g], c->copy_stream)); CU(cudaStreamWaitEvent(st, c->ev_h2d[g], 0)); }
+      if (c->trace) CU(cudaEventRecord(c->ev_trace[4 * g + 0], st));
       const unsigned gx256 = (unsigned)((gn + 255) / 256), gtiles = (unsigned)((gn + SORT_TILE - 1) / SORT_TILE);
       LAUNCH("bbox_kernel", bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 0));
       LAUNCH("bbox_fixup_kernel", bbox_fixup_kernel<<<gf, 32, 0, st>>>(dg, P));
@@ -581,16 +602,23 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       LAUNCH("rc_encode_kernel", rc_encode_kernel<<<c->n_sm, 96, 0, st>>>(dg, f0, gf, cen, color));
       LAUNCH("assemble_kernel", assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H));
       CU(cudaMemcpyAsync(hf + f0, dg, sizeof(EncFrame) * gf, cudaMemcpyDeviceToHost, st));
+      if (c->trace) CU(cudaEventRecord(c->ev_trace[4 * g + 1], st));
     }
     if (do_dec) {
       DecFrame *dg = dd + f0;
       size_t pmax = 1;
+      bool any_h2d = false;
       for (int i = 0; i < gf; i++) {
         const int k = f0 + i;
         pmax = std::max(pmax, pts_cap[k]);
-        if (!rt && !din_dev[k] && in_len[k]) CU(cudaMemcpyAsync((void *)hd[k].in, in[k], in_len[k], cudaMemcpyHostToDevice, st));
+        if (!rt && !din_dev[k] && in_len[k]) {
+          if (!any_h2d && g == 0) CU(cudaStreamWaitEvent(c->copy_stream, ev_setup, 0));
+          CU(cudaMemcpyAsync((void *)hd[k].in, in[k], in_len[k], cudaMemcpyHostToDevice, c->copy_stream));
+          any_h2d = true;
+        }
         CU(cudaMemsetAsync((uint8_t *)c->dec_work.p + work_off[k], 0, zb[k], st));
       }
+      if (any_h2d) { CU(cudaEventRecord(c->ev_h2d[g], c->copy_stream)); CU(cudaStreamWaitEvent(st, c->ev_h2d[g], 0)); }
       if (rt) LAUNCH("link_kernel", link_kernel<<<(gf + 63) / 64, 64, 0, st>>>(df + f0, dg, gf));
       LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<c->n_sm, 96, 0, st>>>(dg, f0, gf, c->use_ring));
       LAUNCH("dec_expand_kernel", dec_expand_kernel<<<dim3((unsigned)((pmax + 255) / 256), gf), 256, 0, st>>>(dg));
@@ -600,6 +628,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       LAUNCH("jpeg_idct_kernel", jpeg_idct_kernel<<<dim3((unsigned)((nblocks + 31) / 32), gf), 256, 0, st>>>(dg, c->d_tables));
       LAUNCH("dec_points_kernel", dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg));
       CU(cudaMemcpyAsync(hd + f0, dg, sizeof(DecFrame) * gf, cudaMemcpyDeviceToHost, st));
+      if (c->trace) CU(cudaEventRecord(c->ev_trace[4 * g + 2], st));
     }
     CU(cudaGetLastError());
   }
@@ -650,12 +679,23 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
         if (!dout_dev[k] && f.V) CU(cudaMemcpyAsync(pts_out[k], f.out_pts, 32ull * f.V, cudaMemcpyDeviceToHost, st));
       }
     }
+    if (c->trace) CU(cudaEventRecord(c->ev_trace[4 * g + 3], st));
     CU(cudaEventRecord(ev, st));
     CU(cudaStreamWaitEvent(ms, ev, 0));
   }
   CU(cudaEventRecord(c->ev_end, ms));
   CU(cudaEventSynchronize(c->ev_end));
   CU(cudaEventElapsedTime(&c->device_ms, c->ev_start, c->ev_end));
+  if (c->trace) {
+    fprintf(stderr, "ccv2 trace mode=%d frames=%d groups=%d total %.1f ms\n", mode, nframes, ngroups, c->device_ms);
+    for (int g = 0; g < ngroups; g++) {
+      float t[4] = {-1, -1, -1, -1};
+      if (do_enc) { cudaEventElapsedTime(&t[0], c->ev_start, c->ev_trace[4 * g + 0]); cudaEventElapsedTime(&t[1], c->ev_start, c->ev_trace[4 * g + 1]); }
+      if (do_dec) cudaEventElapsedTime(&t[2], c->ev_start, c->ev_trace[4 * g + 2]);
+      cudaEventElapsedTime(&t[3], c->ev_start, c->ev_trace[4 * g + 3]);
+      fprintf(stderr, "  group %2d: inputs on device %.1f | encode done %.1f | decode done %.1f | results copied %.1f\n", g, t[0], t[1], t[2], t[3]);
+    }
+  }
   prof_collect(c);
   c->launches = launches;
   if (do_enc) {
