@@ -229,12 +229,11 @@ def main():
     # ---- e2e: same calls with pinned host buffers ----
     e2e = None
     if not args.no_e2e:
-        h_in = [K.PinnedBuffer(NP * 32) for _ in range(F)]
-        for hb, f in zip(h_in, frames):
-            hb.array[:] = f.view(np.uint8).reshape(-1)
-        h_str = [K.PinnedBuffer(cap) for _ in range(F)]
-        h_out = [K.PinnedBuffer(NP * 32) for _ in range(F)]
-        hi = [b.ptr for b in h_in]; hs = [b.ptr for b in h_str]; ho = [b.ptr for b in h_out]
+        # one pinned allocation per role, sliced per frame (many separate cudaMallocHost blocks copy ~30 % slower D2H here)
+        h_in, h_str, h_out = K.PinnedBuffer(F * NP * 32), K.PinnedBuffer(F * cap), K.PinnedBuffer(F * NP * 32)
+        for i, f in enumerate(frames):
+            h_in.array[i * NP * 32:(i + 1) * NP * 32] = f.view(np.uint8).reshape(-1)
+        hi = [h_in.ptr + i * NP * 32 for i in range(F)]; hs = [h_str.ptr + i * cap for i in range(F)]; ho = [h_out.ptr + i * NP * 32 for i in range(F)]
 
         def step_host():
             if args.e2e_api == "roundtrip":          # one pipelined call: encode -> decode per frame, streams and clouds back on the host
@@ -254,7 +253,7 @@ def main():
                "h2d_bytes_per_step": int(F * NP * 32 + sum(l2)), "d2h_bytes_per_step": int(sum(l2) + 32 * sum(n2)),
                "api": "ccv2_roundtrip_batch" if args.e2e_api == "roundtrip" else "ccv2_encode_batch + ccv2_decode_batch",
                "timing": "wall clock around the C-ABI calls (synchronous), pinned host buffers in and out, max over ranks"}
-        for b in h_in + h_str + h_out:
+        for b in (h_in, h_str, h_out):
             b.close()
 
     # ---- per-kernel profile (one extra, untimed, single-stream step over one group) -> roofline of the dominant kernel ----

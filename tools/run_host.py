@@ -10,7 +10,14 @@ cap = 4 * n + (1 << 16)
 h_in = [K.PinnedBuffer(n * 32) for _ in range(F)]
 for i, b in enumerate(h_in): b.array[:] = base[i % len(base)].view(np.uint8).reshape(-1)
 h_str = [K.PinnedBuffer(cap) for _ in range(F)]
-h_out = [K.PinnedBuffer(n * 32) for _ in range(F)]
+ONE = os.environ.get("ONE_BUF", "0") == "1"
+if ONE:
+    big = K.PinnedBuffer(n * 32 * F)
+    class _V:                                   # view into the single allocation
+        def __init__(self, p): self.ptr = p
+    h_out = [_V(big.ptr + i * n * 32) for i in range(F)]
+else:
+    h_out = [K.PinnedBuffer(n * 32) for _ in range(F)]
 # raw PCIe bandwidth with torch
 x = torch.empty(1 << 30, dtype=torch.uint8).pin_memory(); y = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
 for name, a, b in (("H2D", x, y), ("D2H", y, x)):
