@@ -173,13 +173,39 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     F, NP = args.frames, args.points
-    frames = gen_frames(args.kind, NP, shard_frames(F, rank, world))
     codec = K.Codec(K.default_params(octree_bits=args.bits), device=local)
     lib = K.load_library()
+    cap = 4 * NP + (1 << 16)
+
+    # ---- host memory budget: the e2e leg needs pinned input + stream + output buffers on every rank of the node
+    F_e2e = 0
+    if not args.no_e2e:
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 64 << 30
+        per_frame = NP * 32 * 2 + cap
+        F_e2e = int(max(8, min(F, (0.45 * avail / world) // per_frame)))
+    h_in = K.PinnedBuffer(F_e2e * NP * 32) if F_e2e else None
+
+    # ---- synthetic frames, generated in chunks and moved straight to the device (and to the pinned e2e input buffer);
+    # only the first 16 stay on the host for the oracle checks / cpu_baseline
+    seeds = shard_frames(F, rank, world)
+    d_in, frames = [], []
+    for c0 in range(0, F, 32):
+        chunk = gen_frames(args.kind, NP, seeds[c0:c0 + 32])
+        for j, fr in enumerate(chunk):
+            i = c0 + j
+            flat = fr.view(np.uint8).reshape(-1)
+            d_in.append(torch.from_numpy(flat).to(dev))
+            if i < F_e2e:
+                h_in.array[i * NP * 32:(i + 1) * NP * 32] = flat
+            if i < 16:
+                frames.append(fr)
+        del chunk
 
     # ---- device-resident buffers (value) ----
-    d_in = [torch.from_numpy(f.view(np.uint8).reshape(-1)).to(dev) for f in frames]
-    cap = 4 * NP + (1 << 16)
     d_str = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(F)]
     d_out = [torch.empty(NP * 32, dtype=torch.uint8, device=dev) for _ in range(F)]
     in_ptrs = [t.data_ptr() for t in d_in]; str_ptrs = [t.data_ptr() for t in d_str]; out_ptrs = [t.data_ptr() for t in d_out]
@@ -228,18 +254,17 @@ def main():
 
     # ---- e2e: same calls with pinned host buffers ----
     e2e = None
-    if not args.no_e2e:
+    if F_e2e:
         # one pinned allocation per role, sliced per frame (many separate cudaMallocHost blocks copy ~30 % slower D2H here)
-        h_in, h_str, h_out = K.PinnedBuffer(F * NP * 32), K.PinnedBuffer(F * cap), K.PinnedBuffer(F * NP * 32)
-        for i, f in enumerate(frames):
-            h_in.array[i * NP * 32:(i + 1) * NP * 32] = f.view(np.uint8).reshape(-1)
-        hi = [h_in.ptr + i * NP * 32 for i in range(F)]; hs = [h_str.ptr + i * cap for i in range(F)]; ho = [h_out.ptr + i * NP * 32 for i in range(F)]
+        FE = F_e2e
+        h_str, h_out = K.PinnedBuffer(FE * cap), K.PinnedBuffer(FE * NP * 32)
+        hi = [h_in.ptr + i * NP * 32 for i in range(FE)]; hs = [h_str.ptr + i * cap for i in range(FE)]; ho = [h_out.ptr + i * NP * 32 for i in range(FE)]
 
         def step_host():
             if args.e2e_api == "roundtrip":          # one pipelined call: encode -> decode per frame, streams and clouds back on the host
-                return codec.roundtrip_batch_raw(hi, [NP] * F, hs, [cap] * F, ho, [NP] * F)
-            l2 = codec.encode_batch_raw(hi, [NP] * F, hs, [cap] * F)
-            n2 = codec.decode_batch_raw(hs, l2, ho, [NP] * F)
+                return codec.roundtrip_batch_raw(hi, [NP] * FE, hs, [cap] * FE, ho, [NP] * FE)
+            l2 = codec.encode_batch_raw(hi, [NP] * FE, hs, [cap] * FE)
+            n2 = codec.decode_batch_raw(hs, l2, ho, [NP] * FE)
             return l2, n2
         for _ in range(2):
             step_host()
@@ -249,10 +274,12 @@ def main():
             l2, n2 = step_host()
         barrier()
         t_e2e = reduce_max(time.perf_counter() - t0, dist if world > 1 else None, dev)
-        e2e = {"value": world * F * NP * args.steps / t_e2e / 1e6, "unit": "Mpoints/s",
-               "h2d_bytes_per_step": int(F * NP * 32 + sum(l2)), "d2h_bytes_per_step": int(sum(l2) + 32 * sum(n2)),
+        e2e = {"value": world * FE * NP * args.steps / t_e2e / 1e6, "unit": "Mpoints/s", "frames_per_step_per_gpu": FE,
+               "h2d_bytes_per_step": int(FE * NP * 32), "d2h_bytes_per_step": int(sum(l2) + 32 * sum(n2)),
                "api": "ccv2_roundtrip_batch" if args.e2e_api == "roundtrip" else "ccv2_encode_batch + ccv2_decode_batch",
                "timing": "wall clock around the C-ABI calls (synchronous), pinned host buffers in and out, max over ranks"}
+        if args.e2e_api != "roundtrip":
+            e2e["h2d_bytes_per_step"] += int(sum(l2))
         for b in (h_in, h_str, h_out):
             b.close()
 
@@ -263,7 +290,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        nb = min(F, 16)
+        nb = min(F, len(frames))
         t, p = cpu_oracle_run(frames[:nb], args.bits, 1)
         cpu_baseline = {"value": p / t / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "port",
                         "sample": "%d of the step's %d frames, encode+decode, oracle port single thread (the reference's intra path is single-threaded)" % (nb, F)}
@@ -290,7 +317,7 @@ def profile_roofline(K, lib, args, frames, alg_bytes_frame):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     which = "measured (MEASURED_PEAKS.json, copy kernel)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    prof = K.profile_step(frames[:min(len(frames), 32)], args.bits)
+    prof = K.profile_step(frames[:min(len(frames), 16)], args.bits)
     if not prof:
         return None
     name, tot_ms, count, frames_per_launch = max(prof, key=lambda r: r[1])
