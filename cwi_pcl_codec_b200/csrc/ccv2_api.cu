@@ -335,7 +335,16 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   if ((e = cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail(e, "cudaDeviceGetAttribute");
   if ((e = cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
-  for (int i = 0; i < c->n_streams; i++) if ((e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+  {
+    // optional (CCV2_PRIORITY=1): earlier groups get higher stream priority.  Measured neutral on B200 (the long serial
+    // kernels are resident anyway), so it is off by default.
+    int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);      // lo = least urgent (numerically largest)
+    const bool prio = getenv("CCV2_PRIORITY") && atoi(getenv("CCV2_PRIORITY")) != 0;
+    for (int i = 0; i < c->n_streams; i++) {
+      int p = prio ? std::min(lo, hi + i * (lo - hi + 1) / std::max(1, c->n_streams)) : lo;
+      if ((e = cudaStreamCreateWithPriority(&c->streams[i], cudaStreamNonBlocking, p)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    }
+  }
   if ((e = cudaEventCreate(&c->ev_start)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if ((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
