@@ -500,6 +500,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       f.n_finite = (uint32_t)npts[i];                               // keygen subtracts the non-finite points
       f.violator = NONE_U32;
       carve_enc_slot((uint8_t *)c->enc_slots.p + slot_bytes * slot, nmax, &f, prm, nullptr, nullptr);
+      f.zero_ptr = (uint8_t *)c->enc_slots.p + slot_bytes * slot + zoff; f.zero_bytes = zbytes;
       carve_enc_persist((uint8_t *)c->enc_persist.p + persist_off[i], npts[i], &f, cen);
       f.hist = (uint32_t *)((uint8_t *)c->enc_frames.p + frames_bytes) + (size_t)i * 3 * 256;
       if (color && prm.color_coding_type != 1) f.avg = f.cpay;       // raw averages are the colour payload (types 0, 3)
@@ -548,6 +549,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       f.out_pts = dout_dev[i] ? (uint8_t *)pts_out[i] : (uint8_t *)c->dec_output.p + output_off[i];
       f.out_cap = pts_cap[i];
       carve_dec((uint8_t *)c->dec_work.p + work_off[i], pts_cap[i], &f, nullptr, nullptr);
+      f.zero_ptr = (uint8_t *)c->dec_work.p + work_off[i]; f.zero_bytes = zb[i];
     }
   }
 
@@ -580,9 +582,8 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
           CU(cudaMemcpyAsync((void *)hf[f0 + i].pts, pts[f0 + i], 32 * npts[f0 + i], cudaMemcpyHostToDevice, c->copy_stream));
           any_h2d = true;
         }
-        const int slot = (g % NS) * G + i;
-        CU(cudaMemsetAsync((uint8_t *)c->enc_slots.p + slot_bytes * slot + zoff, 0, zbytes, st));
       }
+      LAUNCH("zero_region_kernel", zero_region_kernel<EncFrame><<<dim3(128, gf), 256, 0, st>>>(dg));
       if (any_h2d) { CU(cudaEventRecord(c->ev_h2d[g], c->copy_stream)); CU(cudaStreamWaitEvent(st, c->ev_h2d[g], 0)); }
       if (c->trace) CU(cudaEventRecord(c->ev_trace[4 * g + 0], st));
       const unsigned gx256 = (unsigned)((gn + 255) / 256), gtiles = (unsigned)((gn + SORT_TILE - 1) / SORT_TILE);
@@ -625,8 +626,8 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
           CU(cudaMemcpyAsync((void *)hd[k].in, in[k], in_len[k], cudaMemcpyHostToDevice, c->copy_stream));
           any_h2d = true;
         }
-        CU(cudaMemsetAsync((uint8_t *)c->dec_work.p + work_off[k], 0, zb[k], st));
       }
+      LAUNCH("zero_region_kernel", zero_region_kernel<DecFrame><<<dim3(64, gf), 256, 0, st>>>(dg));
       if (any_h2d) { CU(cudaEventRecord(c->ev_h2d[g], c->copy_stream)); CU(cudaStreamWaitEvent(st, c->ev_h2d[g], 0)); }
       if (rt) LAUNCH("link_kernel", link_kernel<<<(gf + 63) / 64, 64, 0, st>>>(df + f0, dg, gf));
       LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<c->n_sm, 96, 0, st>>>(dg, f0, gf, c->use_ring));

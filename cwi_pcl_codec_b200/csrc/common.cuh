@@ -40,6 +40,8 @@ struct EncParams {             // by value to kernels
 };
 
 struct EncFrame {
+  // region of the group-slot workspace that must be zero before the pipeline starts (zero_region_kernel)
+  uint8_t *zero_ptr; uint64_t zero_bytes;
   // input
   const uint8_t *pts; uint32_t n; uint32_t _pad0;
   // bbox / keys
@@ -79,6 +81,7 @@ struct EncFrame {
 };
 
 struct DecFrame {
+  uint8_t *zero_ptr; uint64_t zero_bytes;      // scan status + JPEG coefficients: zero before the pipeline starts
   const uint8_t *in; uint64_t in_len;
   uint8_t *out_pts; uint64_t out_cap;       // points
   // header
@@ -211,6 +214,18 @@ __device__ __forceinline__ int steered_frame(uint32_t first_slot, uint32_t group
   const uint32_t g = gridDim.x;
   const uint32_t f = (blockIdx.x + g - first_slot % g) % g;
   return f < group_frames ? (int)f : -1;
+}
+
+// Zeroing as a kernel on the group's own stream.  cudaMemsetAsync goes through a shared in-order engine: a memset queued
+// behind a long kernel on one stream held back the memsets (and so the start) of every other group (measured with
+// CCV2_TRACE: groups 1..7 of a round trip started only when group 0's encode had finished).
+template <typename Frame>
+__global__ void __launch_bounds__(256) zero_region_kernel(Frame *frames) {
+  Frame &f = frames[blockIdx.y];
+  const uint64_t n16 = f.zero_bytes / 16;                   // regions are 256-byte aligned multiples of 256
+  uint4 *p = (uint4 *)f.zero_ptr;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) p[i] = z;
 }
 
 // Granlund-Montgomery division of a 32-bit value by an invariant d (2 <= d < 2^31): q = n / d exactly.
