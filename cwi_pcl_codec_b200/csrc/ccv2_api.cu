@@ -73,6 +73,19 @@ constexpr int MAX_STREAMS = 16;
 
 }  // namespace
 
+// Per-frame results published straight into pinned host memory by a kernel (zero-copy store over PCIe): the host learns
+// the sizes from an event right after the group's last kernel instead of waiting for a D2H copy that would queue behind
+// other groups' result copies in the copy engine.
+struct FrameResult { uint64_t out_len; uint32_t enc_error, dec_error, V, _pad; };
+__global__ void publish_kernel(const EncFrame *enc, const DecFrame *dec, FrameResult *res, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  FrameResult r; r.out_len = 0; r.enc_error = 0; r.dec_error = 0; r.V = 0; r._pad = 0;
+  if (enc) { r.out_len = enc[i].out_len; r.enc_error = enc[i].error; }
+  if (dec) { r.dec_error = dec[i].error; r.V = dec[i].V; }
+  res[i] = r;
+}
+
 struct ccv2_codec {
   ccv2_params prm;
   int device = 0;
@@ -96,7 +109,7 @@ struct ccv2_codec {
   std::vector<EncFrame> enc_host;        // host mirror of the last batch's frame records (with device pointers)
   // decode workspaces
   DevBuf dec_frames, dec_work, dec_input, dec_output;
-  HostBuf h_dframes;
+  HostBuf h_dframes, h_results;
   uint64_t metrics[3] = {0, 0, 0};
   uint64_t launches = 0;
   float device_ms = 0.f;
@@ -376,7 +389,7 @@ void ccv2_destroy(ccv2_codec *c) {
   if (c->d_frame_counter) cudaFree(c->d_frame_counter);
   c->enc_frames.release(); c->enc_slots.release(); c->enc_persist.release(); c->enc_input.release();
   c->dec_frames.release(); c->dec_work.release(); c->dec_input.release(); c->dec_output.release();
-  c->h_frames.release(); c->h_dframes.release();
+  c->h_frames.release(); c->h_dframes.release(); c->h_results.release();
   delete c;
 }
 
@@ -463,6 +476,8 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
   while ((int)c->ev_h2d.size() < ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_h2d.push_back(ev); }
   while ((int)c->ev_group.size() < 2 * ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_group.push_back(ev); }
   cudaStream_t ms = c->main_stream;
+  CU(c->h_results.ensure(sizeof(FrameResult) * nframes));
+  FrameResult *hres = (FrameResult *)c->h_results.p;
   if (c->trace) while ((int)c->ev_trace.size() < 4 * ngroups) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); c->ev_trace.push_back(ev); }
 
   // ------------------------------------------------------------------ encode side set-up
@@ -611,7 +626,6 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       LAUNCH("hist_kernel", hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), 3, gf), 256, 0, st>>>(dg));
       LAUNCH("rc_encode_kernel", rc_encode_kernel<<<c->n_sm, 96, 0, st>>>(dg, f0, gf, cen, color));
       LAUNCH("assemble_kernel", assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H));
-      CU(cudaMemcpyAsync(hf + f0, dg, sizeof(EncFrame) * gf, cudaMemcpyDeviceToHost, st));
       if (c->trace) CU(cudaEventRecord(c->ev_trace[4 * g + 1], st));
     }
     if (do_dec) {
@@ -637,9 +651,10 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       const size_t img_h = pmax / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
       LAUNCH("jpeg_idct_kernel", jpeg_idct_kernel<<<dim3((unsigned)((nblocks + 31) / 32), gf), 256, 0, st>>>(dg, c->d_tables));
       LAUNCH("dec_points_kernel", dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg));
-      CU(cudaMemcpyAsync(hd + f0, dg, sizeof(DecFrame) * gf, cudaMemcpyDeviceToHost, st));
       if (c->trace) CU(cudaEventRecord(c->ev_trace[4 * g + 2], st));
     }
+    LAUNCH("publish_kernel", publish_kernel<<<(gf + 63) / 64, 64, 0, st>>>(do_enc ? df + f0 : nullptr, do_dec ? dd + f0 : nullptr, hres + f0, gf));
+    CU(cudaEventRecord(c->ev_group[ngroups + g], st));
     CU(cudaGetLastError());
   }
 
@@ -649,46 +664,47 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
   for (int g = 0; g < ngroups; g++) {
     cudaStream_t st = c->streams[g % NS];
     cudaEvent_t ev = c->ev_group[ngroups + g];
-    CU(cudaEventRecord(ev, st));
-    CU(cudaEventSynchronize(ev));
+    CU(cudaEventSynchronize(ev));                            // the group's kernels are done and its FrameResults are in host memory
     const int f0 = g * G, gf = std::min(G, nframes - f0);
     for (int i = 0; i < gf; i++) {
       const int k = f0 + i;
+      const FrameResult &r = hres[k];
       bool enc_ok = true;
       if (do_enc) {
-        EncFrame &f = hf[k];
         if (out_len) out_len[k] = 0;
-        if (f.error) {
+        if (r.enc_error) {
           enc_ok = false;
           if (rc == CCV2_OK) {
-            rc = (f.error & FERR_DEPTH) ? CCV2_ERR_DEPTH : CCV2_ERR_WORKSPACE;
-            char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x (encode)", k, f.error); c->err = b;
+            rc = (r.enc_error & FERR_DEPTH) ? CCV2_ERR_DEPTH : CCV2_ERR_WORKSPACE;
+            char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x (encode)", k, r.enc_error); c->err = b;
           }
-        } else if (f.out_len && out && out[k]) {
-          if (f.out_len > out_cap[k]) { if (rc == CCV2_OK) { rc = CCV2_ERR_CAPACITY; c->err = "output buffer too small"; } }
+        } else if (r.out_len && out && out[k]) {
+          if (r.out_len > out_cap[k]) { if (rc == CCV2_OK) { rc = CCV2_ERR_CAPACITY; c->err = "output buffer too small"; } }
           else {
-            CU(cudaMemcpyAsync(out[k], f.stream, f.out_len, out_dev[k] ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-            out_len[k] = f.out_len;
+            CU(cudaMemcpyAsync(out[k], hf[k].stream, r.out_len, out_dev[k] ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+            out_len[k] = r.out_len;
           }
-        } else if (f.out_len && !rt) { if (rc == CCV2_OK) { rc = CCV2_ERR_CAPACITY; c->err = "output buffer too small"; } }
-        else if (f.out_len && out_len) out_len[k] = f.out_len;      // round trip without a stream buffer: report the size only
+        } else if (r.out_len && !rt) { if (rc == CCV2_OK) { rc = CCV2_ERR_CAPACITY; c->err = "output buffer too small"; } }
+        else if (r.out_len && out_len) out_len[k] = r.out_len;      // round trip without a stream buffer: report the size only
       }
       if (do_dec) {
-        DecFrame &f = hd[k];
         npts_out[k] = 0;
-        if (rt && (!enc_ok || hf[k].out_len == 0)) continue;       // empty frame: nothing was written, nothing to decode
-        if (f.error) {
+        if (rt && (!enc_ok || r.out_len == 0)) continue;           // empty frame: nothing was written, nothing to decode
+        if (r.dec_error) {
           if (rc == CCV2_OK) {
-            rc = (f.error & FERR_OUT_CAP) ? CCV2_ERR_CAPACITY : (f.error & FERR_DEPTH) ? CCV2_ERR_DEPTH : (f.error & FERR_UNSUPPORTED) ? CCV2_ERR_UNSUPPORTED
-               : (f.error & (FERR_TREE_CAP | FERR_JPEG_CAP)) ? CCV2_ERR_WORKSPACE : CCV2_ERR_STREAM;
-            char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x (decode)", k, f.error); c->err = b;
+            rc = (r.dec_error & FERR_OUT_CAP) ? CCV2_ERR_CAPACITY : (r.dec_error & FERR_DEPTH) ? CCV2_ERR_DEPTH : (r.dec_error & FERR_UNSUPPORTED) ? CCV2_ERR_UNSUPPORTED
+               : (r.dec_error & (FERR_TREE_CAP | FERR_JPEG_CAP)) ? CCV2_ERR_WORKSPACE : CCV2_ERR_STREAM;
+            char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x (decode)", k, r.dec_error); c->err = b;
           }
           continue;
         }
-        npts_out[k] = f.V;
-        if (!dout_dev[k] && f.V) CU(cudaMemcpyAsync(pts_out[k], f.out_pts, 32ull * f.V, cudaMemcpyDeviceToHost, st));
+        npts_out[k] = r.V;
+        if (!dout_dev[k] && r.V) CU(cudaMemcpyAsync(pts_out[k], hd[k].out_pts, 32ull * r.V, cudaMemcpyDeviceToHost, st));
       }
     }
+    // full frame records (metrics, debug hook) come back last on this stream
+    if (do_enc) CU(cudaMemcpyAsync(hf + f0, df + f0, sizeof(EncFrame) * gf, cudaMemcpyDeviceToHost, st));
+    if (do_dec) CU(cudaMemcpyAsync(hd + f0, dd + f0, sizeof(DecFrame) * gf, cudaMemcpyDeviceToHost, st));
     if (c->trace) CU(cudaEventRecord(c->ev_trace[4 * g + 3], st));
     CU(cudaEventRecord(ev, st));
     CU(cudaStreamWaitEvent(ms, ev, 0));
