@@ -210,10 +210,13 @@ def main():
     d_out = [torch.empty(NP * 32, dtype=torch.uint8, device=dev) for _ in range(F)]
     in_ptrs = [t.data_ptr() for t in d_in]; str_ptrs = [t.data_ptr() for t in d_str]; out_ptrs = [t.data_ptr() for t in d_out]
 
+    split = {"enc": 0.0, "dec": 0.0}
+
     def step_device():
         lens = codec.encode_batch_raw(in_ptrs, [NP] * F, str_ptrs, [cap] * F)
         ms, launches = codec.last_device_ms, codec.last_launch_count
         ns = codec.decode_batch_raw(str_ptrs, lens, out_ptrs, [NP] * F)
+        split["enc"] += ms; split["dec"] += codec.last_device_ms
         return ms + codec.last_device_ms, launches + codec.last_launch_count, lens, ns
 
     def barrier():
@@ -226,6 +229,7 @@ def main():
         _, _, lens, ns = step_device()
     sampler = ClockSampler(local)
     barrier()
+    split["enc"] = split["dec"] = 0.0
     sampler.start()
     t0 = time.perf_counter()
     dev_ms, launches = 0.0, 0
@@ -300,6 +304,8 @@ def main():
                 "vs_baseline": None, "dtype": "u8/u32/f64 (integer codec, FP64 keys)", "data": "synthetic",
                 "config": workload_config(args, F), "bit_exact_vs_oracle": bit_exact, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "encode_ms_per_step": split["enc"] / args.steps, "decode_ms_per_step": split["dec"] / args.steps,
+                "encode_only_mpoints_s": F * NP * args.steps / max(split["enc"], 1e-9) / 1e3, "decode_only_mpoints_s": F * NP * args.steps / max(split["dec"], 1e-9) / 1e3,
                 "stream_bytes_per_frame": S, "voxels_per_frame": V}
         print(json.dumps(line))
     if world > 1:

@@ -237,3 +237,25 @@ def test_roundtrip_call_matches_separate_calls(K, oracle):
                                          [o.ctypes.data for o in outs], [max(1, n) for n in ns])
     assert lens2 == lens and cnts2 == cnts
     c.close()
+
+
+def test_config4_shape_4m_points_depth12(K, oracle):
+    """BASELINE configs[3] shape on one GPU: dense 4M-point frame, octree_bits 12 (realised depth 15), JPEG Q95."""
+    pts = synth.gen_surface(4000000, 0)
+    check_batch(K, oracle, [pts], K.default_params(octree_bits=12, jpeg_quality=95))
+
+
+def test_many_frames_in_one_call_all_groups_and_streams(K, oracle):
+    """more frames than streams x 1, mixed sizes: every stream gets a multi-frame group; spot-check against the oracle."""
+    clouds = [synth.gen_surface(40000 + 997 * (i % 7), 200 + i) for i in range(70)]
+    kp = K.default_params(octree_bits=9)
+    c = K.Codec(kp)
+    streams = c.encode_batch(clouds)
+    dec = c.decode_batch(streams)
+    op = oparams(oracle, kp)
+    for i in (0, 8, 9, 33, 69):
+        ref, _ = oracle.encode(clouds[i], op, frame_id=i + 1)
+        assert streams[i] == ref
+        assert np.array_equal(dec[i], oracle.decode(ref)[0])
+    assert c.frame_id == 70
+    c.close()
