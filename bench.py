@@ -336,7 +336,18 @@ def profile_roofline(K, lib, args, frames, alg_bytes_frame):
         traffic = int(t[name]) * frames_per_launch if name in t else None
     except Exception:
         pass
+    # the HBM-bound parallel kernels against their OWN algorithmic bytes (per frame: N points, V voxels), for context:
+    # the dominant kernel above is a serial dependency chain whose HBM fraction is tiny by construction
+    N_, V_ = float(len(frames[0])), (alg_bytes_frame - 32.0 * len(frames[0])) / 32.0 * 0.96
+    own = {"keygen_kernel": 32 * N_ + 12 * N_, "sort_pass_kernel": 24 * N_, "leaf_scan_kernel": 8 * N_ + 17 * V_,
+           "dec_points_kernel": 32 * V_ + 9 * V_ / 1.7, "hist_kernel": 1.6 * V_ + 0.25 * V_}
+    hbm_kernels = {}
+    for n_, ms_, k_, fpl_ in prof:
+        if n_ in own and ms_ > 0:
+            gbs = own[n_] * fpl_ / (ms_ / k_ / 1e3) / 1e9
+            hbm_kernels[n_] = {"own_algorithmic_bytes_per_frame": int(own[n_]), "avg_launch_ms": ms_ / k_, "achieved_GBs": gbs, "frac": gbs / peak}
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "hbm_bound_kernels_vs_own_bytes": hbm_kernels,
             "peak_source": which, "avg_launch_ms": avg_s * 1e3, "frames_per_launch": frames_per_launch,
             "algorithmic_bytes_per_frame": alg_bytes_frame, "share_of_step": tot_ms / total_ms,
             "kernels_ms": {r[0]: round(r[1], 4) for r in prof}}
