@@ -11,6 +11,8 @@
 #include "jpeg_enc_kernels.cuh"
 #include "entropy_kernels.cuh"
 #include "dec_kernels.cuh"
+#include "lines_kernels.cuh"
+#include "lines_dec_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -241,7 +243,9 @@ size_t carve_enc_slot(uint8_t *base, size_t n, EncFrame *f, const ccv2_params &p
   const uint32_t tiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE) + 1;
   const uint32_t scan_tiles = (uint32_t)(n / 1024) + 8;
   const size_t img_h = n / 256 + 1, mcu_h = (img_h + 15) / 16;
-  const size_t jbits_words = ((4 * n + 8192) / 4 + 63) & ~size_t(63);
+  const bool lines = prm.color_coding_type == 2;
+  const size_t lines_cap = n / LINE_PX + 2;
+  const size_t jbits_words = lines ? lines_cap * LINE_BITS_WORDS : (((4 * n + 8192) / 4 + 63) & ~size_t(63));
   // --- zero-initialised region first
   cv.off = 0;
   uint32_t *ghist = cv.take<uint32_t>(8 * 256);
@@ -257,14 +261,16 @@ size_t carve_enc_slot(uint8_t *base, size_t n, EncFrame *f, const ccv2_params &p
   uint32_t *leaf_start = cv.take<uint32_t>(n + 8), *leaf_off = cv.take<uint32_t>(n + 8);
   uint8_t *first_new = cv.take<uint8_t>(n + 8);
   uint8_t *avg = cv.take<uint8_t>(3 * n + 64);
-  int16_t *coef = cv.take<int16_t>(mcu_h * 16 * 384 + 64);
-  (void)prm;
+  int16_t *coef = cv.take<int16_t>((lines ? (n / 16 + 260) : mcu_h * 16) * 384 + 64);
+  uint8_t *line_slots = cv.take<uint8_t>(lines ? lines_cap * LINE_SLOT_BYTES : 16);
+  uint32_t *line_len = cv.take<uint32_t>(lines ? lines_cap : 4), *line_off = cv.take<uint32_t>(lines ? lines_cap : 4);
   if (f) {
     f->ghist = ghist; f->sort_status = sort_status; f->tiles_max = tiles; f->scan_status = scan_status; f->scan_tiles_max = scan_tiles;
     f->jbits_buf = jbits; f->jbits_cap_words = (uint32_t)jbits_words;
     f->keys[0] = k0; f->keys[1] = k1; f->vals[0] = v0; f->vals[1] = v1;
     f->leaf_key = leaf_key; f->leaf_start = leaf_start; f->leaf_off = leaf_off; f->first_new = first_new;
     f->avg = avg; f->coef = coef;
+    f->line_slots = line_slots; f->line_len = line_len; f->line_off = line_off; f->lines_cap = lines ? (uint32_t)lines_cap : 0;
   }
   if (zero_off) *zero_off = z0;
   if (zero_bytes) *zero_bytes = z1 - z0;
@@ -291,7 +297,6 @@ int check_params(const ccv2_params *p, std::string &err) {
   if (p->profile != CCV2_MANUAL_CONFIGURATION) { err = "only MANUAL_CONFIGURATION is implemented"; return CCV2_ERR_UNSUPPORTED; }
   if (!p->do_voxel_grid_downsampling) { err = "detail mode (doVoxelGridDownDownSampling=false) is not implemented"; return CCV2_ERR_UNSUPPORTED; }
   if (!(p->octree_resolution > 0)) { err = "octree_resolution must be > 0"; return CCV2_ERR_ARG; }
-  if (p->color_coding_type == 2) { err = "colorCodingType 2 (JPEG lines) is not implemented yet"; return CCV2_ERR_UNSUPPORTED; }
   if (p->color_coding_type > 3) { err = "unknown colorCodingType"; return CCV2_ERR_ARG; }
   if (p->color_bit_resolution > 8) { err = "colorBitResolution > 8"; return CCV2_ERR_ARG; }
   return CCV2_OK;
@@ -427,9 +432,10 @@ int ccv2_peek_point_count(const void *in_host, size_t len, uint64_t *npts) {
   return CCV2_OK;
 }
 
-static size_t carve_dec(uint8_t *base, size_t pcap, DecFrame *f, size_t *zero_off, size_t *zero_bytes) {
+static size_t carve_dec(uint8_t *base, size_t pcap, DecFrame *f, size_t *zero_off, size_t *zero_bytes, bool lines = false) {
   Carver cv(base);
-  const size_t img_h = pcap / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
+  const size_t lines_cap = lines ? pcap / LINE_PX + 2 : 0;
+  const size_t img_h = pcap / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = lines ? (lines_cap * LINE_MCU_STRIDE + LINE_MCU_STRIDE) * 6 : mcu_h * 16 * 6;
   const uint32_t scan_tiles = (uint32_t)(pcap / NODE_THREADS) + 8;
   uint64_t *scan_status = cv.take<uint64_t>(2 * (size_t)scan_tiles);
   int16_t *coef = cv.take<int16_t>(nblocks * 64 + 64);
@@ -445,6 +451,9 @@ static size_t carve_dec(uint8_t *base, size_t pcap, DecFrame *f, size_t *zero_of
   uint8_t *planes = cv.take<uint8_t>(mcu_h * 16 * 256 * 3 / 2 + 256);
   uint16_t *qt = cv.take<uint16_t>(128);
   uint8_t *scan = cv.take<uint8_t>(cpay_cap_for(pcap));
+  uint32_t *line_off = cv.take<uint32_t>(lines_cap + 4), *line_len = cv.take<uint32_t>(lines_cap + 4), *line_w = cv.take<uint32_t>(lines_cap + 4);
+  uint16_t *line_qt = cv.take<uint16_t>(lines_cap * 128 + 128);
+  uint8_t *line_planes = cv.take<uint8_t>(lines_cap * 8192 + 256);
   if (f) {
     f->scan_status = scan_status; f->scan_tiles_max = scan_tiles; f->coef = coef; f->coef_cap_blocks = (uint32_t)nblocks;
     f->tree = tree; f->tree_cap = (uint32_t)tree_cap_for(pcap) - 64; f->cen = cen; f->cen_cap = (uint32_t)cen_cap_for(pcap) - 64;
@@ -452,6 +461,7 @@ static size_t carve_dec(uint8_t *base, size_t pcap, DecFrame *f, size_t *zero_of
     f->node_prefix = node_prefix; f->node_byte = node_byte; f->node_cap = (uint32_t)pcap;
     f->l2_prefix = l2_prefix; f->l2_mask = l2_mask; f->l2_off = l2_off;
     f->planes = planes; f->planes_cap = (uint32_t)(mcu_h * 16 * 256 * 3 / 2); f->qt = qt; f->scan = scan;
+    f->lines_cap = (uint32_t)lines_cap; f->line_off = line_off; f->line_len = line_len; f->line_w = line_w; f->line_qt = line_qt; f->line_planes = line_planes;
   }
   if (zero_off) *zero_off = 0;
   if (zero_bytes) *zero_bytes = z1;
@@ -518,7 +528,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       f.zero_ptr = (uint8_t *)c->enc_slots.p + slot_bytes * slot + zoff; f.zero_bytes = zbytes;
       carve_enc_persist((uint8_t *)c->enc_persist.p + persist_off[i], npts[i], &f, cen);
       f.hist = (uint32_t *)((uint8_t *)c->enc_frames.p + frames_bytes) + (size_t)i * 3 * 256;
-      if (color && prm.color_coding_type != 1) f.avg = f.cpay;       // raw averages are the colour payload (types 0, 3)
+      if (color && (prm.color_coding_type == 0 || prm.color_coding_type == 3)) f.avg = f.cpay;   // raw averages are the colour payload
     }
     P.res = prm.octree_resolution;
     { int ex; double m = frexp(P.res, &ex); P.res_pow2 = (m == 0.5); P.inv_res = P.res_pow2 ? 1.0 / P.res : 0.0; }
@@ -540,7 +550,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       if (pts_cap[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; }
       if ((!rt && in_len[i] && !in[i]) || (pts_cap[i] && !pts_out[i])) return CCV2_ERR_ARG;
       size_t zo;
-      work_off[i + 1] = work_off[i] + carve_dec(nullptr, pts_cap[i], nullptr, &zo, &zb[i]);
+      work_off[i + 1] = work_off[i] + carve_dec(nullptr, pts_cap[i], nullptr, &zo, &zb[i], prm.color_coding_type == 2);
       din_dev[i] = rt ? 1 : (in_len[i] ? is_device_ptr(in[i]) : 1);
       dout_dev[i] = pts_cap[i] ? is_device_ptr(pts_out[i]) : 1;
       dinput_off[i + 1] = dinput_off[i] + (din_dev[i] ? 0 : ((in_len[i] + 64 + 255) & ~size_t(255)));
@@ -563,7 +573,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       }
       f.out_pts = dout_dev[i] ? (uint8_t *)pts_out[i] : (uint8_t *)c->dec_output.p + output_off[i];
       f.out_cap = pts_cap[i];
-      carve_dec((uint8_t *)c->dec_work.p + work_off[i], pts_cap[i], &f, nullptr, nullptr);
+      carve_dec((uint8_t *)c->dec_work.p + work_off[i], pts_cap[i], &f, nullptr, nullptr, prm.color_coding_type == 2);
       f.zero_ptr = (uint8_t *)c->dec_work.p + work_off[i]; f.zero_bytes = zb[i];
     }
   }
@@ -622,6 +632,13 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
         const size_t jb = 4 * gn + 8192;
         LAUNCH("jpeg_stuff_kernel", jpeg_stuff_kernel<<<dim3((unsigned)((jb + STUFF_THREADS * STUFF_BYTES - 1) / (STUFF_THREADS * STUFF_BYTES)), gf), STUFF_THREADS, 0, st>>>(dg, c->d_tables));
       }
+      if (color && prm.color_coding_type == 2) {
+        const unsigned lines_max = (unsigned)(gn / LINE_PX + 1), mcus_max = (unsigned)(gn / 16 + 256);
+        LAUNCH("lines_mcu_kernel", lines_mcu_kernel<<<dim3(mcus_max, gf), 256, 0, st>>>(dg, c->d_tables));
+        LAUNCH("lines_huff_kernel", lines_huff_kernel<<<dim3(lines_max, gf), 256, 0, st>>>(dg, c->d_tables));
+        LAUNCH("lines_offsets_kernel", lines_offsets_kernel<<<gf, 1024, 0, st>>>(dg));
+        LAUNCH("lines_copy_kernel", lines_copy_kernel<<<dim3(lines_max, gf), 256, 0, st>>>(dg));
+      }
       const size_t hmax = std::max(tree_cap_for(gn), cpay_cap_for(gn));
       LAUNCH("hist_kernel", hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), 3, gf), 256, 0, st>>>(dg));
       LAUNCH("rc_encode_kernel", rc_encode_kernel<<<c->n_sm, 96, 0, st>>>(dg, f0, gf, cen, color));
@@ -648,6 +665,12 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       LAUNCH("dec_expand_kernel", dec_expand_kernel<<<dim3((unsigned)((pmax + 255) / 256), gf), 256, 0, st>>>(dg));
       LAUNCH("jpeg_destuff_kernel", jpeg_destuff_kernel<<<gf, 1024, 0, st>>>(dg));
       LAUNCH("dec_serial_kernel", dec_serial_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf));
+      if (prm.color_coding_type == 2) {
+        const unsigned lines_max = (unsigned)(pmax / LINE_PX + 2);
+        LAUNCH("lines_index_kernel", lines_index_kernel<<<gf, 32, 0, st>>>(dg));
+        LAUNCH("lines_decode_kernel", lines_decode_kernel<<<dim3(lines_max, gf), 32, 0, st>>>(dg));
+        LAUNCH("lines_idct_kernel", lines_idct_kernel<<<dim3((unsigned)(((size_t)lines_max * LINE_MCU_STRIDE + LINE_MCU_STRIDE) * 6 / 32 + 1), gf), 256, 0, st>>>(dg, c->d_tables));
+      }
       const size_t img_h = pmax / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
       LAUNCH("jpeg_idct_kernel", jpeg_idct_kernel<<<dim3((unsigned)((nblocks + 31) / 32), gf), 256, 0, st>>>(dg, c->d_tables));
       LAUNCH("dec_points_kernel", dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg));

@@ -71,6 +71,7 @@ struct EncFrame {
   int16_t *coef;               // jpeg coefficients [mcu][6][64] zigzag order
   uint32_t *jbits_buf;         // unstuffed entropy-coded bits
   uint32_t jbits_cap_words, _pad4;
+  uint8_t *line_slots; uint32_t *line_len, *line_off; uint32_t lines_cap, _padl;   // LINES colour mode staging
   // per-frame persistent buffers (live until the frame's stream is assembled)
   uint8_t *tree; uint32_t tree_cap; uint32_t _pad5;
   uint8_t *cen;                // centroid residual bytes
@@ -108,6 +109,8 @@ struct DecFrame {
   uint16_t *qt;                                  // [2][64] zigzag order, written by the jpeg header parse
   uint8_t *scan; uint32_t scan_start, scan_len;  // de-stuffed entropy-coded segment of the jpeg
   uint32_t dht_off[4], dht_n[4];                 // offsets of the DHT bits[16] (values follow) inside col: dc0 dc1 ac0 ac1
+  uint32_t n_lines, lines_cap;                   // LINES colour mode: per-line offset/length/width, quant tables, row planes
+  uint32_t *line_off, *line_len, *line_w; uint16_t *line_qt; uint8_t *line_planes;
   uint64_t *scan_status; uint32_t scan_tiles_max, _pad7;
 };
 

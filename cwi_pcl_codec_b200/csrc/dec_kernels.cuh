@@ -369,8 +369,10 @@ __device__ inline void dfs_walk(DecFrame &f) {
 
 // ---- stage 2b: JPEG of the single SNAKE image: marker parse (serial, short), parallel de-stuffing of the
 // entropy-coded segment, serial Huffman decode (no restart markers => one dependent bit stream per image)
-__device__ inline uint32_t jpeg_parse_header(DecFrame &f) {   // returns FERR_* bits (0 = ok); the caller decides whether they count
-  const uint8_t *in = f.col; const uint32_t len = f.ncol;
+struct JpegInfo { uint32_t w, h, scan, dht_off[4], dht_n[4]; };
+// marker parse of one baseline JFIF file as libjpeg writes it for jpeg_io's settings (3 components, 2x2 / 1x1 / 1x1,
+// no restart markers).  qt receives the two quantisation tables in zigzag order.  Returns false on anything else.
+__device__ inline bool jpeg_parse(const uint8_t *in, uint32_t len, JpegInfo &o, uint16_t *qt) {
   bool bad = false;
   uint32_t w = 0, h = 0, scan = 0, have = 0;
   if (len < 4 || in[0] != 0xFF || in[1] != 0xD8) bad = true;
@@ -381,33 +383,41 @@ __device__ inline uint32_t jpeg_parse_header(DecFrame &f) {   // returns FERR_* 
     const uint8_t *s = in + pos + 4;
     if (L < 2 || pos + 2 + L > len) { bad = true; break; }
     if (m == 0xDB) {
-      uint32_t o = 0;
-      while (o + 65 <= L - 2) { uint32_t t = s[o] & 15; if ((s[o] >> 4) || t > 1) { bad = true; break; } for (int i = 0; i < 64; i++) f.qt[t * 64 + i] = s[o + 1 + i]; have |= 1u << t; o += 65; }   // zigzag order kept
+      uint32_t q = 0;
+      while (q + 65 <= L - 2) { uint32_t t = s[q] & 15; if ((s[q] >> 4) || t > 1) { bad = true; break; } for (int i = 0; i < 64; i++) qt[t * 64 + i] = s[q + 1 + i]; have |= 1u << t; q += 65; }
     } else if (m == 0xC0) {
       if (L < 17) { bad = true; break; }
       h = ((uint32_t)s[1] << 8) | s[2]; w = ((uint32_t)s[3] << 8) | s[4];
       if (s[0] != 8 || s[5] != 3 || s[7] != 0x22 || s[10] != 0x11 || s[13] != 0x11 || s[8] != 0 || s[11] != 1 || s[14] != 1) bad = true;
     } else if (m == 0xC4) {
-      uint32_t o = 0;
-      while (o + 17 <= L - 2) {
-        uint32_t tc = s[o] >> 4, th = s[o] & 15, nv = 0;
+      uint32_t q = 0;
+      while (q + 17 <= L - 2) {
+        uint32_t tc = s[q] >> 4, th = s[q] & 15, nv = 0;
         if (tc > 1 || th > 1) { bad = true; break; }
-        for (int i = 0; i < 16; i++) nv += s[o + 1 + i];
-        if (nv > 256 || o + 17 + nv > L - 2) { bad = true; break; }
-        f.dht_off[tc * 2 + th] = pos + 4 + o + 1; f.dht_n[tc * 2 + th] = nv;
+        for (int i = 0; i < 16; i++) nv += s[q + 1 + i];
+        if (nv > 256 || q + 17 + nv > L - 2) { bad = true; break; }
+        o.dht_off[tc * 2 + th] = pos + 4 + q + 1; o.dht_n[tc * 2 + th] = nv;
         have |= 4u << (tc * 2 + th);
-        o += 17 + nv;
+        q += 17 + nv;
       }
     } else if (m == 0xDA) { scan = pos + 2 + L; break; }
     else if (m == 0xC2 || m == 0xDD) { bad = true; break; }      // progressive / restart intervals: libjpeg as driven by jpeg_io never emits them
     pos += 2 + L;
   }
-  if (!scan || w != 256 || h == 0 || have != 0x3F) bad = true;  // SNAKE images are 256 wide (cjpeg.h:197)
-  const uint32_t mcu_w = (w + 15) / 16, mcu_h = (h + 15) / 16, nblocks = mcu_w * mcu_h * 6;
+  if (!scan || w == 0 || h == 0 || have != 0x3F) bad = true;
+  o.w = w; o.h = h; o.scan = scan;
+  return !bad;
+}
+__device__ inline uint32_t jpeg_parse_header(DecFrame &f) {   // SNAKE image of the frame; returns FERR_* bits (0 = ok)
+  JpegInfo ji;
+  bool ok = jpeg_parse(f.col, f.ncol, ji, f.qt);
+  if (ok && ji.w != 256) ok = false;                             // SNAKE images are 256 wide (cjpeg.h:197)
+  const uint32_t mcu_w = 16, mcu_h = ok ? (ji.h + 15) / 16 : 0, nblocks = mcu_w * mcu_h * 6;
   uint32_t eb = 0;
-  if (!bad && nblocks > f.coef_cap_blocks) { bad = true; eb |= FERR_JPEG_CAP; }
-  if (bad) { f.img_w = f.img_h = f.mcu_w = f.mcu_h = f.n_blocks = 0; f.scan_start = f.scan_len = 0; return eb | FERR_BAD_STREAM; }
-  f.img_w = w; f.img_h = h; f.mcu_w = mcu_w; f.mcu_h = mcu_h; f.n_blocks = nblocks; f.scan_start = scan;
+  if (ok && nblocks > f.coef_cap_blocks) { ok = false; eb |= FERR_JPEG_CAP; }
+  if (!ok) { f.img_w = f.img_h = f.mcu_w = f.mcu_h = f.n_blocks = 0; f.scan_start = f.scan_len = 0; return eb | FERR_BAD_STREAM; }
+  for (int t = 0; t < 4; t++) { f.dht_off[t] = ji.dht_off[t]; f.dht_n[t] = ji.dht_n[t]; }
+  f.img_w = ji.w; f.img_h = ji.h; f.mcu_w = mcu_w; f.mcu_h = mcu_h; f.n_blocks = nblocks; f.scan_start = ji.scan;
   return 0;
 }
 
@@ -442,10 +452,13 @@ __global__ void __launch_bounds__(1024) jpeg_destuff_kernel(DecFrame *frames) {
 }
 
 // de-stuffing by one warp (speculative colour path inside dec_entropy_kernel): 4 bytes per lane per step
+__device__ inline uint32_t warp_destuff_span(const uint8_t *in, uint32_t n, uint8_t *out);
 __device__ inline void warp_destuff(DecFrame &f) {
+  const uint32_t len = warp_destuff_span(f.col + f.scan_start, f.ncol - f.scan_start, f.scan);
+  if (lane_id() == 0) f.scan_len = len;
+}
+__device__ inline uint32_t warp_destuff_span(const uint8_t *in, uint32_t n, uint8_t *out) {
   const uint32_t lane = lane_id();
-  const uint8_t *in = f.col + f.scan_start;
-  uint32_t n = f.ncol - f.scan_start;
   if (n >= 2 && in[n - 2] == 0xFF && in[n - 1] == 0xD9) n -= 2;     // EOI
   uint32_t obase = 0, carry = 0;
   for (uint32_t c0 = 0; c0 < n; c0 += 128) {
@@ -460,11 +473,11 @@ __device__ inline void warp_destuff(DecFrame &f) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL_MASK, inc, o); if (lane >= (uint32_t)o) inc += t; }
     uint32_t o = obase + inc - cnt;
-    for (uint32_t k = 0; k < nv; k++) if (keep >> k & 1) f.scan[o++] = (uint8_t)by[k];
+    for (uint32_t k = 0; k < nv; k++) if (keep >> k & 1) out[o++] = (uint8_t)by[k];
     obase += __shfl_sync(FULL_MASK, inc, 31);
     carry = __shfl_sync(FULL_MASK, by[3], 31);
   }
-  if (lane == 0) f.scan_len = obase;
+  return obase;
 }
 
 struct JBits {               // MSB-first bit reader over the de-stuffed segment, 32-bit big-endian refills, next word prefetched
@@ -504,13 +517,17 @@ __device__ inline void huff_build(HuffDec &h, const uint8_t *bits, const uint8_t
 }
 __device__ __forceinline__ int jextend(int v, int n) { return n == 0 ? 0 : (v < (1 << (n - 1)) ? v - (1 << n) + 1 : v); }
 
+__device__ inline void huff_decode_blocks(const uint8_t *scan, uint32_t scan_len, uint32_t nblocks, short *coef, const HuffDec *hd);
 __device__ inline void jpeg_huff_decode(DecFrame &f, HuffDec *hd /* smem[4]: dc0 dc1 ac0 ac1 */) {
   const uint32_t nblocks = f.n_blocks;
   if (nblocks == 0) return;
   for (int t = 0; t < 4; t++) huff_build(hd[t], f.col + f.dht_off[t], f.col + f.dht_off[t] + 16, (int)f.dht_n[t]);
-  JBits br; br.init(f.scan, f.scan_len);
+  huff_decode_blocks(f.scan, f.scan_len, nblocks, f.coef, hd);
+}
+// serial Huffman decode of `nblocks` blocks in MCU order (Y0 Y1 Y2 Y3 Cb Cr); coef is pre-zeroed, zigzag order, quantised
+__device__ inline void huff_decode_blocks(const uint8_t *scan, uint32_t scan_len, uint32_t nblocks, short *coef, const HuffDec *hd) {
+  JBits br; br.init(scan, scan_len);
   int pred[3] = { 0, 0, 0 };
-  short *coef = f.coef;                                   // pre-zeroed; zigzag order, quantised
   uint32_t blk = 0;
   for (uint32_t g = 0; g < nblocks; g++) {
     const int comp = blk < 4 ? 0 : (int)blk - 3; const int ts = comp ? 1 : 0;
@@ -612,8 +629,10 @@ __global__ void __launch_bounds__(256) jpeg_idct_kernel(DecFrame *frames, const 
 
 // ---- stage 4: expand bottom-level branches into leaves (chained scan of popcounts) and write the points
 #define NODE_THREADS 256
+__device__ __forceinline__ uint32_t dec_color_lines(const DecFrame &f, uint32_t i);
 __device__ __forceinline__ uint32_t dec_color(const DecFrame &f, uint32_t i) {
   if (!f.data_with_color) return 0x00FFFFFFu;                 // [PCL] setDefaultColor (white, alpha 0)
+  if (f.cct == 2) return dec_color_lines(f, i);
   if (f.cct != 1) {
     if (3ull * i + 2 >= f.ncol) return 0;
     const uint32_t red = f.cct == 0 ? 8 - f.color_bits : 0;

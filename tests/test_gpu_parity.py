@@ -67,6 +67,9 @@ CASES = {
     "centroid": (lambda: [synth.gen_surface(30000, 12)], dict(octree_bits=7, keep_centroid=1)),
     "q50": (lambda: [synth.gen_surface(50000, 13)], dict(octree_bits=10, jpeg_quality=50)),
     "q100_random_colour": (lambda: [synth.gen_uniform(30000, 14)], dict(octree_bits=9, jpeg_quality=100)),
+    "lines_type2": (lambda: [synth.gen_surface(20000, 20), synth.gen_uniform(9000, 21)], dict(octree_bits=9, color_coding_type=2)),
+    "lines_type2_edge_widths": (lambda: [synth.gen_surface(1500, 22), synth.gen_surface(2, 23), synth.gen_uniform(2049, 24), synth.gen_uniform(4097, 25), synth.gen_uniform(6143, 26)],
+                                dict(octree_bits=10, color_coding_type=2, jpeg_quality=60)),
     "duplicates_one_voxel": (lambda: [np.repeat(synth.gen_surface(7, 15), 3000)], dict(octree_bits=5)),
 }
 

@@ -120,6 +120,8 @@ def main():
         ("nocolor", [synth.gen_surface(20000, 11)], P(octree_bits=9, color_bits=0)),
         ("centroid", [synth.gen_surface(30000, 12)], P(octree_bits=7, keep_centroid=1)),
         ("q50", [synth.gen_surface(50000, 13)], P(octree_bits=10, jpeg_quality=50)),
+        ("lines_type2", [synth.gen_surface(20000, 20), synth.gen_uniform(9000, 21)], P(octree_bits=9, color_coding_type=2)),
+        ("lines_small", [synth.gen_surface(1500, 22), synth.gen_surface(2, 23), synth.gen_uniform(2049, 24), synth.gen_uniform(4097, 25)], P(octree_bits=10, color_coding_type=2, jpeg_quality=60)),
     ]
     # non-finite points and a late bbox violator (slow path)
     a = synth.gen_surface(40000, 14)
@@ -134,6 +136,7 @@ def main():
     if big:
         cases.append(("surf1M_d11", [synth.gen_surface(1000000, 0)], P(octree_bits=11)))
         cases.append(("unif1M_d11", [synth.gen_uniform(1000000, 0)], P(octree_bits=11)))
+        cases.append(("lines1M_d11", [synth.gen_surface(1000000, 1)], P(octree_bits=11, color_coding_type=2)))
     for name, clouds, kp in cases:
         try:
             run_case(name, clouds, kp, results)
