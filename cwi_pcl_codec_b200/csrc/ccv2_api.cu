@@ -94,6 +94,8 @@ struct ccv2_codec {
   int n_sm = 148;
   int trace = 0;                          // CCV2_TRACE=1: print per-group timeline (ms since batch start) to stderr
   std::vector<cudaEvent_t> ev_trace;
+  struct TraceMark { int group; const char *label; };
+  std::vector<TraceMark> trace_marks;
   int use_ring = 1;                       // pipeline the DFS walk behind the range decoder (CCV2_NO_RING=1 disables: debugging)
   int n_streams = 8, group = 0;           // group 0 = auto: spread the batch over all streams
   cudaStream_t main_stream = nullptr;
@@ -104,6 +106,8 @@ struct ccv2_codec {
   std::vector<cudaEvent_t> ev_group;
   JpegTables *d_tables = nullptr;
   uint32_t *d_frame_counter = nullptr;
+  int serial_cap = 0;                     // serial CTAs per SM; 0: ceil(frames in the call / SMs)  (CCV2_CAP overrides, -1 disables the cap)
+  size_t smem_sm = 0, smem_static_enc = 0, smem_static_dec = 0;   // shared memory per SM; static use of the two serial kernels
   uint32_t frame_id = 0;
   // encode workspaces
   DevBuf enc_frames, enc_slots, enc_persist, enc_input;
@@ -345,9 +349,10 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   ccv2_codec *c = new ccv2_codec();
   c->prm = *p; c->device = device;
   if (const char *s = getenv("CCV2_TRACE")) c->trace = atoi(s);
+  if (const char *s = getenv("CCV2_CAP")) c->serial_cap = atoi(s);
   if (const char *s = getenv("CCV2_NO_RING")) c->use_ring = atoi(s) ? 0 : 1;
   if (const char *s = getenv("CCV2_STREAMS")) c->n_streams = std::max(1, std::min(MAX_STREAMS, atoi(s)));
-  if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(64, atoi(s)));
+  if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(1024, atoi(s)));
   auto fail = [&](cudaError_t ee, const char *what) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ee); ccv2_destroy(c); return CCV2_ERR_CUDA; };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
   if ((e = cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail(e, "cudaDeviceGetAttribute");
@@ -372,6 +377,20 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   if ((e = cudaMemcpy(c->d_tables, &T, sizeof T, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "cudaMemcpy");
   if ((e = cudaMalloc(&c->d_frame_counter, 4)) != cudaSuccess) return fail(e, "cudaMalloc");
   if ((e = cudaMemset(c->d_frame_counter, 0, 4)) != cudaSuccess) return fail(e, "cudaMemset");
+  {
+    cudaFuncAttributes fa; int per_sm = 0, per_block = 0;
+    if ((e = cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device)) != cudaSuccess) return fail(e, "cudaDeviceGetAttribute");
+    if ((e = cudaDeviceGetAttribute(&per_block, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) return fail(e, "cudaDeviceGetAttribute");
+    c->smem_sm = (size_t)per_sm;
+    if ((e = cudaFuncGetAttributes(&fa, rc_encode_kernel)) != cudaSuccess) return fail(e, "cudaFuncGetAttributes");
+    c->smem_static_enc = fa.sharedSizeBytes;
+    if ((e = cudaFuncSetAttribute(rc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, per_block - (int)fa.sharedSizeBytes)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if ((e = cudaFuncGetAttributes(&fa, dec_entropy_kernel)) != cudaSuccess) return fail(e, "cudaFuncGetAttributes");
+    c->smem_static_dec = fa.sharedSizeBytes;
+    if ((e = cudaFuncSetAttribute(dec_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, per_block - (int)fa.sharedSizeBytes)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    cudaFuncSetAttribute(rc_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(dec_entropy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   *out = c;
   return CCV2_OK;
 }
@@ -488,7 +507,13 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
   cudaStream_t ms = c->main_stream;
   CU(c->h_results.ensure(sizeof(FrameResult) * nframes));
   FrameResult *hres = (FrameResult *)c->h_results.p;
-  if (c->trace) while ((int)c->ev_trace.size() < 4 * ngroups) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); c->ev_trace.push_back(ev); }
+  c->trace_marks.clear();
+  auto mark = [&](int g, const char *label, cudaStream_t s) {       // CCV2_TRACE: timestamp on the group's stream
+    if (!c->trace) return;
+    if (c->ev_trace.size() <= c->trace_marks.size()) { cudaEvent_t ev; if (cudaEventCreate(&ev) != cudaSuccess) return; c->ev_trace.push_back(ev); }
+    cudaEventRecord(c->ev_trace[c->trace_marks.size()], s);
+    c->trace_marks.push_back({g, label});
+  };
 
   // ------------------------------------------------------------------ encode side set-up
   size_t nmax = 1, zoff = 0, zbytes = 0, slot_bytes = 0, frames_bytes = 0;
@@ -585,6 +610,14 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
     CU(cudaMemsetAsync((uint8_t *)c->enc_frames.p + frames_bytes, 0, (size_t)nframes * 3 * 256 * 4, ms));
   }
   if (do_dec) CU(cudaMemcpyAsync(dd, hd, sizeof(DecFrame) * nframes, cudaMemcpyHostToDevice, ms));
+  // serial CTAs reserve enough shared memory (1 KB per CTA is the system's) that only serial_cap of them fit on an SM
+  const int serial_cap = c->serial_cap ? c->serial_cap : (nframes + c->n_sm - 1) / c->n_sm;
+  size_t serial_smem_enc = 0, serial_smem_dec = 0;
+  if (serial_cap > 0 && serial_cap <= 14 && !c->profiling) {
+    const size_t per_cta = (c->smem_sm / 1024 / (size_t)(serial_cap + 1) + 1) * 1024;
+    if (per_cta > c->smem_static_enc + 1024) serial_smem_enc = per_cta - c->smem_static_enc - 1024;
+    if (per_cta > c->smem_static_dec + 1024) serial_smem_dec = per_cta - c->smem_static_dec - 1024;
+  }
   cudaEvent_t ev_setup = c->ev_fork;
   CU(cudaEventRecord(ev_setup, ms));
   uint64_t launches = 0;
@@ -592,6 +625,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
   for (int g = 0; g < ngroups; g++) {
     cudaStream_t st = c->streams[g % NS];
     const int f0 = g * G, gf = std::min(G, nframes - f0);
+    const unsigned steered_grid = (unsigned)((gf + c->n_sm - 1) / c->n_sm * c->n_sm);
     CU(cudaStreamWaitEvent(st, ev_setup, 0));
     if (do_enc) {
       EncFrame *dg = df + f0;
@@ -610,7 +644,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       }
       LAUNCH("zero_region_kernel", zero_region_kernel<EncFrame><<<dim3(128, gf), 256, 0, st>>>(dg));
       if (any_h2d) { CU(cudaEventRecord(c->ev_h2d[g], c->copy_stream)); CU(cudaStreamWaitEvent(st, c->ev_h2d[g], 0)); }
-      if (c->trace) CU(cudaEventRecord(c->ev_trace[4 * g + 0], st));
+      mark(g, "inputs", st);
       const unsigned gx256 = (unsigned)((gn + 255) / 256), gtiles = (unsigned)((gn + SORT_TILE - 1) / SORT_TILE);
       LAUNCH("bbox_kernel", bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 0));
       LAUNCH("bbox_fixup_kernel", bbox_fixup_kernel<<<gf, 32, 0, st>>>(dg, P));
@@ -640,10 +674,11 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
         LAUNCH("lines_copy_kernel", lines_copy_kernel<<<dim3(lines_max, gf), 256, 0, st>>>(dg));
       }
       const size_t hmax = std::max(tree_cap_for(gn), cpay_cap_for(gn));
+      mark(g, "leaves", st);
       LAUNCH("hist_kernel", hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), 3, gf), 256, 0, st>>>(dg));
-      LAUNCH("rc_encode_kernel", rc_encode_kernel<<<c->n_sm, 96, 0, st>>>(dg, f0, gf, cen, color));
+      LAUNCH("rc_encode_kernel", rc_encode_kernel<<<gf, 96, serial_smem_enc, st>>>(dg, cen, color));
       LAUNCH("assemble_kernel", assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H));
-      if (c->trace) CU(cudaEventRecord(c->ev_trace[4 * g + 1], st));
+      mark(g, "encoded", st);
     }
     if (do_dec) {
       DecFrame *dg = dd + f0;
@@ -661,10 +696,11 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       LAUNCH("zero_region_kernel", zero_region_kernel<DecFrame><<<dim3(64, gf), 256, 0, st>>>(dg));
       if (any_h2d) { CU(cudaEventRecord(c->ev_h2d[g], c->copy_stream)); CU(cudaStreamWaitEvent(st, c->ev_h2d[g], 0)); }
       if (rt) LAUNCH("link_kernel", link_kernel<<<(gf + 63) / 64, 64, 0, st>>>(df + f0, dg, gf));
-      LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<c->n_sm, 96, 0, st>>>(dg, f0, gf, c->use_ring));
+      LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<gf, 96, serial_smem_dec, st>>>(dg, c->use_ring));
+      mark(g, "entropy", st);
       LAUNCH("dec_expand_kernel", dec_expand_kernel<<<dim3((unsigned)((pmax + 255) / 256), gf), 256, 0, st>>>(dg));
       LAUNCH("jpeg_destuff_kernel", jpeg_destuff_kernel<<<gf, 1024, 0, st>>>(dg));
-      LAUNCH("dec_serial_kernel", dec_serial_kernel<<<c->n_sm, 64, 0, st>>>(dg, f0, gf));
+      LAUNCH("dec_serial_kernel", dec_serial_kernel<<<steered_grid, 64, 0, st>>>(dg, f0, gf));
       if (prm.color_coding_type == 2) {
         const unsigned lines_max = (unsigned)(pmax / LINE_PX + 2);
         LAUNCH("lines_index_kernel", lines_index_kernel<<<gf, 32, 0, st>>>(dg));
@@ -674,7 +710,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       const size_t img_h = pmax / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
       LAUNCH("jpeg_idct_kernel", jpeg_idct_kernel<<<dim3((unsigned)((nblocks + 31) / 32), gf), 256, 0, st>>>(dg, c->d_tables));
       LAUNCH("dec_points_kernel", dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg));
-      if (c->trace) CU(cudaEventRecord(c->ev_trace[4 * g + 2], st));
+      mark(g, "decoded", st);
     }
     LAUNCH("publish_kernel", publish_kernel<<<(gf + 63) / 64, 64, 0, st>>>(do_enc ? df + f0 : nullptr, do_dec ? dd + f0 : nullptr, hres + f0, gf));
     CU(cudaEventRecord(c->ev_group[ngroups + g], st));
@@ -728,7 +764,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
     // full frame records (metrics, debug hook) come back last on this stream
     if (do_enc) CU(cudaMemcpyAsync(hf + f0, df + f0, sizeof(EncFrame) * gf, cudaMemcpyDeviceToHost, st));
     if (do_dec) CU(cudaMemcpyAsync(hd + f0, dd + f0, sizeof(DecFrame) * gf, cudaMemcpyDeviceToHost, st));
-    if (c->trace) CU(cudaEventRecord(c->ev_trace[4 * g + 3], st));
+    mark(g, "copied", st);
     CU(cudaEventRecord(ev, st));
     CU(cudaStreamWaitEvent(ms, ev, 0));
   }
@@ -738,11 +774,24 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
   if (c->trace) {
     fprintf(stderr, "ccv2 trace mode=%d frames=%d groups=%d total %.1f ms\n", mode, nframes, ngroups, c->device_ms);
     for (int g = 0; g < ngroups; g++) {
-      float t[4] = {-1, -1, -1, -1};
-      if (do_enc) { cudaEventElapsedTime(&t[0], c->ev_start, c->ev_trace[4 * g + 0]); cudaEventElapsedTime(&t[1], c->ev_start, c->ev_trace[4 * g + 1]); }
-      if (do_dec) cudaEventElapsedTime(&t[2], c->ev_start, c->ev_trace[4 * g + 2]);
-      cudaEventElapsedTime(&t[3], c->ev_start, c->ev_trace[4 * g + 3]);
-      fprintf(stderr, "  group %2d: inputs on device %.1f | encode done %.1f | decode done %.1f | results copied %.1f\n", g, t[0], t[1], t[2], t[3]);
+      fprintf(stderr, "  group %2d:", g);
+      for (size_t k = 0; k < c->trace_marks.size(); k++) if (c->trace_marks[k].group == g) {
+        float t = -1; cudaEventElapsedTime(&t, c->ev_start, c->ev_trace[k]);
+        fprintf(stderr, " %s %.1f |", c->trace_marks[k].label, t);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
+  if (c->trace) {                                            // how evenly did the serial CTAs spread?  (frame records are back on the host)
+    for (int dir = 0; dir < 2; dir++) {
+      if (dir == 0 ? !do_enc : !do_dec) continue;
+      std::vector<int> per_sm(256, 0);
+      for (int i = 0; i < nframes; i++) per_sm[(dir == 0 ? hf[i].serial_sm : hd[i].serial_sm) & 255]++;
+      std::vector<int> hist(64, 0); int mx = 0;
+      for (int s2 = 0; s2 < c->n_sm; s2++) { hist[std::min(63, per_sm[s2])]++; mx = std::max(mx, per_sm[s2]); }
+      fprintf(stderr, "  %s serial CTAs per SM (cap %d):", dir == 0 ? "encode" : "decode", serial_cap);
+      for (int k = 0; k <= mx; k++) fprintf(stderr, " %dx%d", hist[k], k);
+      fprintf(stderr, "\n");
     }
   }
   prof_collect(c);

@@ -43,7 +43,7 @@ struct EncFrame {
   // region of the group-slot workspace that must be zero before the pipeline starts (zero_region_kernel)
   uint8_t *zero_ptr; uint64_t zero_bytes;
   // input
-  const uint8_t *pts; uint32_t n; uint32_t _pad0;
+  const uint8_t *pts; uint32_t n; uint32_t serial_sm;   // serial_sm: SM the range-coder CTA ran on (CCV2_TRACE)
   // bbox / keys
   double bmin[3], bmax[3];
   uint32_t depth, defined, n_finite, violator, rekey, npasses;
@@ -95,7 +95,7 @@ struct DecFrame {
   uint32_t walk_done, huff_done;                 // DFS walk / JPEG Huffman decode already done inside dec_entropy_kernel
   uint32_t img_w, img_h, mcu_w, mcu_h, n_blocks;
   uint32_t ticket[TK_COUNT];
-  uint32_t error, _pad0;
+  uint32_t error, serial_sm;
   uint64_t coded[3];
   // buffers
   uint8_t *tree; uint32_t tree_cap, _pad1;
@@ -218,6 +218,17 @@ __device__ __forceinline__ int steered_frame(uint32_t first_slot, uint32_t group
   const uint32_t f = (blockIdx.x + g - first_slot % g) % g;
   return f < group_frames ? (int)f : -1;
 }
+
+// ---- serial CTAs: at most `cap` per SM, enforced by the hardware ------------------------------------------------------
+// The range-coder kernels run one CTA per frame and are latency bound, so what matters is how many of them share an
+// SM.  Which SM a CTA lands on is the block scheduler's choice, and with eight groups launching serial kernels between
+// each other's parallel kernels it is far from even (measured with CCV2_TRACE, which records %smid per frame: up to
+// 10 serial CTAs on one SM while 9 SMs had none; one group ran at the solo time of 189 ms, the others took 400-600 ms,
+// against 230 ms when every SM holds exactly four).  Steering by block index or letting surplus CTAs exit when their
+// SM is full (both tried) depend on the scheduler's policy.  What does not: a serial CTA asks for so much dynamic
+// shared memory that only `cap` of them fit on an SM (cap = ceil(frames in the call / SMs)); the scheduler then has
+// to put the next one on another SM, whatever else is running.  The memory itself is not used.
+__device__ __forceinline__ uint32_t sm_id() { uint32_t v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
 
 // Zeroing as a kernel on the group's own stream.  cudaMemsetAsync goes through a shared in-order engine: a memset queued
 // behind a long kernel on one stream held back the memsets (and so the start) of every other group (measured with

@@ -27,10 +27,9 @@ __device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *
 // result only if its own position after the preceding layers lands exactly there, otherwise it decodes the layer
 // itself as the reference would.
 struct SpecColour { volatile uint32_t state; uint32_t pos, ncol, coded, jerr; uint32_t with_color, cct; };
-__global__ void __launch_bounds__(96) dec_entropy_kernel(DecFrame *frames, int first_slot, int group_frames, int use_ring) {
-  const int fi = steered_frame(first_slot, group_frames);
-  if (fi < 0) return;
-  DecFrame &f = frames[fi];
+__global__ void __launch_bounds__(96) dec_entropy_kernel(DecFrame *frames, int use_ring) {
+  DecFrame &f = frames[blockIdx.x];
+  if (threadIdx.x == 0) f.serial_sm = sm_id();
   __shared__ uint32_t freq[257], freq2[257];
   __shared__ WalkRing rg;
   __shared__ SpecColour sc;

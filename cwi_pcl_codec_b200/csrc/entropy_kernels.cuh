@@ -63,10 +63,9 @@ __device__ __forceinline__ uint32_t rc_equal_bits(uint32_t x) {
 }
 
 // ---- range encoder: one block per frame (steered over the SMs), one warp per layer (tree, centroid, colour)
-__global__ void __launch_bounds__(96) rc_encode_kernel(EncFrame *frames, int first_slot, int group_frames, int do_centroid, int do_color) {
-  const int fi = steered_frame(first_slot, group_frames);
-  if (fi < 0) return;
-  EncFrame &f = frames[fi];
+__global__ void __launch_bounds__(96) rc_encode_kernel(EncFrame *frames, int do_centroid, int do_color) {
+  EncFrame &f = frames[blockIdx.x];
+  if (threadIdx.x == 0) f.serial_sm = sm_id();
   if (f.V == 0) return;
   const int which = threadIdx.x >> 5;
   if ((which == 1 && !do_centroid) || (which == 2 && !do_color)) return;
