@@ -3,9 +3,10 @@
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C ABI)
   python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithm (the oracle port, all host cores)
 
-A "step" is one pass of the hot path over one batch of F frames: every cloud is encoded and the stream it produced is
-decoded again (ccv2_roundtrip_batch: one pipelined C-ABI call; --value-api separate uses ccv2_encode_batch followed by
-ccv2_decode_batch instead).  `value` is measured with the clouds already resident in HBM
+A "step" is one pass of the hot path over one batch of F frames: ccv2_encode_batch over the F clouds followed by
+ccv2_decode_batch over the F streams it produced (--value-api roundtrip uses the pipelined ccv2_roundtrip_batch call
+instead; the end-to-end leg with host buffers uses the round trip by default, --e2e-api separate switches it).
+`value` is measured with the clouds already resident in HBM
 (device pointers in, device pointers out); `e2e` is the same work through the C ABI with pinned HOST buffers
 (ccv2_roundtrip_batch: encode -> decode per frame in one pipelined call, like evaluate_compression's per-frame
 loop), so the host->device copy of every cloud and the device->host copy of every stream and decoded cloud are
@@ -150,13 +151,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--frames", type=int, default=int(os.environ.get("BENCH_FRAMES", "512")), help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=int(os.environ.get("BENCH_FRAMES", "0")),
+                    help="frames per step per GPU (0: as many as fit in device memory, at most 1024 -- the serial entropy stage is latency bound, so throughput grows with the frames in flight)")
     ap.add_argument("--points", type=int, default=1000000)
     ap.add_argument("--bits", type=int, default=11)
     ap.add_argument("--kind", default="surf", choices=["surf", "unif"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--value-api", default="roundtrip", choices=["roundtrip", "separate"],
+    ap.add_argument("--value-api", default="separate", choices=["roundtrip", "separate"],
                     help="device-resident step through ccv2_roundtrip_batch (default) or ccv2_encode_batch + ccv2_decode_batch")
     ap.add_argument("--e2e-api", default="roundtrip", choices=["roundtrip", "separate"],
                     help="e2e through ccv2_roundtrip_batch (default) or ccv2_encode_batch + ccv2_decode_batch")
@@ -175,7 +177,11 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    F, NP = args.frames, args.points
+    NP = args.points
+    F = args.frames
+    if F <= 0:                                   # device-resident step: clouds in and out, streams (user side, 68 B/point) + the library's workspace (~82 B/point)
+        free_b, _total_b = torch.cuda.mem_get_info(local)
+        F = int(max(8, min(1024, (0.9 * free_b) // (150 * NP)))) // 8 * 8
     codec = K.Codec(K.default_params(octree_bits=args.bits), device=local)
     lib = K.load_library()
     cap = 4 * NP + (1 << 16)
@@ -238,6 +244,7 @@ def main():
         _, _, lens, ns = step_device()
     sampler = ClockSampler(local)
     barrier()
+    split["enc"] = split["dec"] = 0.0
     sampler.start()
     t0 = time.perf_counter()
     dev_ms, launches = 0.0, 0
@@ -252,11 +259,14 @@ def main():
     t_wall = reduce_max(wall, dist if world > 1 else None, dev)
     value = world * F * NP * args.steps / t_dev / 1e6
 
-    # ---- encode / decode split (informational): two untimed steps through the separate calls
-    split["enc"] = split["dec"] = 0.0
-    for _ in range(2):
-        step_separate()
-    split_steps = 2
+    # ---- encode / decode split: from the timed steps, or from two untimed steps when the timed call was the round trip
+    split_steps = args.steps
+    if args.value_api != "separate":
+        split["enc"] = split["dec"] = 0.0
+        for _ in range(2):
+            step_separate()
+        split_steps = 2
+    split_final = dict(split)                    # frozen: the extra step below is not part of it
     codec.frame_id = 0
     _, _, lens, ns = step_device()               # streams with frame ids 1..F again, for the oracle check below
 
@@ -277,6 +287,8 @@ def main():
     if F_e2e:
         # one pinned allocation per role, sliced per frame (many separate cudaMallocHost blocks copy ~30 % slower D2H here)
         FE = F_e2e
+        del d_in, d_str, d_out, in_ptrs, str_ptrs, out_ptrs      # the library stages host buffers in its own device pools: make room
+        torch.cuda.empty_cache()
         h_str, h_out = K.PinnedBuffer(FE * cap), K.PinnedBuffer(FE * NP * 32)
         hi = [h_in.ptr + i * NP * 32 for i in range(FE)]; hs = [h_str.ptr + i * cap for i in range(FE)]; ho = [h_out.ptr + i * NP * 32 for i in range(FE)]
 
@@ -321,8 +333,8 @@ def main():
                 "config": workload_config(args, F), "bit_exact_vs_oracle": bit_exact, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "value_api": "ccv2_roundtrip_batch" if args.value_api == "roundtrip" else "ccv2_encode_batch + ccv2_decode_batch",
-                "encode_ms_per_step": split["enc"] / split_steps, "decode_ms_per_step": split["dec"] / split_steps,
-                "encode_only_mpoints_s": F * NP * split_steps / max(split["enc"], 1e-9) / 1e3, "decode_only_mpoints_s": F * NP * split_steps / max(split["dec"], 1e-9) / 1e3,
+                "encode_ms_per_step": split_final["enc"] / split_steps, "decode_ms_per_step": split_final["dec"] / split_steps,
+                "encode_only_mpoints_s": F * NP * split_steps / max(split_final["enc"], 1e-9) / 1e3, "decode_only_mpoints_s": F * NP * split_steps / max(split_final["dec"], 1e-9) / 1e3,
                 "stream_bytes_per_frame": S, "voxels_per_frame": V}
         print(json.dumps(line))
     if world > 1:

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libccv2.so")
+LIB_PATH = os.environ.get("CCV2_LIBRARY") or os.path.join(_HERE, "libccv2.so")   # CCV2_LIBRARY: developer override (A/B builds of the same ABI)
 
 MANUAL_CONFIGURATION = 13  # pcl::io::compression_Profiles_e (12 profiles, COMPRESSION_PROFILE_COUNT, MANUAL_CONFIGURATION)
 

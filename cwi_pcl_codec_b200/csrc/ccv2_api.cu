@@ -39,7 +39,7 @@ struct DevBuf {
     if (bytes <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    size_t want = bytes + bytes / 8 + 4096;
+    size_t want = bytes + std::min(bytes / 8, (size_t)64 << 20) + 4096;   // slack so slowly growing batches do not reallocate every call
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
@@ -110,11 +110,13 @@ struct ccv2_codec {
   size_t smem_sm = 0, smem_static_enc = 0, smem_static_dec = 0;   // shared memory per SM; static use of the two serial kernels
   uint32_t frame_id = 0;
   // encode workspaces
-  DevBuf enc_frames, enc_slots, enc_persist, enc_input;
+  DevBuf work;                             // encode slots / decode workspaces (one arena: see run_batch)
+  int work_mode = -1;                      // mode of the call that last wrote the arena
+  DevBuf enc_frames, enc_persist, enc_input;
   HostBuf h_frames;
   std::vector<EncFrame> enc_host;        // host mirror of the last batch's frame records (with device pointers)
   // decode workspaces
-  DevBuf dec_frames, dec_work, dec_input, dec_output;
+  DevBuf dec_frames, dec_input, dec_output;
   HostBuf h_dframes, h_results;
   uint64_t metrics[3] = {0, 0, 0};
   uint64_t launches = 0;
@@ -411,8 +413,8 @@ void ccv2_destroy(ccv2_codec *c) {
   for (auto ev : c->ev_h2d) cudaEventDestroy(ev);
   if (c->d_tables) cudaFree(c->d_tables);
   if (c->d_frame_counter) cudaFree(c->d_frame_counter);
-  c->enc_frames.release(); c->enc_slots.release(); c->enc_persist.release(); c->enc_input.release();
-  c->dec_frames.release(); c->dec_work.release(); c->dec_input.release(); c->dec_output.release();
+  c->work.release(); c->enc_frames.release(); c->enc_persist.release(); c->enc_input.release();
+  c->dec_frames.release(); c->dec_input.release(); c->dec_output.release();
   c->h_frames.release(); c->h_dframes.release(); c->h_results.release();
   delete c;
 }
@@ -496,11 +498,12 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
   const bool do_enc = mode != 1, do_dec = mode != 0, rt = mode == 2;
   c->err.clear(); c->launches = 0; c->device_ms = 0;
   if (nframes == 0) return CCV2_OK;
+  c->work_mode = mode;
   CU(cudaSetDevice(c->device));
   const ccv2_params &prm = c->prm;
   const bool cen = prm.do_voxel_grid_centroid != 0, color = prm.do_color_encoding != 0;
   const int NS = c->profiling ? 1 : c->n_streams;
-  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(64, (nframes + NS - 1) / NS)));
+  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(256, (nframes + NS - 1) / NS)));
   const int ngroups = (nframes + G - 1) / G;
   while ((int)c->ev_h2d.size() < ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_h2d.push_back(ev); }
   while ((int)c->ev_group.size() < 2 * ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_group.push_back(ev); }
@@ -526,8 +529,14 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
     for (int i = 0; i < nframes; i++) { if (npts[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; } if (npts[i] && !pts[i]) return CCV2_ERR_ARG; nmax = std::max(nmax, npts[i]); }
     // Slots: one per (stream, frame-in-group); persist + input staging: one per frame of the batch
     slot_bytes = carve_enc_slot(nullptr, nmax, nullptr, prm, &zoff, &zbytes);
+    if (rt) {                                                        // round trip: a frame's decode workspace reuses its encode slot (dead once the stream is assembled)
+      size_t pmax = 0, zo, zz;
+      for (int i = 0; i < nframes; i++) pmax = std::max(pmax, pts_cap[i]);
+      if (pmax >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; }
+      slot_bytes = std::max(slot_bytes, carve_dec(nullptr, pmax, nullptr, &zo, &zz, prm.color_coding_type == 2));
+    }
     const int nslots = std::min(ngroups, NS) * G;
-    CU(c->enc_slots.ensure(slot_bytes * nslots));
+    CU(c->work.ensure(slot_bytes * nslots));
     std::vector<size_t> persist_off(nframes + 1, 0);
     for (int i = 0; i < nframes; i++) {
       persist_off[i + 1] = persist_off[i] + carve_enc_persist(nullptr, npts[i], nullptr, cen);
@@ -549,8 +558,8 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       f.n = (uint32_t)npts[i];
       f.n_finite = (uint32_t)npts[i];                               // keygen subtracts the non-finite points
       f.violator = NONE_U32;
-      carve_enc_slot((uint8_t *)c->enc_slots.p + slot_bytes * slot, nmax, &f, prm, nullptr, nullptr);
-      f.zero_ptr = (uint8_t *)c->enc_slots.p + slot_bytes * slot + zoff; f.zero_bytes = zbytes;
+      carve_enc_slot((uint8_t *)c->work.p + slot_bytes * slot, nmax, &f, prm, nullptr, nullptr);
+      f.zero_ptr = (uint8_t *)c->work.p + slot_bytes * slot + zoff; f.zero_bytes = zbytes;
       carve_enc_persist((uint8_t *)c->enc_persist.p + persist_off[i], npts[i], &f, cen);
       f.hist = (uint32_t *)((uint8_t *)c->enc_frames.p + frames_bytes) + (size_t)i * 3 * 256;
       if (color && (prm.color_coding_type == 0 || prm.color_coding_type == 3)) f.avg = f.cpay;   // raw averages are the colour payload
@@ -581,7 +590,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       dinput_off[i + 1] = dinput_off[i] + (din_dev[i] ? 0 : ((in_len[i] + 64 + 255) & ~size_t(255)));
       output_off[i + 1] = output_off[i] + (dout_dev[i] ? 0 : ((32 * pts_cap[i] + 255) & ~size_t(255)));
     }
-    CU(c->dec_work.ensure(work_off[nframes]));
+    if (!rt) CU(c->work.ensure(work_off[nframes]));                  // one arena serves encode slots and decode workspaces: a call uses one or the other (or aliases them, round trip)
     CU(c->dec_input.ensure(dinput_off[nframes] + 256));
     CU(c->dec_output.ensure(output_off[nframes] + 256));
     CU(c->dec_frames.ensure(sizeof(DecFrame) * nframes));
@@ -598,8 +607,9 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       }
       f.out_pts = dout_dev[i] ? (uint8_t *)pts_out[i] : (uint8_t *)c->dec_output.p + output_off[i];
       f.out_cap = pts_cap[i];
-      carve_dec((uint8_t *)c->dec_work.p + work_off[i], pts_cap[i], &f, nullptr, nullptr, prm.color_coding_type == 2);
-      f.zero_ptr = (uint8_t *)c->dec_work.p + work_off[i]; f.zero_bytes = zb[i];
+      uint8_t *wbase = rt ? (uint8_t *)c->work.p + slot_bytes * (((i / G) % NS) * G + (i % G)) : (uint8_t *)c->work.p + work_off[i];
+      carve_dec(wbase, pts_cap[i], &f, nullptr, nullptr, prm.color_coding_type == 2);
+      f.zero_ptr = wbase; f.zero_bytes = zb[i];
     }
   }
 
@@ -831,6 +841,7 @@ int ccv2_debug_fetch(ccv2_codec *c, int frame, int what, void *host_buf, size_t 
   CU(cudaSetDevice(c->device));
   const EncFrame &f = c->enc_host[frame];
   const void *src = nullptr; size_t n = 0;
+  if ((what == 0 || what == 2 || what == 4) && c->work_mode != 0) { c->err = "encode intermediates are only available right after ccv2_encode_batch"; return CCV2_ERR_UNSUPPORTED; }
   ccv2_frame_info info;
   switch (what) {
     case 0: src = f.leaf_key; n = (size_t)f.V * 8; break;

@@ -265,7 +265,7 @@ __device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *
   auto read_byte = [&](uint32_t &dst) -> bool {             // byte at stream offset pos; false when the producer died
     const uint32_t wi = pos >> 2;
     if (wi != cw) {
-      while (wi >= avail) { avail = rg->prod; if (rg->dead) return false; }
+      while (wi >= avail) { avail = rg->prod; if (rg->dead) return false; if (wi >= avail) __nanosleep(256); }   // the decoder publishes every 64 symbols (~8 us): sleep rather than take issue slots from the decoders on this SM
       win = rg->ring[wi & (RING_WORDS - 1)]; cw = wi;
       if ((wi >> 4) != pub) { pub = wi >> 4; rg->cons = wi; }
     }
