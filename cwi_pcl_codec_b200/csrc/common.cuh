@@ -209,10 +209,8 @@ __device__ __forceinline__ uint64_t scan_lookback(uint64_t *status, uint32_t til
   return excl;
 }
 
-// The serial one-warp-per-stream kernels are launched with one block per SM (gridDim.x = SM count); the block that
-// serves frame f of a group is (first_slot + f) mod gridDim.x, where first_slot is the group's first frame index in
-// the batch.  The first wave of a classic launch maps block ids to SMs deterministically, so frames of different
-// groups running concurrently on different streams land on different SMs instead of piling onto the same few.
+// dec_serial_kernel (the fallback path) still maps frames to blocks by index: the block that serves frame f of a group
+// is (first_slot + f) mod gridDim.x, so the few frames that need it do not all start on the same SMs.
 __device__ __forceinline__ int steered_frame(uint32_t first_slot, uint32_t group_frames) {
   const uint32_t g = gridDim.x;
   const uint32_t f = (blockIdx.x + g - first_slot % g) % g;
