@@ -106,6 +106,8 @@ struct ccv2_codec {
   std::vector<cudaEvent_t> ev_group;
   JpegTables *d_tables = nullptr;
   uint32_t *d_frame_counter = nullptr;
+  size_t lps_smem_enc = 0;                // dynamic shared memory that keeps the lane-per-stream coder CTAs one to an SM
+  int lps_enc = 1;                        // lane-per-stream range encoder (CCV2_LPS_ENC=0: one warp per stream)
   int serial_cap = 0;                     // serial CTAs per SM; 0: ceil(frames in the call / SMs)  (CCV2_CAP overrides, -1 disables the cap)
   size_t smem_sm = 0, smem_static_enc = 0, smem_static_dec = 0;   // shared memory per SM; static use of the two serial kernels
   uint32_t frame_id = 0;
@@ -352,6 +354,7 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   c->prm = *p; c->device = device;
   if (const char *s = getenv("CCV2_TRACE")) c->trace = atoi(s);
   if (const char *s = getenv("CCV2_CAP")) c->serial_cap = atoi(s);
+  if (const char *s = getenv("CCV2_LPS_ENC")) c->lps_enc = atoi(s) != 0;
   if (const char *s = getenv("CCV2_NO_RING")) c->use_ring = atoi(s) ? 0 : 1;
   if (const char *s = getenv("CCV2_STREAMS")) c->n_streams = std::max(1, std::min(MAX_STREAMS, atoi(s)));
   if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(1024, atoi(s)));
@@ -390,6 +393,10 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
     if ((e = cudaFuncGetAttributes(&fa, dec_entropy_kernel)) != cudaSuccess) return fail(e, "cudaFuncGetAttributes");
     c->smem_static_dec = fa.sharedSizeBytes;
     if ((e = cudaFuncSetAttribute(dec_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, per_block - (int)fa.sharedSizeBytes)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if ((e = cudaFuncGetAttributes(&fa, rc_encode_lps_kernel)) != cudaSuccess) return fail(e, "cudaFuncGetAttributes");
+    c->lps_smem_enc = ((size_t)per_sm / 1024 / 2 + 1) * 1024 - fa.sharedSizeBytes - 1024;      // more than half an SM's shared memory per CTA
+    if ((e = cudaFuncSetAttribute(rc_encode_lps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lps_smem_enc)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    cudaFuncSetAttribute(rc_encode_lps_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(rc_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(dec_entropy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
@@ -686,7 +693,8 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       const size_t hmax = std::max(tree_cap_for(gn), cpay_cap_for(gn));
       mark(g, "leaves", st);
       LAUNCH("hist_kernel", hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), 3, gf), 256, 0, st>>>(dg));
-      LAUNCH("rc_encode_kernel", rc_encode_kernel<<<gf, 96, serial_smem_enc, st>>>(dg, cen, color));
+      if (c->lps_enc) LAUNCH("rc_encode_lps_kernel", rc_encode_lps_kernel<<<dim3((unsigned)((gf + 31) / 32), 3), 32, c->lps_smem_enc, st>>>(dg, gf, cen, color));
+      else LAUNCH("rc_encode_kernel", rc_encode_kernel<<<gf, 96, serial_smem_enc, st>>>(dg, cen, color));
       LAUNCH("assemble_kernel", assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H));
       mark(g, "encoded", st);
     }
@@ -798,7 +806,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       std::vector<int> per_sm(256, 0);
       for (int i = 0; i < nframes; i++) per_sm[(dir == 0 ? hf[i].serial_sm : hd[i].serial_sm) & 255]++;
       std::vector<int> hist(64, 0); int mx = 0;
-      for (int s2 = 0; s2 < c->n_sm; s2++) { hist[std::min(63, per_sm[s2])]++; mx = std::max(mx, per_sm[s2]); }
+      for (int s2 = 0; s2 < c->n_sm; s2++) { hist[std::min(63, per_sm[s2])]++; mx = std::max(mx, std::min(63, per_sm[s2])); }
       fprintf(stderr, "  %s serial CTAs per SM (cap %d):", dir == 0 ? "encode" : "decode", serial_cap);
       for (int k = 0; k <= mx; k++) fprintf(stderr, " %dx%d", hist[k], k);
       fprintf(stderr, "\n");

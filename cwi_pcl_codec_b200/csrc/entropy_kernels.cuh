@@ -165,6 +165,120 @@ __global__ void __launch_bounds__(96) rc_encode_kernel(EncFrame *frames, int do_
   }
 }
 
+// ---- range encoder, lane per stream ---------------------------------------------------------------------------------
+// The coder's state machine is scalar, so in rc_encode_kernel 31 of a warp's 32 lanes repeat lane 0's arithmetic and a
+// frame costs a whole warp's issue slots; with hundreds of frames in flight the SMs run out of them (7 coder CTAs per
+// SM at 1024 frames).  Here every LANE is a coder of its own: a warp encodes the same layer of 32 frames in lock step
+// (same instruction stream, 32 different (low, range) states, tables interleaved in shared memory so that lane l only
+// ever touches bank l), so 1024 frames need 32 warps per layer and each of them runs at the latency of a lone warp.
+// The arithmetic per symbol is the one above (closed-form renormalisation, branch-free word flush); only the rare
+// underflow loop diverges.  grid (ceil(frames / 32), 3 layers), one warp per CTA.
+#define LPS_SYMS 16
+__global__ void __launch_bounds__(32) rc_encode_lps_kernel(EncFrame *frames, int nframes, int do_centroid, int do_color) {
+  const int which = blockIdx.y;
+  if ((which == 1 && !do_centroid) || (which == 2 && !do_color)) return;
+  __shared__ uint32_t tab[257 * 32];                       // [symbol][lane]: cumulative table, then (cum << 16 | width)
+  const uint32_t lane = lane_id();
+  const int fi = blockIdx.x * 32 + lane;
+  const bool have = fi < nframes && frames[fi].V != 0;
+  EncFrame &f = frames[have ? fi : blockIdx.x * 32];
+  const uint8_t *src = nullptr; uint32_t n = 0;
+  uint8_t *dst = nullptr; uint64_t cap = 0;
+  if (have) {
+    enc_layer(f, which, src, n);
+    if (which == 0) { dst = f.stream + FRAME_HDR_BYTES + 8; cap = f.stream_cap > FRAME_HDR_BYTES + 8 ? f.stream_cap - FRAME_HDR_BYTES - 8 : 0; }
+    else { dst = f.rc_tmp[which - 1]; cap = f.rc_tmp_cap[which - 1]; }
+    if (which == 0) f.serial_sm = sm_id();
+  }
+  bool overflow = false;
+  if (have && cap < 1028 + 8) { overflow = true; n = 0; }
+  // cumulative table with PCL's "+1 if empty" rule and the halving rescale (rc_build_table), one column per lane
+  uint32_t *col = tab + lane;
+  {
+    const uint32_t *hist = f.hist + which * 256;
+    uint32_t prev = 0; col[0] = 0;
+    for (int s2 = 1; s2 <= 256; s2++) { uint32_t v = prev + (have ? hist[s2 - 1] : 1u); if (v <= prev) v = prev + 1; col[s2 * 32] = v; prev = v; }
+    while (col[256 * 32] >= RC_BOTTOM) {
+      prev = 0;
+      for (int s2 = 1; s2 <= 256; s2++) { uint32_t v = col[s2 * 32] >> 1; if (v <= prev) v = prev + 1; col[s2 * 32] = v; prev = v; }
+    }
+  }
+  const FastDiv fd = fastdiv_make(col[256 * 32]);
+  if (have && !overflow) for (int s2 = 0; s2 <= 256; s2++) ((uint32_t *)dst)[s2] = col[s2 * 32];     // dst is 4-byte aligned
+  { uint32_t c0 = col[0]; for (int s2 = 0; s2 < 256; s2++) { const uint32_t c1 = col[(s2 + 1) * 32]; col[s2 * 32] = (c0 << 16) | (c1 - c0); c0 = c1; } }
+  __syncwarp();
+  uint32_t *out32 = (uint32_t *)(dst + 1028);
+  const uint32_t cap_words = (have && !overflow) ? (uint32_t)min((uint64_t)0x7FFFFFFFu, (cap - 1028) / 4) : 0;
+  uint32_t low = 0, range = 0xFFFFFFFFu;
+  uint64_t acc = 0; uint32_t nacc = 0, wp = 0;
+#define LPS_FLUSH() do { const bool fl_ = nacc >= 4; const uint32_t nn_ = fl_ ? nacc - 4 : nacc; \
+    if (fl_) out32[wp] = __byte_perm((uint32_t)(acc >> (8 * nn_)), 0, 0x0123); wp += fl_ ? 1u : 0u; nacc = nn_; } while (0)
+#define LPS_MAP(P) const uint32_t p_ = (P); const uint32_t r_ = fastdiv(range, fd); \
+    low += (p_ >> 16) * r_; range = r_ * (p_ & 0xFFFFu); \
+    const uint32_t sh_ = rc_equal_bits(low ^ (low + range)); \
+    acc = (acc << sh_) | __funnelshift_l(low, 0, sh_); nacc += sh_ >> 3; low <<= sh_; range <<= sh_;
+#define LPS_UNDERFLOW() do { \
+      LPS_FLUSH(); \
+      range = (0u - low) & (RC_BOTTOM - 1); acc = (acc << 8) | (low >> 24); nacc++; low <<= 8; range <<= 8; \
+      const uint32_t s2_ = rc_equal_bits(low ^ (low + range)); \
+      acc = (acc << s2_) | __funnelshift_l(low, 0, s2_); nacc += s2_ >> 3; low <<= s2_; range <<= s2_; } while (range < RC_BOTTOM)
+#define LPS_SYMBOL(P) do { LPS_MAP(P) if (__builtin_expect(range < RC_BOTTOM, 0)) LPS_UNDERFLOW(); LPS_FLUSH(); } while (0)
+  // fast path: 16 symbols of straight-line code, their table entries fetched up front; the only branches on it are
+  // never-taken forward jumps to the underflow handler placed after the loop body (a lane that takes one finishes
+  // the batch on its own and meets the others at the loop end).
+#define LPS_FAST(P, K) do { LPS_MAP(P) if (__builtin_expect(range < RC_BOTTOM, 0)) { kk = (K); goto slow_path; } LPS_FLUSH(); } while (0)
+  const uint32_t nfull = n & ~(uint32_t)(LPS_SYMS - 1);
+  uint32_t nmax = nfull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL_MASK, nmax, o));
+  uint4 nxt = make_uint4(0, 0, 0, 0);
+  if (nfull) nxt = *(const uint4 *)src;                                // layers start 16-byte aligned
+  for (uint32_t base = 0; base < nmax; base += LPS_SYMS) {
+    if (base >= nfull) continue;                                       // lanes whose vector is shorter idle (layers of one kind have similar lengths)
+    if (wp + LPS_SYMS + 8 > cap_words) { overflow = true; break; }     // a symbol emits at most 4 bytes
+    uint32_t pk[LPS_SYMS];
+    {
+      const uint4 cur = nxt;
+      if (base + LPS_SYMS < nfull) nxt = *(const uint4 *)(src + base + LPS_SYMS);   // next batch in flight while this one is coded
+      const uint32_t wv[4] = { cur.x, cur.y, cur.z, cur.w };
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        pk[4 * k] = col[(wv[k] & 255u) * 32]; pk[4 * k + 1] = col[((wv[k] >> 8) & 255u) * 32];
+        pk[4 * k + 2] = col[((wv[k] >> 16) & 255u) * 32]; pk[4 * k + 3] = col[(wv[k] >> 24) * 32];
+      }
+    }
+    uint32_t kk;
+    LPS_FAST(pk[0], 0); LPS_FAST(pk[1], 1); LPS_FAST(pk[2], 2); LPS_FAST(pk[3], 3);
+    LPS_FAST(pk[4], 4); LPS_FAST(pk[5], 5); LPS_FAST(pk[6], 6); LPS_FAST(pk[7], 7);
+    LPS_FAST(pk[8], 8); LPS_FAST(pk[9], 9); LPS_FAST(pk[10], 10); LPS_FAST(pk[11], 11);
+    LPS_FAST(pk[12], 12); LPS_FAST(pk[13], 13); LPS_FAST(pk[14], 14); LPS_FAST(pk[15], 15);
+    continue;
+  slow_path:                                                           // rare: finish symbol kk's underflow, then the rest of the batch
+    LPS_UNDERFLOW();
+    LPS_FLUSH();
+    for (uint32_t k = kk + 1; k < LPS_SYMS; k++) LPS_SYMBOL(col[(uint32_t)src[base + k] * 32]);
+  }
+#undef LPS_FAST
+  if (!overflow && nfull < n) {
+    if (wp + LPS_SYMS + 8 > cap_words) overflow = true;
+    else for (uint32_t i = nfull; i < n; i++) LPS_SYMBOL(col[(uint32_t)src[i] * 32]);
+  }
+  if (!have) return;
+  uint64_t cnt = 0;
+  if (!overflow) {
+    for (int k = 0; k < 4; k++) { acc = (acc << 8) | (low >> 24); nacc++; low <<= 8; LPS_FLUSH(); }   // flush
+    uint8_t *tail = (uint8_t *)(out32 + wp);
+    for (uint32_t k = 0; k < nacc; k++) tail[k] = (uint8_t)(acc >> (8 * (nacc - 1 - k)));
+    cnt = 4ull * wp + nacc;
+  }
+#undef LPS_SYMBOL
+#undef LPS_UNDERFLOW
+#undef LPS_MAP
+#undef LPS_FLUSH
+  if (overflow) atomicOr(&f.error, FERR_STREAM_CAP);
+  f.rc_len[which] = (uint32_t)(1028 + cnt);
+}
+
 // ---- frame assembly: header + size words + layers: grid (blocks, frames)
 struct HeaderParams { double octree_res, point_res; uint8_t do_voxel_grid, with_color, color_bits, do_centroid, connectivity, scalable, icp_offset, _p; uint32_t color_type; int32_t macroblock; };
 
