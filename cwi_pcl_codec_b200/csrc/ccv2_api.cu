@@ -11,6 +11,7 @@
 #include "jpeg_enc_kernels.cuh"
 #include "entropy_kernels.cuh"
 #include "dec_kernels.cuh"
+#include "dec_lps_kernels.cuh"
 #include "lines_kernels.cuh"
 #include "lines_dec_kernels.cuh"
 
@@ -102,6 +103,9 @@ struct ccv2_codec {
   cudaStream_t copy_stream = nullptr;     // all host->device input copies, in group order (see run_batch)
   std::vector<cudaEvent_t> ev_h2d;
   cudaStream_t streams[MAX_STREAMS] = {};
+  cudaStream_t side_streams[MAX_STREAMS] = {};   // colour layer of a group, concurrent with its tree layer (lane-per-stream decoder)
+  std::vector<cudaEvent_t> ev_side;
+  int lps_dec = -1;                       // lane-per-stream range decoder: -1 auto (round trips only), 0 off, 1 on (CCV2_LPS_DEC)
   cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_fork = nullptr;
   std::vector<cudaEvent_t> ev_group;
   JpegTables *d_tables = nullptr;
@@ -159,7 +163,8 @@ void prof_collect(ccv2_codec *c) {
   }
   c->prof_recs.clear(); c->prof_used = 0;
 }
-#define LAUNCH(name, ...) do { prof_begin(c, st, name); __VA_ARGS__; prof_end(c, st); launches++; } while (0)
+#define LAUNCH_S(stream, name, ...) do { prof_begin(c, stream, name); __VA_ARGS__; prof_end(c, stream); launches++; } while (0)
+#define LAUNCH(name, ...) LAUNCH_S(st, name, __VA_ARGS__)
 
 bool is_device_ptr(const void *p) {
   cudaPointerAttributes a;
@@ -355,6 +360,7 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   if (const char *s = getenv("CCV2_TRACE")) c->trace = atoi(s);
   if (const char *s = getenv("CCV2_CAP")) c->serial_cap = atoi(s);
   if (const char *s = getenv("CCV2_LPS_ENC")) c->lps_enc = atoi(s) != 0;
+  if (const char *s = getenv("CCV2_LPS_DEC")) c->lps_dec = atoi(s);
   if (const char *s = getenv("CCV2_NO_RING")) c->use_ring = atoi(s) ? 0 : 1;
   if (const char *s = getenv("CCV2_STREAMS")) c->n_streams = std::max(1, std::min(MAX_STREAMS, atoi(s)));
   if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(1024, atoi(s)));
@@ -371,6 +377,7 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
     for (int i = 0; i < c->n_streams; i++) {
       int p = prio ? std::min(lo, hi + i * (lo - hi + 1) / std::max(1, c->n_streams)) : lo;
       if ((e = cudaStreamCreateWithPriority(&c->streams[i], cudaStreamNonBlocking, p)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+      if ((e = cudaStreamCreateWithPriority(&c->side_streams[i], cudaStreamNonBlocking, lo)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     }
   }
   if ((e = cudaEventCreate(&c->ev_start)) != cudaSuccess) return fail(e, "cudaEventCreate");
@@ -397,6 +404,10 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
     c->lps_smem_enc = ((size_t)per_sm / 1024 / 2 + 1) * 1024 - fa.sharedSizeBytes - 1024;      // more than half an SM's shared memory per CTA
     if ((e = cudaFuncSetAttribute(rc_encode_lps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lps_smem_enc)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     cudaFuncSetAttribute(rc_encode_lps_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if ((e = cudaFuncSetAttribute(rc_decode_lps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpsSmem))) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if ((e = cudaFuncSetAttribute(rc_decode_lps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)offsetof(LpsSmem, rg))) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    cudaFuncSetAttribute(rc_decode_lps_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(rc_decode_lps_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(rc_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(dec_entropy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
@@ -415,6 +426,8 @@ void ccv2_destroy(ccv2_codec *c) {
   if (c->ev_end) cudaEventDestroy(c->ev_end);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (int i = 0; i < MAX_STREAMS; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+  for (int i = 0; i < MAX_STREAMS; i++) if (c->side_streams[i]) cudaStreamDestroy(c->side_streams[i]);
+  for (auto ev : c->ev_side) cudaEventDestroy(ev);
   if (c->main_stream) cudaStreamDestroy(c->main_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (auto ev : c->ev_h2d) cudaEventDestroy(ev);
@@ -513,6 +526,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
   const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(256, (nframes + NS - 1) / NS)));
   const int ngroups = (nframes + G - 1) / G;
   while ((int)c->ev_h2d.size() < ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_h2d.push_back(ev); }
+  while ((int)c->ev_side.size() < 2 * ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_side.push_back(ev); }
   while ((int)c->ev_group.size() < 2 * ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_group.push_back(ev); }
   cudaStream_t ms = c->main_stream;
   CU(c->h_results.ensure(sizeof(FrameResult) * nframes));
@@ -714,6 +728,24 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       LAUNCH("zero_region_kernel", zero_region_kernel<DecFrame><<<dim3(64, gf), 256, 0, st>>>(dg));
       if (any_h2d) { CU(cudaEventRecord(c->ev_h2d[g], c->copy_stream)); CU(cudaStreamWaitEvent(st, c->ev_h2d[g], 0)); }
       if (rt) LAUNCH("link_kernel", link_kernel<<<(gf + 63) / 64, 64, 0, st>>>(df + f0, dg, gf));
+      // Two entropy stages.  dec_entropy_kernel (a CTA per frame) is the faster one when nothing else runs (decode-only
+      // calls: 374 ms against 414 ms for 1024 frames); in a round trip its 7 CTAs per SM compete with the other groups'
+      // encode kernels and the lane-per-stream decoder, 8 frames to a warp on an SM of its own, wins (677 ms against 753 ms).
+      if (c->lps_dec < 0 ? rt : c->lps_dec != 0) {
+        // tree layers on the group's stream, speculated colour layers on a side stream at the same time
+        cudaStream_t s2 = c->profiling ? st : c->side_streams[g % NS];
+        const unsigned lps_ctas = (unsigned)((gf + LPS_DEC_FRAMES - 1) / LPS_DEC_FRAMES);
+        LAUNCH("dec_head_kernel", dec_head_kernel<<<gf, 32, 0, st>>>(dg));
+        if (s2 != st) { CU(cudaEventRecord(c->ev_side[2 * g], st)); CU(cudaStreamWaitEvent(s2, c->ev_side[2 * g], 0)); }
+        LAUNCH("rc_decode_lps_kernel<tree>", rc_decode_lps_kernel<true><<<lps_ctas, 32 * (1 + LPS_DEC_FRAMES), sizeof(LpsSmem), st>>>(dg, gf, c->use_ring));
+        LAUNCH_S(s2, "rc_decode_lps_kernel<colour>", rc_decode_lps_kernel<false><<<lps_ctas, 32, offsetof(LpsSmem, rg), s2>>>(dg, gf, 0));
+        mark(g, "tree", st);
+        mark(g, "colour-rc", s2);
+        LAUNCH_S(s2, "dec_jpeg_kernel", dec_jpeg_kernel<<<gf, 32, 0, s2>>>(dg));
+        mark(g, "jpeg", s2);
+        if (s2 != st) { CU(cudaEventRecord(c->ev_side[2 * g + 1], s2)); CU(cudaStreamWaitEvent(st, c->ev_side[2 * g + 1], 0)); }
+        LAUNCH("dec_finish_kernel", dec_finish_kernel<<<gf, 32, 0, st>>>(dg));
+      } else
       LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<gf, 96, serial_smem_dec, st>>>(dg, c->use_ring));
       mark(g, "entropy", st);
       LAUNCH("dec_expand_kernel", dec_expand_kernel<<<dim3((unsigned)((pmax + 255) / 256), gf), 256, 0, st>>>(dg));

@@ -92,7 +92,10 @@ struct DecFrame {
   uint32_t data_with_color, do_centroid, color_bits;
   uint32_t B, ncen, ncol;
   uint32_t n_bottom, V;
-  uint32_t walk_done, huff_done;                 // DFS walk / JPEG Huffman decode already done inside dec_entropy_kernel
+  uint32_t walk_done, huff_done;                 // DFS walk / JPEG Huffman decode already done inside the entropy stage
+  // lane-per-stream entropy stage (dec_lps_kernels.cuh): header result, tree layer span, colour speculation
+  uint32_t head_ok, tree_n, tree_ok, spec_found, spec_state, spec_ncol, spec_jerr, _pad8;
+  uint64_t tree_pos, tree_end, spec_pos, spec_coded;
   uint32_t img_w, img_h, mcu_w, mcu_h, n_blocks;
   uint32_t ticket[TK_COUNT];
   uint32_t error, serial_sm;

@@ -321,9 +321,9 @@ __global__ void __launch_bounds__(256) assemble_kernel(EncFrame *frames, HeaderP
 // three cached aligned 64-bit words (A, B and the prefetched C) whenever whole bytes have been consumed.  The fast
 // path consumes at most one byte per symbol, so the window is rebuilt once per 8 symbols, off the per-symbol path.
 struct WindowFeed {
-  const uint64_t *w; uint32_t last, widx, sbyte, ubits, consumed; uint64_t A, B, C, W;
-  __device__ __forceinline__ uint64_t fetch(uint32_t i) const {
-    const uint64_t v = w[min(i, last)];
+  const uint64_t *w; uint32_t last, widx, sbyte, ubits, consumed; uint64_t A, B, Craw, W;
+  __device__ __forceinline__ uint64_t raw(uint32_t i) const { return w[min(i, last)]; }
+  __device__ __forceinline__ static uint64_t be(uint64_t v) {           // the stream is consumed most significant byte first
     return ((uint64_t)__byte_perm((uint32_t)v, 0, 0x0123) << 32) | __byte_perm((uint32_t)(v >> 32), 0, 0x0123);
   }
   __device__ __forceinline__ void rebuild() { W = sbyte ? (A << (8 * sbyte)) | (B >> (64 - 8 * sbyte)) : A; }
@@ -333,13 +333,14 @@ struct WindowFeed {
     w = (const uint64_t *)(a - sbyte);
     const uintptr_t end = ((uintptr_t)(base + len) + 7) & ~(uintptr_t)7;
     last = (uint32_t)((end - (a - sbyte)) / 8) - 1;        // reads past the end repeat the last word (PCL would read EOF garbage)
-    widx = 0; A = fetch(0); B = fetch(1); C = fetch(2); ubits = 0; consumed = 0;
+    widx = 0; A = be(raw(0)); B = be(raw(1)); Craw = raw(2); ubits = 0; consumed = 0;
     rebuild();
   }
-  // whole bytes consumed since the last rebuild are in ubits (multiple of 8, <= 64)
+  // whole bytes consumed since the last rebuild are in ubits (multiple of 8, <= 64).  The word loaded here is not
+  // touched (not even byte-swapped) until the NEXT shift, so its latency never lands on the decode chain.
   __device__ __forceinline__ void advance() {
     consumed += ubits >> 3; sbyte += ubits >> 3; ubits = 0;
-    while (sbyte >= 8) { sbyte -= 8; A = B; B = C; widx++; C = fetch(widx + 2); }
+    while (sbyte >= 8) { sbyte -= 8; A = B; B = be(Craw); widx++; Craw = raw(widx + 2); }
     rebuild();
   }
   __device__ __forceinline__ uint32_t take_byte() {        // generic path: any number of bytes
@@ -352,7 +353,7 @@ struct WindowFeed {
 
 // Shared-memory ring through which the range decoder (warp 0) hands the tree bytes to the DFS walker (warp 1) while it
 // is still decoding: the walk is serial too, and pipelining it behind the decoder takes it off the frame's latency.
-#define RING_WORDS 2048
+#define RING_WORDS 512
 struct WalkRing { volatile uint32_t ring[RING_WORDS]; volatile uint32_t prod, cons, done, dead; uint32_t B, depth, go; };
 
 // decodeStreamToCharVector, warp-uniform. Symbol search without a division: lane l owns the cumulative
