@@ -79,6 +79,7 @@ def load_library():
     L.ccv2_host_free.argtypes = [C.c_void_p]
     L.ccv2_host_free.restype = None
     L.ccv2_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, szp]
+    L.ccv2_get_output_cloud.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, szp]
     L.ccv2_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.ccv2_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int)]
     _lib = L
@@ -88,7 +89,7 @@ def load_library():
 EXPORTED_SYMBOLS = ["ccv2_default_params", "ccv2_create", "ccv2_destroy", "ccv2_max_compressed_size",
                     "ccv2_encode_batch", "ccv2_decode_batch", "ccv2_roundtrip_batch", "ccv2_peek_point_count", "ccv2_get_metrics",
                     "ccv2_set_frame_id", "ccv2_get_frame_id", "ccv2_last_launch_count", "ccv2_last_device_ms",
-                    "ccv2_last_error", "ccv2_status_string", "ccv2_host_alloc", "ccv2_host_free", "ccv2_debug_fetch",
+                    "ccv2_last_error", "ccv2_status_string", "ccv2_host_alloc", "ccv2_host_free", "ccv2_debug_fetch", "ccv2_get_output_cloud",
                     "ccv2_set_profiling", "ccv2_get_profile"]
 
 
@@ -298,6 +299,16 @@ class Codec:
             out.append((name.value.decode(), float(ms.value), int(n.value)))
             i += 1
 
+    def output_cloud(self, frame=0):
+        """[PCL] getOutputCloud() for frame `frame` of the last encode_batch: (V, 32) uint8 PointXYZRGB records."""
+        n = C.c_size_t()
+        rc = self._L.ccv2_get_output_cloud(self._h, frame, None, 0, C.byref(n))
+        if rc not in (0, -4):
+            self._check(rc)
+        out = np.zeros((max(1, n.value), 32), np.uint8)
+        self._check(self._L.ccv2_get_output_cloud(self._h, frame, out.ctypes.data, out.shape[0], C.byref(n)))
+        return out[:n.value]
+
     def debug_fetch(self, frame, what):
         """Test hook: 0 leaf codes (u64), 1 tree bytes, 2 avg colours, 3 colour payload, 4 sorted indices, 5 info."""
         ln = C.c_size_t()
@@ -362,6 +373,10 @@ class OctreePointCloudCodecV2:
 
     def getPerformanceMetrics(self):
         return self._codec.metrics()
+
+    def getOutputCloud(self):
+        """The simplified cloud of the last encodePointCloud call ([PCL] getOutputCloud, eval.hpp:862)."""
+        return self._codec.output_cloud(0)
 
 
 def profile_step(clouds, octree_bits=11, device=0):

@@ -118,6 +118,8 @@ struct ccv2_codec {
   // encode workspaces
   DevBuf work;                             // encode slots / decode workspaces (one arena: see run_batch)
   int work_mode = -1;                      // mode of the call that last wrote the arena
+  EncParams last_enc_params;               // of the last encode (ccv2_get_output_cloud)
+  DevBuf out_cloud;                        // staging for ccv2_get_output_cloud into host memory
   DevBuf enc_frames, enc_persist, enc_input;
   HostBuf h_frames;
   std::vector<EncFrame> enc_host;        // host mirror of the last batch's frame records (with device pointers)
@@ -433,7 +435,7 @@ void ccv2_destroy(ccv2_codec *c) {
   for (auto ev : c->ev_h2d) cudaEventDestroy(ev);
   if (c->d_tables) cudaFree(c->d_tables);
   if (c->d_frame_counter) cudaFree(c->d_frame_counter);
-  c->work.release(); c->enc_frames.release(); c->enc_persist.release(); c->enc_input.release();
+  c->work.release(); c->out_cloud.release(); c->enc_frames.release(); c->enc_persist.release(); c->enc_input.release();
   c->dec_frames.release(); c->dec_input.release(); c->dec_output.release();
   c->h_frames.release(); c->h_dframes.release(); c->h_results.release();
   delete c;
@@ -594,6 +596,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
     H.do_voxel_grid = 1; H.with_color = color; H.color_bits = prm.color_bit_resolution; H.do_centroid = cen;
     H.connectivity = prm.code_connectivity != 0; H.scalable = prm.create_scalable_stream != 0; H.icp_offset = prm.do_icp_color_offset != 0; H._p = 0;
     H.color_type = prm.color_coding_type; H.macroblock = prm.macroblock_size;
+    c->last_enc_params = P;
   }
 
   // ------------------------------------------------------------------ decode side set-up
@@ -874,6 +877,25 @@ int ccv2_roundtrip_batch(ccv2_codec *c, int nframes, const void *const *pts, con
   if (!c || nframes < 0 || (nframes && (!pts || !npts || !pts_out || !pts_cap || !npts_out))) return CCV2_ERR_ARG;
   if (out && (!out_cap || !out_len)) return CCV2_ERR_ARG;
   return run_batch(c, 2, nframes, pts, npts, out, out_cap, out_len, nullptr, nullptr, pts_out, pts_cap, npts_out);
+}
+
+int ccv2_get_output_cloud(ccv2_codec *c, int frame, void *points_out, size_t cap_points, size_t *npoints) {
+  if (!c || frame < 0 || frame >= (int)c->enc_host.size() || !npoints) return CCV2_ERR_ARG;
+  if (c->work_mode != 0) { c->err = "the output cloud is only available right after ccv2_encode_batch"; return CCV2_ERR_UNSUPPORTED; }
+  CU(cudaSetDevice(c->device));
+  const EncFrame &f = c->enc_host[frame];
+  if (f.error) { *npoints = 0; return CCV2_OK; }
+  *npoints = f.V;
+  if (f.V == 0) return CCV2_OK;
+  if (f.V > cap_points || !points_out) return CCV2_ERR_CAPACITY;
+  const bool dev = is_device_ptr(points_out);
+  uint8_t *dst = (uint8_t *)points_out;
+  if (!dev) { CU(c->out_cloud.ensure(32ull * f.V)); dst = (uint8_t *)c->out_cloud.p; }
+  output_cloud_kernel<<<(f.V + 255) / 256, 256, 0, c->main_stream>>>(f, c->last_enc_params, dst);
+  CU(cudaGetLastError());
+  if (!dev) CU(cudaMemcpyAsync(points_out, dst, 32ull * f.V, cudaMemcpyDeviceToHost, c->main_stream));
+  CU(cudaStreamSynchronize(c->main_stream));
+  return CCV2_OK;
 }
 
 int ccv2_debug_fetch(ccv2_codec *c, int frame, int what, void *host_buf, size_t cap, size_t *len) {

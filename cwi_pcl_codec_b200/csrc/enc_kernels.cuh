@@ -440,3 +440,37 @@ __global__ void __launch_bounds__(256) leaf_emit_kernel(EncFrame *frames, EncPar
     if (P.do_color && P.color_type != 1 && P.color_type != 2) f.ncolor = 3 * V;   // raw averages are the payload
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// The encoder's simplified cloud output_ (impl.hpp:1549-1576; [PCL] getOutputCloud, eval.hpp:862), produced on demand
+// from the leaf arrays of the last encode: one thread per leaf.  grid (ceil(V / 256))
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) output_cloud_kernel(EncFrame f, EncParams P, uint8_t *out) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= f.V) return;
+  const uint64_t key = f.leaf_key[j];
+  const uint32_t k3[3] = { compact3(key >> 2), compact3(key >> 1), compact3(key) };
+  float xyz[3];
+  if (P.do_centroid) {                                   // pcl::compute3DCentroid: float accumulation in index order (impl.hpp:1565-1571)
+    const uint32_t s0 = f.leaf_start[j], s1 = f.leaf_start[j + 1];
+    const uint32_t *vals = f.vals[f.npasses & 1];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (uint32_t k = s0; k < s1; k++) {
+      float4 q = __ldg((const float4 *)(f.pts + 32ull * vals[k]));
+      ax = __fadd_rn(ax, q.x); ay = __fadd_rn(ay, q.y); az = __fadd_rn(az, q.z);
+    }
+    const float cnt = (float)(s1 - s0);
+    xyz[0] = __fdiv_rn(ax, cnt); xyz[1] = __fdiv_rn(ay, cnt); xyz[2] = __fdiv_rn(az, cnt);
+  } else {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {                        // impl.hpp:1518-1520, 1559-1563
+      const double corner = __dadd_rn(__dmul_rn((double)k3[a], P.res), f.bmin[a]);
+      xyz[a] = (float)__dadd_rn(corner, __dmul_rn(0.5, P.res));
+    }
+  }
+  uint32_t rgba = 0xFF000000u;                           // PointXYZRGB(): r = g = b = 0, a = 255
+  if (P.do_color) { const uint8_t *c = f.avg + 3ull * j; rgba |= (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16); }
+  uint4 *o = (uint4 *)(out + 32ull * j);
+  o[0] = make_uint4(__float_as_uint(xyz[0]), __float_as_uint(xyz[1]), __float_as_uint(xyz[2]), 0x3F800000u);
+  o[1] = make_uint4(rgba, 0, 0, 0);
+}

@@ -83,6 +83,20 @@ public:
     ccv2_get_metrics(h_, metrics_);
   }
 
+  // [PCL] OctreePointCloudCompression::getOutputCloud (eval.hpp:862): the simplified cloud of the last encodePointCloud
+  // (impl.hpp:96, 1549-1576), fetched from the device on demand.
+  PointCloudPtr getOutputCloud() {
+    PointCloudPtr out(new PointCloud());
+    if (!h_) return out;
+    size_t n = 0;
+    int rc = ccv2_get_output_cloud(h_, 0, nullptr, 0, &n);
+    if ((rc != CCV2_OK && rc != CCV2_ERR_CAPACITY) || n == 0) return out;
+    out->points.resize(n);
+    if (ccv2_get_output_cloud(h_, 0, out->points.data(), n, &n) != CCV2_OK) { last_error_ = ccv2_last_error(h_); out->points.clear(); return out; }
+    out->width = static_cast<std::uint32_t>(n); out->height = 1;
+    return out;
+  }
+
   // codec.h:193-197
   uint64_t *getPerformanceMetrics() { return metrics_; }
   const std::string &lastError() const { return last_error_; }

@@ -120,6 +120,16 @@ int ccv2_get_profile(const ccv2_codec *c, int idx, const char **name, float *tot
 const char *ccv2_last_error(const ccv2_codec *c);
 const char *ccv2_status_string(int status);
 
+/* [PCL] OctreePointCloudCompression::getOutputCloud() as evaluate_compression uses it after encodePointCloud
+ * (eval.hpp:862): the encoder's simplified cloud output_ (impl.hpp:96, filled at impl.hpp:1549-1576) -- one 32-byte
+ * PointXYZRGB per occupied voxel in stream (DFS) order, at the voxel centre `corner + 0.5 * resolution` (or the float
+ * centroid of the voxel's points when doVoxelGridCentroid is set), carrying the voxel's average colour before JPEG.
+ * Valid for frame `frame` of the LAST ccv2_encode_batch call, until the next call on the handle (centroid mode
+ * re-reads the input cloud, which must still be alive if it was passed as a device pointer).  points_out: host or
+ * device memory for cap_points records; *npoints receives the voxel count (also when cap_points is too small:
+ * CCV2_ERR_CAPACITY). */
+int ccv2_get_output_cloud(ccv2_codec *c, int frame, void *points_out, size_t cap_points, size_t *npoints);
+
 /* Pinned host memory helpers (cudaMallocHost / cudaFreeHost) for callers that want full-speed PCIe copies. */
 void *ccv2_host_alloc(size_t bytes);
 void ccv2_host_free(void *p);

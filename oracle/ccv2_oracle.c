@@ -34,7 +34,7 @@ static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, 
 void orc_free(void *p) { free(p); }
 void orc_free_debug(orc_debug *d) {
   if (!d) return;
-  free(d->leaf_keys); free(d->tree_bytes); free(d->avg_colors); free(d->color_payload); free(d->centroid_bytes);
+  free(d->leaf_keys); free(d->tree_bytes); free(d->avg_colors); free(d->color_payload); free(d->centroid_bytes); free(d->output_cloud);
   memset(d, 0, sizeof *d);
 }
 void orc_default_params(orc_params *p) {
@@ -702,6 +702,7 @@ int orc_encode(const orc_params *p, uint32_t frame_id, const void *pts, size_t n
   if (reduction < 0) reduction = 0;
   bbuf tree = {0}, avg = {0}, cen = {0};
   uint64_t *leaf_keys = (uint64_t *)malloc(nf * 8); size_t V = 0;
+  uint8_t *outc = dbg ? (uint8_t *)calloc(nf ? nf : 1, 32) : NULL;   /* output_: one PointXYZRGB per leaf, DFS order (impl.hpp:1576) */
   uint32_t d = b.depth;
   /* pass 1: leaves, colours */
   for (size_t i = 0; i < nf;) {
@@ -714,6 +715,11 @@ int orc_encode(const orc_params *p, uint32_t frame_id, const void *pts, size_t n
       s0 >>= reduction; s1 >>= reduction; s2 >>= reduction;
       bb_push(&avg, (uint8_t)s0); bb_push(&avg, (uint8_t)s1); bb_push(&avg, (uint8_t)s2);
     }
+    float outp[3];
+    {                                                            /* impl.hpp:1518-1520, 1559-1563: corner + 0.5 * resolution, assigned to float */
+      uint32_t k3c[3]; demorton3(codes[i], d, k3c);
+      for (int a = 0; a < 3; a++) { double corner = (double)k3c[a] * p->octree_resolution + b.min[a]; outp[a] = (float)(corner + 0.5 * p->octree_resolution); }
+    }
     if (p->do_centroid) {                                        /* impl.hpp:1565-1573, pcv2.h:83-97, pcl::compute3DCentroid (float accumulation, index order) */
       uint32_t k3[3]; demorton3(codes[i], d, k3);
       float acc[3] = { 0, 0, 0 };
@@ -721,12 +727,20 @@ int orc_encode(const orc_params *p, uint32_t frame_id, const void *pts, size_t n
       float cnt = (float)(j - i);
       for (int a = 0; a < 3; a++) {
         float c = acc[a] / cnt;
+        outp[a] = c;                                             /* impl.hpp:1569-1571 */
         double corner = (double)k3[a] * p->octree_resolution + b.min[a];
         int q = (int)(((double)c - corner) / 0.001f);          /* centroid_coder_ precision stays 0.001f (App. C-4) */
         if (q > 127) q = 127;
         if (q < -127) q = -127;
         bb_push(&cen, (uint8_t)q);
       }
+    }
+    if (outc) {                                                  /* PointXYZRGB(): data[3] = 1, r = g = b = 0, a = 255; colours = the bytes just pushed (impl.hpp:1552-1556) */
+      uint8_t *o = outc + 32 * (V - 1);
+      const float one = 1.0f;
+      memcpy(o, outp, 12); memcpy(o + 12, &one, 4);
+      if (with_color) { o[16] = avg.p[avg.n - 3]; o[17] = avg.p[avg.n - 2]; o[18] = avg.p[avg.n - 1]; }
+      o[19] = 255;
     }
     i = j;
   }
@@ -782,8 +796,8 @@ int orc_encode(const orc_params *p, uint32_t frame_id, const void *pts, size_t n
     info->t_ms[7] = t6 - t0;
   }
   if (dbg) { dbg->leaf_keys = leaf_keys; leaf_keys = NULL; dbg->tree_bytes = tree.p; tree.p = NULL; dbg->avg_colors = avg.p; avg.p = NULL;
-             dbg->color_payload = col.p; col.p = NULL; dbg->centroid_bytes = cen.p; cen.p = NULL; }
-  free(leaf_keys); free(tree.p); free(avg.p); free(cen.p); free(col.p); free(codes); free(idx);
+             dbg->color_payload = col.p; col.p = NULL; dbg->centroid_bytes = cen.p; cen.p = NULL; dbg->output_cloud = outc; outc = NULL; }
+  free(leaf_keys); free(tree.p); free(avg.p); free(cen.p); free(col.p); free(codes); free(idx); free(outc);
   *out = os.p; *out_len = os.n;
   return 0;
 }

@@ -67,6 +67,7 @@ typedef struct orc_debug {
   uint8_t *avg_colors;          /* 3V bytes, B,G,R per leaf, before jpeg */
   uint8_t *color_payload;       /* n_color_bytes */
   uint8_t *centroid_bytes;      /* 3V or NULL */
+  uint8_t *output_cloud;        /* V x 32 bytes: the encoder's simplified cloud output_ (impl.hpp:96,1549-1576; [PCL] getOutputCloud, eval.hpp:862) */
 } orc_debug;
 
 void orc_default_params(orc_params *p);

@@ -30,7 +30,7 @@ class OrcInfo(C.Structure):
 class OrcDebug(C.Structure):
     _fields_ = [("leaf_keys", C.POINTER(C.c_uint64)), ("tree_bytes", C.POINTER(C.c_uint8)),
                 ("avg_colors", C.POINTER(C.c_uint8)), ("color_payload", C.POINTER(C.c_uint8)),
-                ("centroid_bytes", C.POINTER(C.c_uint8))]
+                ("centroid_bytes", C.POINTER(C.c_uint8)), ("output_cloud", C.POINTER(C.c_uint8))]
 
 
 def build(force=False):
@@ -117,6 +117,7 @@ def encode(points, params=None, frame_id=1, debug=False):
         avg_colors=_take(dbg.avg_colors, 3 * V) if dbg.avg_colors else np.zeros(0, np.uint8),
         color_payload=_take(dbg.color_payload, info.n_color_bytes) if dbg.color_payload else np.zeros(0, np.uint8),
         centroid_bytes=_take(dbg.centroid_bytes, 3 * V) if dbg.centroid_bytes else np.zeros(0, np.uint8),
+        output_cloud=_take(dbg.output_cloud, 32 * V).reshape(-1, 32) if dbg.output_cloud else np.zeros((0, 32), np.uint8),
     )
     L.orc_free_debug(C.byref(dbg))
     return data, info, d

@@ -211,6 +211,35 @@ def test_reference_facade(K, oracle):
     assert cdc.getPerformanceMetrics()[0] > 0
 
 
+@pytest.mark.parametrize("centroid", [False, True])
+def test_output_cloud_matches_oracle(K, oracle, centroid):
+    """[PCL] getOutputCloud() after encodePointCloud (eval.hpp:862): the encoder's simplified cloud, impl.hpp:1549-1576."""
+    clouds = [synth.gen_surface(30000, 60), synth.gen_uniform(5000, 61), np.zeros(0, synth.POINT_DTYPE)]
+    kp = K.default_params(octree_bits=9, keep_centroid=centroid)
+    c = K.Codec(kp)
+    streams = c.encode_batch(clouds)
+    op = oracle.default_params(octree_bits=9, do_centroid=int(centroid))
+    for i, cl in enumerate(clouds):
+        got = c.output_cloud(i)
+        if np.asarray(cl).size == 0:
+            assert got.shape[0] == 0
+            continue
+        _, _, dbg = oracle.encode(cl, op, frame_id=1, debug=True)
+        assert np.array_equal(got, dbg["output_cloud"])
+    c.decode_batch([streams[0]])                                   # any later call invalidates it
+    with pytest.raises(K.Ccv2Error) as ei:
+        c.output_cloud(0)
+    assert ei.value.status == -3
+    c.close()
+    cdc = K.OctreePointCloudCodecV2(K.MANUAL_CONFIGURATION, False, 2.0 ** -9, 2.0 ** -9, True, 0, True, 8, 1, False, False, False, 85, 1)
+    cdc.encodePointCloud(clouds[0])
+    assert cdc.getOutputCloud().shape[0] == c_leaves(oracle, clouds[0])
+
+
+def c_leaves(oracle, cl):
+    return oracle.encode(cl, oracle.default_params(octree_bits=9), frame_id=1, debug=True)[1].n_leaves
+
+
 def test_roundtrip_call_matches_separate_calls(K, oracle):
     clouds = [synth.gen_surface(20000 + 1000 * i, 60 + i) for i in range(11)] + [np.zeros(0, synth.POINT_DTYPE)]
     kp = K.default_params(octree_bits=9)

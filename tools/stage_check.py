@@ -79,6 +79,7 @@ def run_case(name, clouds, kp, results):
         if kp.do_color_encoding:
             cmp("avg_colors", cdc.debug_fetch(i, 2), dbg["avg_colors"], res)
             cmp("color_payload", cdc.debug_fetch(i, 3), dbg["color_payload"], res)
+        cmp("output_cloud", cdc.output_cloud(i).reshape(-1), dbg["output_cloud"].reshape(-1), res)
         if streams is not None:
             cmp("stream", np.frombuffer(streams[i], np.uint8), np.frombuffer(data, np.uint8), res)
         results.extend((name + ":f%d:" % i + k, v) for k, v in res)
