@@ -289,6 +289,14 @@ def main():
     S = float(np.mean(lens)); V = float(np.mean(ns))
     alg_bytes_frame = 32 * NP + 32 * V + 2 * S                                # encode+decode, per frame
 
+    # ---- single-frame latency: one cloud per call, device resident, best of 3 ----
+    lat = {"encode": 1e30, "decode": 1e30}
+    for _ in range(3):
+        l1 = codec.encode_batch_raw(in_ptrs[:1], [NP], str_ptrs[:1], [cap])
+        lat["encode"] = min(lat["encode"], codec.last_device_ms)
+        codec.decode_batch_raw(str_ptrs[:1], l1, out_ptrs[:1], [NP])
+        lat["decode"] = min(lat["decode"], codec.last_device_ms)
+
     # ---- e2e: same calls with pinned host buffers ----
     e2e = None
     if F_e2e:
@@ -342,7 +350,7 @@ def main():
                 "value_api": "ccv2_roundtrip_batch" if args.value_api == "roundtrip" else "ccv2_encode_batch + ccv2_decode_batch",
                 "encode_ms_per_step": split_final["enc"] / split_steps, "decode_ms_per_step": split_final["dec"] / split_steps,
                 "encode_only_mpoints_s": F * NP * split_steps / max(split_final["enc"], 1e-9) / 1e3, "decode_only_mpoints_s": F * NP * split_steps / max(split_final["dec"], 1e-9) / 1e3,
-                "stream_bytes_per_frame": S, "voxels_per_frame": V}
+                "single_frame_latency_ms": lat, "stream_bytes_per_frame": S, "voxels_per_frame": V}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -666,30 +666,39 @@ __global__ void __launch_bounds__(NODE_THREADS) dec_points_kernel(DecFrame *fram
   const uint32_t ntiles = (nb + NODE_THREADS - 1) / NODE_THREADS;
   if (f.error || blockIdx.x >= ntiles) return;
   __shared__ uint32_t s_tile; __shared__ uint64_t s_scan[33]; __shared__ uint64_t s_excl;
+  __shared__ uint64_t s_prefix[NODE_THREADS];
+  __shared__ uint16_t s_leaf[NODE_THREADS * 8];             // node-in-tile << 3 | child, in output order
   if (threadIdx.x == 0) s_tile = atomicAdd(&f.ticket[TK_NODES], 1u);
   __syncthreads();
   const uint32_t tile = s_tile, g = tile * NODE_THREADS + threadIdx.x;
   uint32_t byte = 0; uint64_t prefix = 0;
   if (g < nb) { byte = f.node_byte[g]; prefix = f.node_prefix[g]; }
+  s_prefix[threadIdx.x] = prefix;
   const uint32_t cnt = __popc(byte);
   uint64_t tot;
-  uint64_t excl = block_excl_scan_u64(cnt, &tot, s_scan);
+  const uint64_t excl_local = block_excl_scan_u64(cnt, &tot, s_scan);
   if (threadIdx.x < 32) { uint64_t e = scan_lookback(f.scan_status, tile, tot); if (threadIdx.x == 0) s_excl = e; }
+  {                                                          // a node lists its leaves; afterwards one thread per LEAF
+    uint32_t w = (uint32_t)excl_local, m = byte;
+    while (m) { s_leaf[w++] = (uint16_t)((threadIdx.x << 3) | (__ffs(m) - 1)); m &= m - 1; }
+  }
   __syncthreads();
-  excl += s_excl;
-  if (g >= nb) return;
-  if (g == nb - 1) { uint64_t V = excl + cnt; f.V = (uint32_t)V; if (V != f.point_count || V > f.out_cap) atomicOr(&f.error, FERR_BAD_STREAM); }
+  const uint64_t base = s_excl;
+  if (g == nb - 1) { uint64_t V = base + excl_local + cnt; f.V = (uint32_t)V; if (V != f.point_count || V > f.out_cap) atomicOr(&f.error, FERR_BAD_STREAM); }
   const double res = f.res;
-  uint32_t i = (uint32_t)excl;
-  while (byte) {
-    const uint32_t c = __ffs(byte) - 1; byte &= byte - 1;
-    if (i >= f.out_cap) break;
-    const uint64_t key = (prefix << 3) | c;
+  const uint32_t do_centroid = f.do_centroid;
+  const uint64_t out_cap = f.out_cap;
+  for (uint32_t j = threadIdx.x; j < (uint32_t)tot; j += NODE_THREADS) {     // consecutive threads write consecutive 32-byte records
+    const uint64_t i64 = base + j;
+    if (i64 >= out_cap) break;
+    const uint32_t i = (uint32_t)i64;
+    const uint32_t e = s_leaf[j];
+    const uint64_t key = (s_prefix[e >> 3] << 3) | (e & 7u);
     const uint32_t k3[3] = { compact3(key >> 2), compact3(key >> 1), compact3(key) };
     float xyz[3];
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-      if (f.do_centroid) {                                  // pcv2.h:103-118
+      if (do_centroid) {                                    // pcv2.h:103-118
         double corner = __dadd_rn(__dmul_rn((double)k3[a], res), f.bmin[a]);
         uint32_t q = (3ull * i + a) < f.ncen ? f.cen[3ull * i + a] : 0;
         xyz[a] = (float)__dadd_rn(corner, (double)__fmul_rn((float)q, 0.001f));
@@ -699,7 +708,6 @@ __global__ void __launch_bounds__(NODE_THREADS) dec_points_kernel(DecFrame *fram
     uint4 *o = (uint4 *)(f.out_pts + 32ull * i);
     o[0] = make_uint4(__float_as_uint(xyz[0]), __float_as_uint(xyz[1]), __float_as_uint(xyz[2]), 0x3F800000u);
     o[1] = make_uint4(rgba, 0, 0, 0);
-    i++;
   }
 }
 
