@@ -123,6 +123,15 @@ __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0,
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p) { return *(const volatile uint64_t *)p; }
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 
+// Shared memory through 32-bit window addresses: with generic pointers the compiler rebuilds the CTA's shared window base
+// (S2R SR_CgaCtaId + LEA) in front of every access, which is a third of the instructions of the serial one-lane loops.
+__device__ __forceinline__ uint32_t smem_addr(const volatile void *p) { return (uint32_t)__cvta_generic_to_shared(const_cast<const void *>(p)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_volatile_u32(uint32_t a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+
 // spread the low 21 bits of v so that bit i lands at bit 3i
 __device__ __forceinline__ uint64_t spread3(uint32_t v) {
   uint64_t x = v & 0x1FFFFFull;

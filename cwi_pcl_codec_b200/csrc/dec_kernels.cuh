@@ -260,14 +260,18 @@ __device__ inline void dfs_walk_fast(DecFrame &f) {
 // bytes -- dec_expand_kernel turns those records into bottom-level records in parallel afterwards.
 __device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *lut, uint32_t *stack) {
   const uint32_t B = rg->B, d = rg->depth;
+  const uint32_t rg_a = smem_addr(rg), lut_a = smem_addr(lut), st_a = smem_addr(stack);
+  const uint32_t ring_a = rg_a + (uint32_t)offsetof(WalkRing, ring), prod_a = rg_a + (uint32_t)offsetof(WalkRing, prod),
+                 cons_a = rg_a + (uint32_t)offsetof(WalkRing, cons), dead_a = rg_a + (uint32_t)offsetof(WalkRing, dead);
   uint32_t pos = 0, cw = NONE_U32, win = 0, avail = 0, pub = 0;
   bool bad = false;
   auto read_byte = [&](uint32_t &dst) -> bool {             // byte at stream offset pos; false when the producer died
     const uint32_t wi = pos >> 2;
     if (wi != cw) {
-      while (wi >= avail) { avail = rg->prod; if (rg->dead) return false; if (wi >= avail) __nanosleep(256); }   // the decoder publishes every 64 symbols (~8 us): sleep rather than take issue slots from the decoders on this SM
-      win = rg->ring[wi & (RING_WORDS - 1)]; cw = wi;
-      if ((wi >> 4) != pub) { pub = wi >> 4; rg->cons = wi; }
+      // the decoder publishes every 64 symbols (~8 us): sleep rather than take issue slots from the decoders on this SM
+      while (wi >= avail) { avail = lds_volatile_u32(prod_a); if (lds_volatile_u32(dead_a)) return false; if (wi >= avail) __nanosleep(256); }
+      win = lds_volatile_u32(ring_a + ((wi & (RING_WORDS - 1)) << 2)); cw = wi;
+      if ((wi >> 4) != pub) { pub = wi >> 4; sts_volatile_u32(cons_a, wi); }
     }
     dst = __byte_perm(win, 0, 0x4440u | (pos & 3u)); pos++;
     return true;
@@ -282,20 +286,20 @@ __device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *
     const uint32_t Lb = d - 2;                              // branches at this level have bottom-level children
     for (;;) {
       if (L == Lb) {                                        // record (prefix, mask, offset of the first child) and skip the children
-        const uint32_t k = lut[m] >> 16;
+        const uint32_t k = lds_u32(lut_a + (m << 2)) >> 16;
         if (pos + k > B || n2 >= cap) { bad = true; break; }
         l2p[n2] = prefix; l2m[n2] = (uint8_t)m; l2o[n2] = pos; n2++;
         pos += k; m = 0;
       }
-      while (m == 0 && L) { L--; prefix >>= 3; m = stack[L]; }   // pop exhausted branches
+      while (m == 0 && L) { L--; prefix >>= 3; m = lds_u32(st_a + (L << 2)); }   // pop exhausted branches
       if (m == 0) break;                                     // the root is exhausted: done
-      const uint32_t e = lut[m];                             // descend into the next child
-      stack[L] = e & 255u; prefix = (prefix << 3) | ((e >> 8) & 7u); L++;
+      const uint32_t e = lds_u32(lut_a + (m << 2));          // descend into the next child
+      sts_u32(st_a + (L << 2), e & 255u); prefix = (prefix << 3) | ((e >> 8) & 7u); L++;
       if (pos >= B) { bad = true; break; }
       if (!read_byte(m)) { bad = true; break; }
     }
   }
-  rg->dead = 1;                                            // the decoder must never wait for a walker that has left
+  sts_volatile_u32(dead_a, 1u);                             // the decoder must never wait for a walker that has left
   if (pos != B) bad = true;
   if (bad) { atomicOr(&f.error, FERR_BAD_STREAM); nb = 0; n2 = 0; }
   f.n_bottom = nb; f.n_l2 = n2; f.l2_valid = (d >= 2 && !bad) ? 1u : 0u;

@@ -26,8 +26,7 @@
 #define LPS_LUT_SHIFT 4
 #define LPS_LUT_ENTRIES (65536 >> LPS_LUT_SHIFT)
 #define LPS_Q_SLACK 3                                      // the float quotient estimate is within [-3, +0] of ... see LPS_DEC_LOOKUP
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+
 struct LpsSmem {
   uint32_t pair[(256 + 2) * LPS_DEC_FRAMES];               // [symbol][lane]: cum[s] | cum[s+1] << 16 (two pad rows: the search reads s0 + 1, s0 + 2 unguarded)
   uint8_t lut[LPS_LUT_ENTRIES * LPS_DEC_FRAMES];           // [bucket][lane]: largest s with cum[s] <= (bucket << LPS_LUT_SHIFT) - LPS_Q_SLACK
