@@ -739,9 +739,10 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       if (any_h2d) { CU(cudaEventRecord(c->ev_h2d[g], c->copy_stream)); CU(cudaStreamWaitEvent(st, c->ev_h2d[g], 0)); }
       if (rt) LAUNCH("link_kernel", link_kernel<<<(gf + 63) / 64, 64, 0, st>>>(df + f0, dg, gf));
       // Two entropy stages.  dec_entropy_kernel (a CTA per frame) is the faster one when nothing else runs (decode-only
-      // calls: 374 ms against 414 ms for 1024 frames); in a round trip its 7 CTAs per SM compete with the other groups'
+      // calls: 374 ms against 414 ms for 1024 frames) and when the copies pace the pipeline (host buffers: 935 against
+      // 896 Mpoints/s end to end); in a device-resident round trip its 7 CTAs per SM compete with the other groups'
       // encode kernels and the lane-per-stream decoder, 8 frames to a warp on an SM of its own, wins (677 ms against 753 ms).
-      if (c->lps_dec < 0 ? rt : c->lps_dec != 0) {
+      if (c->lps_dec < 0 ? (rt && !host_io) : c->lps_dec != 0) {
         // tree layers on the group's stream, speculated colour layers on a side stream at the same time
         cudaStream_t s2 = c->profiling ? st : c->side_streams[g % SIDE_STREAMS];
         const unsigned lps_ctas = (unsigned)((gf + LPS_DEC_FRAMES - 1) / LPS_DEC_FRAMES);
