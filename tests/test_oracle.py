@@ -178,3 +178,27 @@ def test_frozen_stream_hashes(oracle, golden_dir):
         assert hashlib.sha256(dec.tobytes()).hexdigest() == e["decoded_sha256"], name
         checked += 1
     assert checked >= 5
+
+
+def test_output_cloud_is_the_simplified_cloud_of_the_encoder():
+    """impl.hpp:1549-1576 / [PCL] getOutputCloud (eval.hpp:862): one point per voxel in stream order, voxel centre (or the
+    float centroid), average colour before JPEG, alpha 255."""
+    from oracle import oracle as O
+    from cwi_pcl_codec_b200 import synth
+    cl = synth.gen_surface(20000, 3)
+    for cen in (0, 1):
+        data, info, dbg = O.encode(cl, O.default_params(octree_bits=8, do_centroid=cen, color_coding_type=3), frame_id=1, debug=True)
+        oc = dbg["output_cloud"]
+        dec, _ = O.decode(data)
+        assert oc.shape == (info.n_leaves, 32) and dec.shape == oc.shape
+        xyz_o = oc[:, :12].copy().view(np.float32).reshape(-1, 3)
+        xyz_d = dec[:, :12].copy().view(np.float32).reshape(-1, 3)
+        if cen == 0:
+            assert np.array_equal(xyz_o, xyz_d)                     # same voxel centres as the decoder reconstructs
+        else:
+            assert np.abs(xyz_o - xyz_d).max() <= 0.001 + 1e-6      # the centroid coder quantises to 1 mm (pcv2.h:83-118)
+        # colour type 3 ships the raw averages: the decoder's colours are the encoder's averages
+        assert np.array_equal(oc[:, 16:19], dec[:, 16:19])
+        assert np.array_equal(oc[:, 16:19].reshape(-1), dbg["avg_colors"])
+        assert set(oc[:, 19].tolist()) == {255}
+        assert np.all(oc[:, 12:16].copy().view(np.float32) == 1.0)
