@@ -384,7 +384,7 @@ def profile_roofline(K, lib, args, frames, alg_bytes_frame):
     # the dominant kernel above is a serial dependency chain whose HBM fraction is tiny by construction
     N_, V_ = float(len(frames[0])), (alg_bytes_frame - 32.0 * len(frames[0])) / 32.0 * 0.96
     own = {"keygen_kernel": 32 * N_ + 12 * N_, "sort_pass_kernel": 24 * N_, "leaf_scan_kernel": 8 * N_ + 17 * V_,
-           "dec_points_kernel": 32 * V_ + 9 * V_ / 1.7, "hist_kernel": 1.6 * V_ + 0.25 * V_}
+           "dec_leaves_kernel": 32 * V_ + 13 * V_ / 2.9 + 1.6 * V_, "hist_kernel": 1.6 * V_ + 0.25 * V_}
     hbm_kernels = {}
     for n_, ms_, k_, fpl_ in prof:
         if n_ in own and ms_ > 0:

@@ -759,7 +759,6 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       } else
       LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<gf, 96, serial_smem_dec, st>>>(dg, c->use_ring));
       mark(g, "entropy", st);
-      LAUNCH("dec_expand_kernel", dec_expand_kernel<<<dim3((unsigned)((pmax + 255) / 256), gf), 256, 0, st>>>(dg));
       LAUNCH("jpeg_destuff_kernel", jpeg_destuff_kernel<<<gf, 1024, 0, st>>>(dg));
       LAUNCH("dec_serial_kernel", dec_serial_kernel<<<steered_grid, 64, 0, st>>>(dg, f0, gf));
       if (prm.color_coding_type == 2) {
@@ -770,6 +769,7 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       }
       const size_t img_h = pmax / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = mcu_h * 16 * 6;
       LAUNCH("jpeg_idct_kernel", jpeg_idct_kernel<<<dim3((unsigned)((nblocks + 31) / 32), gf), 256, 0, st>>>(dg, c->d_tables));
+      LAUNCH("dec_leaves_kernel", dec_leaves_kernel<<<dim3((unsigned)((pmax + 255) / 256), gf), 256, 0, st>>>(dg));        // frames walked by the pipelined walkers
       LAUNCH("dec_points_kernel", dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg));
       mark(g, "decoded", st);
     }

@@ -257,7 +257,7 @@ __device__ inline void dfs_walk_fast(DecFrame &f) {
 // The pipelined walker (warp 1 of dec_entropy_kernel): reads the occupancy bytes out of the shared-memory ring
 // while the range decoder is still producing them.  It only has to visit the branches above the bottom level: for
 // a branch at level depth-2 it records (prefix, child mask, stream offset of the first child) and skips the child
-// bytes -- dec_expand_kernel turns those records into bottom-level records in parallel afterwards.
+// bytes -- dec_leaves_kernel turns those records into points in parallel afterwards.
 __device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *lut, uint32_t *stack) {
   const uint32_t B = rg->B, d = rg->depth;
   const uint32_t rg_a = smem_addr(rg), lut_a = smem_addr(lut), st_a = smem_addr(stack);
@@ -304,35 +304,6 @@ __device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *
   if (bad) { atomicOr(&f.error, FERR_BAD_STREAM); nb = 0; n2 = 0; }
   f.n_bottom = nb; f.n_l2 = n2; f.l2_valid = (d >= 2 && !bad) ? 1u : 0u;
   f.walk_done = 1;
-}
-
-// Expands the level depth-2 records of the pipelined walker into bottom-level records (chained scan of popcounts).
-__global__ void __launch_bounds__(256) dec_expand_kernel(DecFrame *frames) {
-  DecFrame &f = frames[blockIdx.y];
-  if (f.error || !f.l2_valid) return;
-  const uint32_t n2 = f.n_l2;
-  const uint32_t ntiles = (n2 + 255) / 256;
-  if (blockIdx.x >= ntiles) return;
-  __shared__ uint32_t s_tile; __shared__ uint64_t s_scan[33]; __shared__ uint64_t s_excl;
-  if (threadIdx.x == 0) s_tile = atomicAdd(&f.ticket[TK_EXPAND], 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile, g = tile * 256 + threadIdx.x;
-  uint32_t mask = 0, off = 0; uint64_t prefix = 0;
-  if (g < n2) { mask = f.l2_mask[g]; off = f.l2_off[g]; prefix = f.l2_prefix[g]; }
-  const uint32_t k = __popc(mask);
-  uint64_t tot;
-  uint64_t excl = block_excl_scan_u64(k, &tot, s_scan);
-  if (threadIdx.x < 32) { uint64_t e = scan_lookback(f.scan_status + f.scan_tiles_max, tile, tot); if (threadIdx.x == 0) s_excl = e; }
-  __syncthreads();
-  excl += s_excl;
-  if (g >= n2) return;
-  if (g == n2 - 1) { const uint64_t total = excl + k; if (total > f.node_cap) { atomicOr(&f.error, FERR_BAD_STREAM); f.n_bottom = 0; } else f.n_bottom = (uint32_t)total; }
-  uint32_t o = (uint32_t)excl, i = 0;
-  while (mask && o < f.node_cap) {
-    const uint32_t c = __ffs(mask) - 1; mask &= mask - 1;
-    f.node_prefix[o] = (prefix << 3) | c; f.node_byte[o] = f.tree[off + i];
-    o++; i++;
-  }
 }
 
 __device__ inline void dfs_walk(DecFrame &f) {
@@ -668,7 +639,7 @@ __global__ void __launch_bounds__(NODE_THREADS) dec_points_kernel(DecFrame *fram
   DecFrame &f = frames[blockIdx.y];
   const uint32_t nb = f.n_bottom;
   const uint32_t ntiles = (nb + NODE_THREADS - 1) / NODE_THREADS;
-  if (f.error || blockIdx.x >= ntiles) return;
+  if (f.error || f.l2_valid || blockIdx.x >= ntiles) return;       // l2_valid: dec_leaves_kernel has written the points
   __shared__ uint32_t s_tile; __shared__ uint64_t s_scan[33]; __shared__ uint64_t s_excl;
   __shared__ uint64_t s_prefix[NODE_THREADS];
   __shared__ uint16_t s_leaf[NODE_THREADS * 8];             // node-in-tile << 3 | child, in output order
@@ -698,6 +669,72 @@ __global__ void __launch_bounds__(NODE_THREADS) dec_points_kernel(DecFrame *fram
     const uint32_t i = (uint32_t)i64;
     const uint32_t e = s_leaf[j];
     const uint64_t key = (s_prefix[e >> 3] << 3) | (e & 7u);
+    const uint32_t k3[3] = { compact3(key >> 2), compact3(key >> 1), compact3(key) };
+    float xyz[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      if (do_centroid) {                                    // pcv2.h:103-118
+        double corner = __dadd_rn(__dmul_rn((double)k3[a], res), f.bmin[a]);
+        uint32_t q = (3ull * i + a) < f.ncen ? f.cen[3ull * i + a] : 0;
+        xyz[a] = (float)__dadd_rn(corner, (double)__fmul_rn((float)q, 0.001f));
+      } else xyz[a] = (float)__dadd_rn(__dmul_rn(__dadd_rn((double)k3[a], 0.5), res), f.bmin[a]);   // impl.hpp:1630-1632
+    }
+    const uint32_t rgba = dec_color(f, i);
+    uint4 *o = (uint4 *)(f.out_pts + 32ull * i);
+    o[0] = make_uint4(__float_as_uint(xyz[0]), __float_as_uint(xyz[1]), __float_as_uint(xyz[2]), 0x3F800000u);
+    o[1] = make_uint4(rgba, 0, 0, 0);
+  }
+}
+
+// The pipelined walker's level-(d-2) records straight to points: a record's children are the bottom-level bytes at its
+// stream offset, their set bits are the leaves.  One chained scan over the records' leaf counts gives every record its
+// place in the output; the records of a tile list their leaves in shared memory and then one thread per LEAF writes a
+// 32-byte point (consecutive threads, consecutive records).  Does the work of dec_points_kernel (and of a separate expansion pass) on this
+// path: no bottom-node arrays, one scan instead of two.  grid (ceil(node_cap / 256), frames)
+__global__ void __launch_bounds__(256) dec_leaves_kernel(DecFrame *frames) {
+  DecFrame &f = frames[blockIdx.y];
+  if (f.error || !f.l2_valid) return;
+  const uint32_t n2 = f.n_l2;
+  const uint32_t ntiles = (n2 + 255) / 256;
+  if (blockIdx.x >= ntiles) return;
+  __shared__ uint32_t s_tile; __shared__ uint64_t s_scan[33]; __shared__ uint64_t s_excl;
+  __shared__ uint64_t s_prefix[256];
+  __shared__ uint16_t s_leaf[256 * 64];                      // record-in-tile << 6 | child << 3 | leaf bit, in output order
+  if (threadIdx.x == 0) s_tile = atomicAdd(&f.ticket[TK_EXPAND], 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile, g = tile * 256 + threadIdx.x;
+  uint32_t mask = 0, off = 0; uint64_t prefix = 0;
+  if (g < n2) { mask = f.l2_mask[g]; off = f.l2_off[g]; prefix = f.l2_prefix[g]; }
+  s_prefix[threadIdx.x] = prefix;
+  uint32_t bytes[8], cnt = 0;
+  const uint32_t k = __popc(mask);
+#pragma unroll
+  for (int i = 0; i < 8; i++) { bytes[i] = (uint32_t)i < k ? f.tree[off + i] : 0u; cnt += __popc(bytes[i]); }
+  uint64_t tot;
+  const uint64_t excl_local = block_excl_scan_u64(cnt, &tot, s_scan);
+  if (threadIdx.x < 32) { uint64_t e = scan_lookback(f.scan_status + f.scan_tiles_max, tile, tot); if (threadIdx.x == 0) s_excl = e; }
+  {
+    uint32_t w = (uint32_t)excl_local, m = mask;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (!m) break;
+      const uint32_t c = __ffs(m) - 1; m &= m - 1;
+      uint32_t b = bytes[i];
+      while (b) { s_leaf[w++] = (uint16_t)((threadIdx.x << 6) | (c << 3) | (__ffs(b) - 1)); b &= b - 1; }
+    }
+  }
+  __syncthreads();
+  const uint64_t base = s_excl;
+  if (g == n2 - 1) { uint64_t V = base + excl_local + cnt; f.V = (uint32_t)V; if (V != f.point_count || V > f.out_cap) atomicOr(&f.error, FERR_BAD_STREAM); }
+  const double res = f.res;
+  const uint32_t do_centroid = f.do_centroid;
+  const uint64_t out_cap = f.out_cap;
+  for (uint32_t j = threadIdx.x; j < (uint32_t)tot; j += 256) {
+    const uint64_t i64 = base + j;
+    if (i64 >= out_cap) break;
+    const uint32_t i = (uint32_t)i64;
+    const uint32_t e = s_leaf[j];
+    const uint64_t key = (((s_prefix[e >> 6] << 3) | ((e >> 3) & 7u)) << 3) | (e & 7u);
     const uint32_t k3[3] = { compact3(key >> 2), compact3(key >> 1), compact3(key) };
     float xyz[3];
 #pragma unroll
