@@ -2,8 +2,9 @@
 //
 // Execution model: a batch of frames is cut into groups; every group runs start-to-finish on one CUDA stream of
 // a small round-robin pool (H2D of the inputs, the parallel kernels with blockIdx.y = frame, the serial
-// one-warp-per-stream range coder, assembly, D2H of the results).  Groups on different streams overlap, which
-// is what hides the serial entropy stage behind other groups' parallel work.  No host synchronisation happens
+// range coder stage -- lane-per-stream or warp-per-stream kernels, see entropy_kernels.cuh / dec_lps_kernels.cuh --
+// assembly, D2H of the results).  Groups on different streams overlap; throughput is frames in flight divided by
+// the per-frame latency of the serial entropy stage.  No host synchronisation happens
 // inside a group: all sizes (depth, V, B, J, stream length) are device-side values in the frame records.
 #include "../../include/ccv2.h"
 #include "common.cuh"
@@ -27,7 +28,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-// The batch driver keeps 9 streams busy (8 group streams + 1 control stream).  CUDA maps streams onto
+// The batch driver keeps up to 26 streams busy (8 or 16 group streams, 8 side streams, a control and a copy stream).  CUDA maps streams onto
 // CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue serialise behind each other's
 // long serial kernels (measured: 2x on the round trip).  Ask for more queues unless the user already chose -- this only
 // takes effect if it happens before the process creates its CUDA context, so hosts that initialise CUDA first
