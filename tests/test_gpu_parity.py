@@ -211,6 +211,17 @@ def test_reference_facade(K, oracle):
     assert cdc.getPerformanceMetrics()[0] > 0
 
 
+@pytest.mark.parametrize("env", [{"CCV2_LPS_DEC": "1"}, {"CCV2_LPS_ENC": "0", "CCV2_LPS_DEC": "0"}])
+def test_both_entropy_stage_implementations_are_bit_exact(K, oracle, env, monkeypatch):
+    """The lane-per-stream coders and the CTA-per-frame ones are interchangeable (the library picks by call type; the
+    knobs are read when a handle is created): same streams, same clouds, whichever is forced."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    clouds = [synth.gen_surface(40000, 70 + i) for i in range(11)] + [np.zeros(0, synth.POINT_DTYPE), synth.gen_uniform(3000, 90)]
+    for kw in ({"octree_bits": 9}, {"octree_bits": 8, "keep_centroid": True}, {"octree_bits": 9, "color_coding_type": 2}):
+        check_batch(K, oracle, clouds, K.default_params(**kw))
+
+
 @pytest.mark.parametrize("centroid", [False, True])
 def test_output_cloud_matches_oracle(K, oracle, centroid):
     """[PCL] getOutputCloud() after encodePointCloud (eval.hpp:862): the encoder's simplified cloud, impl.hpp:1549-1576."""
