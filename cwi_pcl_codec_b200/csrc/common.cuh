@@ -39,6 +39,13 @@ struct EncParams {             // by value to kernels
   int prefix_len;              // points handled exactly by the single-CTA bbox kernel
 };
 
+// One entry per change of the bounding box while the cloud is added in input order ([PCL] adoptBoundingBoxToPoint):
+// entry 0 is the definition by the first finite point, every later one a growth step (re-rooting).  keygen needs them
+// to give a point the key PCL gave it: computed against the box in force when the point was added, plus 1 << depth_before
+// on every axis whose minimum moved in a later growth step (oracle/ccv2_oracle.c orc_bbox_keys).
+#define CCV2_MAX_EVENTS 32
+struct BoxEvent { double mn[3]; uint32_t idx, depth_before, mask, _pad; };   // mn: box minimum after the event; mask bit a: axis a moved
+
 struct EncFrame {
   // region of the group-slot workspace that must be zero before the pipeline starts (zero_region_kernel)
   uint8_t *zero_ptr; uint64_t zero_bytes;
@@ -47,6 +54,7 @@ struct EncFrame {
   // bbox / keys
   double bmin[3], bmax[3];
   uint32_t depth, defined, n_finite, violator, rekey, npasses;
+  uint32_t n_events, _pade; BoxEvent ev[CCV2_MAX_EVENTS];
   // leaves
   uint32_t V, B;
   // jpeg geometry / sizes

@@ -19,7 +19,9 @@ __device__ __forceinline__ bool box_violates(const Box &b, const double p[3]) {
   return p[0] < b.mn[0] || p[1] < b.mn[1] || p[2] < b.mn[2] || p[0] >= b.mx[0] || p[1] >= b.mx[1] || p[2] >= b.mx[2];
 }
 // adoptBoundingBoxToPoint for one point; loops until the point fits. Returns false on depth overflow.
-__device__ inline bool box_adopt(Box &b, const double p[3], double res) {
+// Every change of the box is logged (log != nullptr only in the one thread that writes the frame record; nev is
+// carried by all threads): keygen replays the log to key every point against the box of its own time.
+__device__ inline bool box_adopt(Box &b, const double p[3], double res, uint32_t idx, uint32_t &nev, BoxEvent *log) {
   const double eps = 1.1920928955078125e-07;   // (double) numeric_limits<float>::epsilon()
   for (int guard = 0; guard < 64; guard++) {
     if (!b.defined) {
@@ -40,6 +42,8 @@ __device__ inline bool box_adopt(Box &b, const double p[3], double res) {
         if (over > eps) { b.mn[a] = __dsub_rn(b.mn[a], over); b.mx[a] = __dadd_rn(b.mx[a], over); }
       }
       b.defined = 1;
+      if (log && nev < CCV2_MAX_EVENTS) { BoxEvent &e = log[nev]; e.idx = idx; e.depth_before = 0; e.mask = 0; e._pad = 0; for (int a = 0; a < 3; a++) e.mn[a] = b.mn[a]; }
+      nev++;
       continue;
     }
     bool up[3], any = false;
@@ -47,7 +51,10 @@ __device__ inline bool box_adopt(Box &b, const double p[3], double res) {
     if (!any) return true;
     if (b.depth >= CCV2_MAX_DEPTH) return false;
     double side = __dmul_rn((double)(1u << b.depth), res);
-    for (int a = 0; a < 3; a++) if (!up[a]) b.mn[a] = __dsub_rn(b.mn[a], side);
+    uint32_t mask = 0;
+    for (int a = 0; a < 3; a++) if (!up[a]) { b.mn[a] = __dsub_rn(b.mn[a], side); mask |= 1u << a; }
+    if (log && nev < CCV2_MAX_EVENTS) { BoxEvent &e = log[nev]; e.idx = idx; e.depth_before = b.depth; e.mask = mask; e._pad = 0; for (int a = 0; a < 3; a++) e.mn[a] = b.mn[a]; }
+    nev++;
     b.depth++;
     side = __dsub_rn(__dmul_rn((double)(1u << b.depth), res), eps);
     for (int a = 0; a < 3; a++) b.mx[a] = __dadd_rn(b.mn[a], side);
@@ -59,15 +66,15 @@ __global__ void __launch_bounds__(1024) bbox_kernel(EncFrame *frames, EncParams 
   EncFrame &f = frames[blockIdx.x];
   __shared__ uint32_t s_first[2][32];
   __shared__ float s_pt[2][3];
-  uint32_t start, end;
+  uint32_t start, end, nev;
   Box b;
   if (mode == 0) {
-    start = 0; end = min(f.n, (uint32_t)P.prefix_len);
+    start = 0; end = min(f.n, (uint32_t)P.prefix_len); nev = 0;
     b.defined = 0; b.depth = 0;
     for (int a = 0; a < 3; a++) { b.mn[a] = 0; b.mx[a] = 0; }
   } else {
     if (f.violator == NONE_U32 || (f.error & FERR_DEPTH)) return;
-    start = f.violator; end = f.n;
+    start = f.violator; end = f.n; nev = f.n_events;
     b.defined = f.defined; b.depth = f.depth;
     for (int a = 0; a < 3; a++) { b.mn[a] = f.bmin[a]; b.mx[a] = f.bmax[a]; }
   }
@@ -94,14 +101,14 @@ __global__ void __launch_bounds__(1024) bbox_kernel(EncFrame *frames, EncParams 
       if (threadIdx.x == m) { s_pt[ph][0] = (float)p[0]; s_pt[ph][1] = (float)p[1]; s_pt[ph][2] = (float)p[2]; }
       __syncthreads();
       double pv[3] = { (double)s_pt[ph][0], (double)s_pt[ph][1], (double)s_pt[ph][2] };
-      if (!box_adopt(b, pv, P.res)) { fail = true; ph ^= 1; break; }
+      if (!box_adopt(b, pv, P.res, base + m, nev, threadIdx.x == 0 ? f.ev : nullptr)) { fail = true; ph ^= 1; break; }
       ph ^= 1;
     }
   }
   if (threadIdx.x == 0) {
-    f.defined = b.defined; f.depth = b.depth;
+    f.defined = b.defined; f.depth = b.depth; f.n_events = nev;
     for (int a = 0; a < 3; a++) { f.bmin[a] = b.mn[a]; f.bmax[a] = b.mx[a]; }
-    if (fail) f.error |= FERR_DEPTH;
+    if (fail || nev > CCV2_MAX_EVENTS) f.error |= FERR_DEPTH;
     if (mode == 1) { f.rekey = 1; f.n_finite = f.n; f.violator = NONE_U32; }
   }
 }
@@ -119,7 +126,20 @@ __global__ void __launch_bounds__(256) keygen_kernel(EncFrame *frames, EncParams
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (blockIdx.x * blockDim.x >= n) return;
   if (!f.defined || (f.error & FERR_DEPTH)) return;     // no finite point in the prefix: handled by the slow path
-  const uint32_t depth = f.depth;
+  const uint32_t depth = f.depth, ne = f.n_events;
+  // Box log.  Points added after the last change (all but a handful) see the final box; an earlier point is keyed
+  // against the box of its own time and then re-rooted: + 1 << depth_before on every axis whose minimum moved later.
+  // For power-of-two resolutions both give the same integers; for any other resolution only this order does.
+  __shared__ BoxEvent s_ev[CCV2_MAX_EVENTS];
+  const uint32_t last_change = f.ev[ne - 1].idx;
+  const bool old_box = blockIdx.x * blockDim.x <= last_change;           // block-uniform
+  if (old_box) {
+    for (uint32_t k = threadIdx.x; k < ne * (sizeof(BoxEvent) / 8); k += blockDim.x) ((uint64_t *)s_ev)[k] = ((const uint64_t *)f.ev)[k];
+    __syncthreads();
+  }
+  // the sequential walk covered [0, prefix) in the first launch and everything in the slow path; only points beyond it
+  // have to be checked against the box (a point inside the walked range fits the box of its own time by construction)
+  const uint32_t walked = rekey_only ? n : min(n, (uint32_t)P.prefix_len);
   bool fin = false, viol = false;
   uint64_t key = 1ull << (3 * depth);                    // sorts after every valid code
   if (i < n) {
@@ -128,12 +148,25 @@ __global__ void __launch_bounds__(256) keygen_kernel(EncFrame *frames, EncParams
     if (fin) {
       double p[3] = { (double)q.x, (double)q.y, (double)q.z };
       uint32_t k[3];
+      if (!old_box || i >= last_change) {
 #pragma unroll
-      for (int a = 0; a < 3; a++) {
-        viol |= (p[a] < f.bmin[a]) | (p[a] >= f.bmax[a]);
-        double t = __dsub_rn(p[a], f.bmin[a]);
-        t = P.res_pow2 ? __dmul_rn(t, P.inv_res) : __ddiv_rn(t, P.res);
-        k[a] = viol ? 0u : __double2uint_rz(t);
+        for (int a = 0; a < 3; a++) {
+          if (i >= walked) viol |= (p[a] < f.bmin[a]) | (p[a] >= f.bmax[a]);
+          double t = __dsub_rn(p[a], f.bmin[a]);
+          t = P.res_pow2 ? __dmul_rn(t, P.inv_res) : __ddiv_rn(t, P.res);
+          k[a] = viol ? 0u : __double2uint_rz(t);
+        }
+      } else {
+        int e = (int)ne - 1;
+        while (e > 0 && s_ev[e].idx > i) e--;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          double t = __dsub_rn(p[a], s_ev[e].mn[a]);
+          t = P.res_pow2 ? __dmul_rn(t, P.inv_res) : __ddiv_rn(t, P.res);
+          uint32_t kk = __double2uint_rz(t);
+          for (int j = e + 1; j < (int)ne; j++) kk += ((s_ev[j].mask >> a) & 1u) << s_ev[j].depth_before;
+          k[a] = kk;
+        }
       }
       key = morton_xyz(k[0], k[1], k[2]);
     }

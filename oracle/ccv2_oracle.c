@@ -123,6 +123,86 @@ int orc_range_decode(const uint8_t *in, size_t in_len, uint8_t *out, size_t n, s
   return pos <= in_len ? 0 : -4;
 }
 
+/* ------------------------------------------------------------------ [PCL] StaticRangeCoder (int vectors)
+ * pcl/compression/impl/entropy_range_coder.hpp, StaticRangeCoder::encodeIntVectorToStream / decodeStreamToIntVector;
+ * called only in detail mode (impl.hpp:1738, :1817) for the per-voxel point counts.  64-bit Subbotin coder
+ * (top = 1<<56, bottom = 1<<48, 8 flush bytes) over `unsigned int` symbols with a table that grows by doubling while
+ * the symbols are scanned; header = u64 table size, u8 bytes per entry, entries 1..size-1 at that width.  Restated from
+ * the published PCL source (status [M]: unverifiable offline like the rest of the PCL-inherited parts). */
+static void rc_encode_int_to(bbuf *os, const uint32_t *in, size_t n, uint64_t *coded_len) {
+  const uint64_t top = 1ull << 56, bottom = 1ull << 48, max_range = 1ull << 48;
+  size_t start = os->n;
+  uint64_t tsize = 1;                                   /* frequencyTableSize */
+  size_t cap = 4;
+  uint64_t *cf = (uint64_t *)calloc(cap, 8);
+  for (size_t i = 0; i < n; i++) {
+    uint64_t sym = in[i];
+    if (sym + 1 >= tsize) {                            /* "frequency table is to small -> adaptively extend it" */
+      uint64_t old = tsize;
+      do { tsize <<= 1; } while (sym + 1 > tsize);
+      if (cap < tsize + 1) { size_t nc = (size_t)tsize + 1; cf = (uint64_t *)realloc(cf, nc * 8); memset(cf + cap, 0, (nc - cap) * 8); cap = nc; }
+      memset(cf + old + 1, 0, (size_t)(tsize - old) * 8);
+    }
+    cf[sym + 1]++;
+  }
+  tsize++;
+  if (cap < tsize) { cf = (uint64_t *)realloc(cf, (size_t)tsize * 8); memset(cf + cap, 0, ((size_t)tsize - cap) * 8); cap = (size_t)tsize; }
+  for (uint64_t f = 1; f < tsize; f++) { cf[f] = cf[f - 1] + cf[f]; if (cf[f] <= cf[f - 1]) cf[f] = cf[f - 1] + 1; }
+  while (cf[tsize - 1] >= max_range)
+    for (uint64_t f = 1; f < tsize; f++) { cf[f] /= 2; if (cf[f] <= cf[f - 1]) cf[f] = cf[f - 1] + 1; }
+  uint8_t bsz = (uint8_t)ceil(log2((double)(cf[tsize - 1] + 1)) / 8.0);
+  bb_write(os, &tsize, 8); bb_write(os, &bsz, 1);
+  for (uint64_t f = 1; f < tsize; f++) bb_write(os, &cf[f], bsz);           /* little-endian host: the low bsz bytes */
+  uint64_t low = 0, range = ~0ull;
+  for (size_t i = 0; i < n; i++) {
+    uint32_t sym = in[i];
+    range /= cf[tsize - 1];
+    low += cf[sym] * range;
+    range *= cf[sym + 1] - cf[sym];
+    while ((low ^ (low + range)) < top || (range < bottom && ((range = (0ull - low) & (bottom - 1)), 1))) {
+      bb_push(os, (uint8_t)(low >> 56));
+      range <<= 8; low <<= 8;
+    }
+  }
+  for (int i = 0; i < 8; i++) { bb_push(os, (uint8_t)(low >> 56)); low <<= 8; }
+  free(cf);
+  if (coded_len) *coded_len = os->n - start;
+}
+int orc_range_encode_int(const uint32_t *in, size_t n, uint8_t **out, size_t *out_len) {
+  bbuf b = {0};
+  rc_encode_int_to(&b, in, n, NULL);
+  *out = b.p; *out_len = b.n; return 0;
+}
+int orc_range_decode_int(const uint8_t *in, size_t in_len, uint32_t *out, size_t n, size_t *consumed) {
+  const uint64_t top = 1ull << 56, bottom = 1ull << 48;
+  size_t pos = 0;
+  if (in_len < 9) return -1;
+  uint64_t tsize; memcpy(&tsize, in, 8); uint8_t bsz = in[8]; pos = 9;
+  if (tsize < 2 || tsize > (1ull << 28) || bsz == 0 || bsz > 8 || pos + (tsize - 1) * bsz + 8 > in_len) return -2;
+  uint64_t *cf = (uint64_t *)calloc((size_t)tsize + 1, 8);
+  for (uint64_t f = 1; f < tsize; f++) { memcpy(&cf[f], in + pos, bsz); pos += bsz; }
+  uint64_t code = 0, low = 0, range = ~0ull;
+  for (int i = 0; i < 8; i++) code = (code << 8) | in[pos++];
+  int rc = 0;
+  for (size_t i = 0; i < n; i++) {
+    range /= cf[tsize - 1];
+    if (range == 0) { rc = -3; break; }
+    uint64_t count = (code - low) / range;
+    size_t sym = 0, ss = (size_t)((tsize - 1) / 2);
+    while (ss > 0) { if (cf[sym + ss] <= count) sym += ss; ss /= 2; }
+    out[i] = (uint32_t)sym;
+    low += cf[sym] * range;
+    range *= cf[sym + 1] - cf[sym];
+    while ((low ^ (low + range)) < top || (range < bottom && ((range = (0ull - low) & (bottom - 1)), 1))) {
+      uint8_t ch = pos < in_len ? in[pos] : 0; pos++;
+      code = (code << 8) | ch; range <<= 8; low <<= 8;
+    }
+  }
+  free(cf);
+  if (consumed) *consumed = pos;
+  return rc ? rc : (pos <= in_len ? 0 : -4);
+}
+
 /* ------------------------------------------------------------------ snake (snake.h:46-71; closed form SURVEY App. B.7) */
 void orc_snake_positions_literal(int w, int h, int32_t *pos) {
   int w_pos = 0, h_pos = 0, mbw = 0, mbh = 0, to_right = 1;
@@ -680,7 +760,7 @@ int orc_encode(const orc_params *p, uint32_t frame_id, const void *pts, size_t n
   *out = NULL; *out_len = 0;
   if (info) memset(info, 0, sizeof *info);
   if (dbg) memset(dbg, 0, sizeof *dbg);
-  if (!p->do_voxel_grid) return -10;                             /* detail mode: SURVEY 8(f-4), not implemented */
+  const int detail = !p->do_voxel_grid;                          /* doVoxelGridDownDownSampling=false: the class default (codec.h:108-143) */
   if (n == 0) return 0;
   double t0 = now_ms();
   const uint8_t *base = (const uint8_t *)pts;
@@ -700,7 +780,9 @@ int orc_encode(const orc_params *p, uint32_t frame_id, const void *pts, size_t n
   int with_color = p->do_color != 0;                             /* PointXYZRGB always has an rgb field (impl.hpp:105-120) */
   int reduction = p->color_coding_type == 0 ? 8 - p->color_bit_resolution : 0;   /* jp_color_coder_ is never configured (App. C-3) */
   if (reduction < 0) reduction = 0;
-  bbuf tree = {0}, avg = {0}, cen = {0};
+  bbuf tree = {0}, avg = {0}, cen = {0}, pdiff = {0}, cdiff = {0};
+  uint32_t *counts = detail ? (uint32_t *)malloc((nf ? nf : 1) * 4) : NULL;   /* point_count_data_vector_ (impl.hpp:1528) */
+  const float pres_f = (float)p->point_resolution;              /* [PCL] PointCoding::setPrecision(float) */
   uint64_t *leaf_keys = (uint64_t *)malloc(nf * 8); size_t V = 0;
   uint8_t *outc = dbg ? (uint8_t *)calloc(nf ? nf : 1, 32) : NULL;   /* output_: one PointXYZRGB per leaf, DFS order (impl.hpp:1576) */
   uint32_t d = b.depth;
@@ -708,6 +790,38 @@ int orc_encode(const orc_params *p, uint32_t frame_id, const void *pts, size_t n
   for (size_t i = 0; i < nf;) {
     size_t j = i; while (j < nf && codes[j] == codes[i]) j++;
     leaf_keys[V++] = codes[i];
+    if (detail) {                                                /* impl.hpp:1525-1541 */
+      uint32_t k3d[3]; demorton3(codes[i], d, k3d);
+      double corner[3];
+      for (int a = 0; a < 3; a++) corner[a] = (double)k3d[a] * p->octree_resolution + b.min[a];
+      counts[V - 1] = (uint32_t)(j - i);
+      for (size_t k = i; k < j; k++) {                          /* [PCL] PointCoding::encodePoints: 3 bytes per point, index order */
+        float pf[3]; memcpy(pf, base + 32 * (size_t)idx[k], 12);
+        for (int a = 0; a < 3; a++) {
+          int q = (int)(((double)pf[a] - corner[a]) / pres_f);
+          if (q > 127) q = 127;
+          if (q < -127) q = -127;
+          bb_push(&pdiff, (uint8_t)q);
+        }
+      }
+      if (with_color) {                                          /* [PCL] ColorCoding::encodePoints (jp_color_coder_ inherits it unchanged) */
+        uint32_t s0 = 0, s1 = 0, s2 = 0, len = (uint32_t)(j - i);
+        for (size_t k = i; k < j; k++) { uint32_t c; memcpy(&c, base + 32 * (size_t)idx[k] + 16, 4); s0 += c & 0xFF; s1 += (c >> 8) & 0xFF; s2 += (c >> 16) & 0xFF; }
+        if (len > 1) {
+          s0 /= len; s1 /= len; s2 /= len;
+          for (size_t k = i; k < j; k++) {
+            uint32_t c; memcpy(&c, base + 32 * (size_t)idx[k] + 16, 4);
+            bb_push(&cdiff, (uint8_t)((uint8_t)((uint8_t)s0 ^ (uint8_t)(c & 0xFF)) >> reduction));
+            bb_push(&cdiff, (uint8_t)((uint8_t)((uint8_t)s1 ^ (uint8_t)((c >> 8) & 0xFF)) >> reduction));
+            bb_push(&cdiff, (uint8_t)((uint8_t)((uint8_t)s2 ^ (uint8_t)((c >> 16) & 0xFF)) >> reduction));
+          }
+        }
+        s0 >>= reduction; s1 >>= reduction; s2 >>= reduction;
+        bb_push(&avg, (uint8_t)s0); bb_push(&avg, (uint8_t)s1); bb_push(&avg, (uint8_t)s2);
+      }
+      i = j;
+      continue;                                                  /* no centroid, no output_ point in detail mode */
+    }
     if (with_color) {                                            /* [PCL] ColorCoding::encodeAverageOfPoints */
       uint32_t s0 = 0, s1 = 0, s2 = 0, len = (uint32_t)(j - i);
       for (size_t k = i; k < j; k++) { uint32_t c; memcpy(&c, base + 32 * (size_t)idx[k] + 16, 4); s0 += c & 0xFF; s1 += (c >> 8) & 0xFF; s2 += (c >> 16) & 0xFF; }
@@ -781,12 +895,19 @@ int orc_encode(const orc_params *p, uint32_t frame_id, const void *pts, size_t n
   double t5 = now_ms();
   /* header + entropy mux (impl.hpp:175-178, 1682-1760) */
   bbuf os = {0};
-  write_header(&os, p, frame_id, with_color, (uint64_t)V, &b);
+  write_header(&os, p, frame_id, with_color, detail ? (uint64_t)nf : (uint64_t)V, &b);   /* [PCL] writeFrameHeader: leaf_count_ or object_count_ */
   uint64_t coded[3] = { 0, 0, 0 };
   uint64_t sz = tree.n; bb_write(&os, &sz, 8);
   rc_encode_to(&os, tree.p, tree.n, &coded[0]);
   if (p->do_centroid) { uint32_t c32 = (uint32_t)cen.n; bb_write(&os, &c32, 4); rc_encode_to(&os, cen.p, cen.n, &coded[1]); }
   if (with_color) { sz = col.n; bb_write(&os, &sz, 8); rc_encode_to(&os, col.p, col.n, &coded[2]); }
+  if (detail) {                                                  /* impl.hpp:1728-1757 */
+    uint64_t c2;
+    sz = V; bb_write(&os, &sz, 8); rc_encode_int_to(&os, counts, V, &c2);
+    sz = pdiff.n; bb_write(&os, &sz, 8); rc_encode_to(&os, pdiff.p, pdiff.n, &c2);
+    if (with_color) { sz = cdiff.n; bb_write(&os, &sz, 8); rc_encode_to(&os, cdiff.p, cdiff.n, &c2); }
+  }
+  free(counts); free(pdiff.p); free(cdiff.p);
   double t6 = now_ms();
   if (info) {
     info->depth = d; memcpy(info->bb_min, b.min, 24); memcpy(info->bb_max, b.max, 24);
@@ -836,7 +957,7 @@ int orc_decode(const uint8_t *in, size_t len, void **pts_out, size_t *n_out, orc
   uint8_t do_centroid = in[pos++]; pos += 2;                     /* connectivity, scalable: carried, unused */
   uint32_t cct; memcpy(&cct, in + pos, 4); pos += 4;
   pos += 4 + 1;                                                  /* macroblock_size, do_icp_color_offset */
-  (void)i_frame; (void)vg; (void)pres; (void)frame_id;
+  (void)i_frame; (void)vg; (void)frame_id;
   /* [PCL] readFrameHeader -> defineBoundingBox -> getKeyBitSize (App. B.3) */
   uint32_t mk = 2;
   for (int a = 0; a < 3; a++) { uint32_t k = (uint32_t)ceil((bmax[a] - bmin[a] - EPSF) / res); if (k > mk) mk = k; }
@@ -866,7 +987,34 @@ int orc_decode(const uint8_t *in, size_t len, void **pts_out, size_t *n_out, orc
     rc = orc_range_decode(in + pos, len - pos, col, ncol, &used); if (rc) return rc;
     pos += used;
   }
-  if (pos != len) return -11;                                    /* trailing data = detail mode (impl.hpp:1802-1806): not implemented */
+  /* trailing data = the enhancement vectors: the reference switches to detail mode on peek() (impl.hpp:1802-1806) */
+  const int detail = pos != len;
+  uint32_t *counts = NULL; uint64_t ncounts = 0; uint8_t *pdiff = NULL; uint64_t npdiff = 0; uint8_t *cdiff = NULL; uint64_t ncdiff = 0;
+  if (detail) {                                                  /* impl.hpp:1808-1832 */
+    if (pos + 8 > len) return -12;
+    memcpy(&ncounts, in + pos, 8); pos += 8;
+    if (ncounts > (1ull << 30)) return -12;
+    counts = (uint32_t *)malloc((ncounts + 1) * 4);
+    rc = orc_range_decode_int(in + pos, len - pos, counts, ncounts, &used); if (rc) return rc;
+    pos += used;
+    if (pos + 8 > len) return -13;
+    memcpy(&npdiff, in + pos, 8); pos += 8;
+    if (npdiff > (1ull << 34)) return -13;
+    pdiff = (uint8_t *)malloc(npdiff + 1);
+    rc = orc_range_decode(in + pos, len - pos, pdiff, npdiff, &used); if (rc) return rc;
+    pos += used;
+    if (data_with_color) {
+      if (pos + 8 > len) return -14;
+      memcpy(&ncdiff, in + pos, 8); pos += 8;
+      if (ncdiff > (1ull << 34)) return -14;
+      cdiff = (uint8_t *)malloc(ncdiff + 1);
+      rc = orc_range_decode(in + pos, len - pos, cdiff, ncdiff, &used); if (rc) return rc;
+      pos += used;
+      /* The reference reads these diffs into color_coder_ (impl.hpp:1828) but decodes JPEG-type colours with
+       * jp_color_coder_, whose diff vector is empty: undefined behaviour.  Only type 0 is defined. */
+      if (cct != 0) return -15;
+    }
+  }
   double t1 = now_ms();
   /* initializeDecoding cjpeg.h:150-172 */
   uint8_t *avg = NULL; size_t navg = 0;
@@ -895,7 +1043,8 @@ int orc_decode(const uint8_t *in, size_t len, void **pts_out, size_t *n_out, orc
   double t2 = now_ms();
   /* deserializeTree (App. B.3): iterative DFS over the byte stream */
   uint8_t *outp = (uint8_t *)calloc(point_count ? point_count : 1, 32);
-  size_t np = 0, bp = 0;
+  size_t np = 0, bp = 0, nleaf = 0, pd = 0, cd = 0;
+  const float pres_f = (float)pres;                              /* [PCL] readFrameHeader: point_coder_.setPrecision (static_cast<float> (point_resolution)) */
   {
     uint8_t mask[32]; uint32_t level = 0; uint64_t code = 0;
     if (B > 0) {
@@ -907,6 +1056,36 @@ int orc_decode(const uint8_t *in, size_t len, void **pts_out, size_t *n_out, orc
         if (level + 1 < d) {
           if (bp >= B) { free(outp); return -7; }
           level++; code = child; mask[level] = tree[bp++];
+        } else if (detail) {                                     /* impl.hpp:1592-1613 + colour :1639-1651 */
+          if (nleaf >= ncounts) { free(outp); return -8; }
+          uint32_t cnt = counts[nleaf], k3[3]; demorton3(child, d, k3);
+          if (np + cnt > point_count || pd + 3ull * cnt > npdiff) { free(outp); return -8; }
+          uint8_t av[3] = { 0, 0, 0 };
+          if (data_with_color) {
+            if (3 * nleaf + 2 >= navg) { free(outp); return -9; }
+            for (int k = 0; k < 3; k++) av[k] = (uint8_t)(avg[3 * nleaf + k] << reduction);
+            if (cnt > 1 && cd + 3ull * cnt > ncdiff) { free(outp); return -9; }
+          }
+          for (uint32_t q = 0; q < cnt; q++) {
+            uint8_t *o = outp + 32 * np;
+            float xyz[3];
+            for (int a = 0; a < 3; a++) {                        /* [PCL] PointCoding::decodePoints */
+              double corner = (double)k3[a] * res + bmin[a];
+              xyz[a] = (float)(corner + pdiff[pd++] * pres_f);
+            }
+            memcpy(o, xyz, 12);
+            float one = 1.0f; memcpy(o + 12, &one, 4);
+            uint32_t rgba;
+            if (data_with_color) {                               /* [PCL] ColorCoding::decodePoints */
+              if (cnt > 1) {
+                uint8_t df[3]; for (int k = 0; k < 3; k++) df[k] = (uint8_t)(cdiff[cd++] << reduction);
+                rgba = (uint32_t)(av[0] ^ df[0]) | ((uint32_t)(av[1] ^ df[1]) << 8) | ((uint32_t)(av[2] ^ df[2]) << 16);
+              } else rgba = (uint32_t)av[0] | ((uint32_t)av[1] << 8) | ((uint32_t)av[2] << 16);
+            } else rgba = 0x00FFFFFFu;
+            memcpy(o + 16, &rgba, 4);
+            np++;
+          }
+          nleaf++;
         } else {
           if (np >= point_count) { free(outp); return -8; }
           uint32_t k3[3]; demorton3(child, d, k3);
@@ -937,7 +1116,7 @@ int orc_decode(const uint8_t *in, size_t len, void **pts_out, size_t *n_out, orc
     info->n_leaves = np; info->n_tree_bytes = B; info->n_color_bytes = ncol;
     info->t_ms[0] = t1 - t0; info->t_ms[1] = t2 - t1; info->t_ms[2] = t3 - t2; info->t_ms[7] = t3 - t0;
   }
-  free(tree); free(cen); free(col); free(avg);
+  free(tree); free(cen); free(col); free(avg); free(counts); free(pdiff); free(cdiff);
   *pts_out = outp; *n_out = np;
   return 0;
 }

@@ -37,7 +37,7 @@ extern "C" {
 typedef struct orc_params {
   double point_resolution;      /* pointResolution_arg  */
   double octree_resolution;     /* octreeResolution_arg */
-  int do_voxel_grid;            /* doVoxelGridDownDownSampling_arg (only 1 is implemented) */
+  int do_voxel_grid;            /* doVoxelGridDownDownSampling_arg; 0 = detail mode (per-point residuals, impl.hpp:1525-1541, 1728-1757) */
   int do_color;                 /* doColorEncoding_arg */
   int color_bit_resolution;     /* colorBitResolution_arg */
   int color_coding_type;        /* 0 = PCL avg (bit-reduced), 1 = SNAKE jpeg, 2 = LINES jpeg, 3 = GRID (raw) */
@@ -89,6 +89,9 @@ void orc_free_debug(orc_debug *d);
 int orc_range_encode(const uint8_t *in, size_t n, uint8_t **out, size_t *out_len);
 /* decodeStreamToCharVector: consumes exactly *consumed bytes of in */
 int orc_range_decode(const uint8_t *in, size_t in_len, uint8_t *out, size_t n, size_t *consumed);
+/* PCL StaticRangeCoder::encodeIntVectorToStream / decodeStreamToIntVector (64-bit coder; detail-mode point counts) */
+int orc_range_encode_int(const uint32_t *in, size_t n, uint8_t **out, size_t *out_len);
+int orc_range_decode_int(const uint8_t *in, size_t in_len, uint32_t *out, size_t n, size_t *consumed);
 /* libjpeg baseline encoder as jpeg_io drives it (jpeg_io.hpp:259-311); rgb interleaved 3 bytes/pixel */
 int orc_jpeg_encode(const uint8_t *rgb, int w, int h, int quality, uint8_t **out, size_t *out_len);
 /* libjpeg decoder defaults (jpeg_io.hpp:140-162): ISLOW + fancy upsampling */

@@ -70,6 +70,7 @@ CASES = {
     "lines_type2": (lambda: [synth.gen_surface(20000, 20), synth.gen_uniform(9000, 21)], dict(octree_bits=9, color_coding_type=2)),
     "lines_type2_edge_widths": (lambda: [synth.gen_surface(1500, 22), synth.gen_surface(2, 23), synth.gen_uniform(2049, 24), synth.gen_uniform(4097, 25), synth.gen_uniform(6143, 26)],
                                 dict(octree_bits=10, color_coding_type=2, jpeg_quality=60)),
+    "q0_cli_default": (lambda: [synth.gen_surface(30000, 27)], dict(octree_bits=9, jpeg_quality=0)),          # eval.hpp:161: the CLI default, libjpeg clamps to 1
     "duplicates_one_voxel": (lambda: [np.repeat(synth.gen_surface(7, 15), 3000)], dict(octree_bits=5)),
 }
 
@@ -90,6 +91,53 @@ def test_nonfinite_points_and_late_bbox_growth(K, oracle):
     lead_nan = synth.gen_surface(30000, 16)
     lead_nan["x"][:20000] = np.nan        # no finite point inside the prefix at all
     check_batch(K, oracle, [a, b, lead_nan], K.default_params(octree_bits=9))
+
+
+def _late_growth_cloud(seed):
+    b = synth.gen_surface(30000, seed)
+    b["x"][25000] = 3.5                    # beyond the exact 16k prefix: slow sequential path, two more growth steps
+    b["z"][28000] = -2.25
+    return b
+
+
+@pytest.mark.parametrize("res,seed", [(0.01, 2), (0.003, 1), (0.007, 0), (0.01, 3)])
+def test_non_power_of_two_resolution_follows_pcl_key_order(K, oracle, res, seed):
+    """octreeResolution that is not a power of two (the class default is 0.01, codec.h:108-143): PCL keys a point against
+    the box in force when it was added and re-roots on growth; recomputing from the final box gives a different key for
+    the first point of these clouds (checked below with the oracle), so only the sequential order is bit-exact."""
+    cl = _late_growth_cloud(seed)
+    bmin, _, _, keys, _ = oracle.bbox_keys(cl, res)
+    xyz = np.stack([cl["x"], cl["y"], cl["z"]], 1).astype(np.float64)
+    differs = int((((xyz - bmin) / res).astype(np.uint32) != keys).any(1).sum())
+    if seed != 3:
+        assert differs > 0                 # the case is a real discriminator
+    kp = K.default_params(octree_resolution=res, point_resolution=res)
+    check_batch(K, oracle, [cl, synth.gen_uniform(5000, seed + 40)], kp)
+    kp = K.default_params(octree_resolution=res, point_resolution=res, keep_centroid=1, color_coding_type=0, color_bits=6)
+    check_batch(K, oracle, [cl], kp)
+
+
+def test_junk_before_the_magic_and_ff_quirk(K, oracle):
+    """syncToHeader (impl.hpp:1660-1676) scans for the magic: leading junk is skipped, unless it holds a 0xFF byte
+    (`readChar == EOF` on a char), which aborts the sync."""
+    cl = synth.gen_surface(12000, 28)
+    kp = K.default_params(octree_bits=9)
+    c = K.Codec(kp)
+    s = c.encode_batch([cl])[0]
+    ref = oracle.decode(s)[0]
+    junk = bytes([1, 2, 3, ord("<"), ord("P"), 0, ord("<")]) * 5
+    out = np.zeros((ref.shape[0], 32), np.uint8)
+    a = np.frombuffer(junk + s, np.uint8)
+    n = c.decode_batch_raw([a.ctypes.data], [a.size], [out.ctypes.data], [out.shape[0]])
+    assert n == [ref.shape[0]] and np.array_equal(out, ref)
+    assert np.array_equal(oracle.decode(junk + s)[0], ref)
+    b = np.frombuffer(b"\x01\xff\x02" + s, np.uint8)
+    with pytest.raises(K.Ccv2Error) as ei:
+        c.decode_batch_raw([b.ctypes.data], [b.size], [out.ctypes.data], [out.shape[0]])
+    assert ei.value.status == -6
+    with pytest.raises(RuntimeError):
+        oracle.decode(b"\x01\xff\x02" + s)
+    c.close()
 
 
 def test_empty_and_all_nonfinite_frames_write_nothing_and_keep_frame_ids(K, oracle):
