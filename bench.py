@@ -3,15 +3,19 @@
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C ABI)
   python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithm (the oracle port, all host cores)
 
-A "step" is one pass of the hot path over one batch of F frames: ccv2_encode_batch over the F clouds followed by
-ccv2_decode_batch over the F streams it produced (--value-api roundtrip uses the pipelined ccv2_roundtrip_batch call
-instead; the end-to-end leg with host buffers uses the round trip by default, --e2e-api separate switches it).
-`value` is measured with the clouds already resident in HBM
-(device pointers in, device pointers out); `e2e` is the same work through the C ABI with pinned HOST buffers
-(ccv2_roundtrip_batch: encode -> decode per frame in one pipelined call, like evaluate_compression's per-frame
-loop), so the host->device copy of every cloud and the device->host copy of every stream and decoded cloud are
-inside the timed region.  For N > 1 the frames are sharded over the ranks (no data-path collective:
-intra frames are independent); timing is bracketed by barrier + synchronize and reduced with MAX.
+  python bench.py --mode decode ...                        BASELINE configs[4]: decode-only on oracle-produced streams
+
+A "step" is one pass of the hot path over one batch of F frames: every cloud is encoded and the stream just produced is
+decoded again, like evaluate_compression's per-frame loop (eval.hpp:818-843) -- one ccv2_submit_roundtrip call per step.
+Steps are submitted back to back (two calls in flight, ccv2_submit_* / ccv2_wait), so the next step's uploads and
+parallel kernels overlap the serial range-coder stages of the previous one; the timed region is bracketed by barrier +
+synchronize and holds exactly K complete steps.  --value-api separate runs ccv2_encode_batch then ccv2_decode_batch per
+step instead (synchronous; it also provides the encode / decode split that is always reported).
+`value` is measured with the clouds already resident in HBM (device pointers in, device pointers out); `e2e` is the same
+work through the C ABI with pinned HOST buffers, so the host->device copy of every cloud and the device->host copy of
+every stream and decoded cloud are inside the timed region (the stream itself stays on the device between encoder and
+decoder: 1.2 MB per frame that a file-based caller would upload again are not counted).  For N > 1 the frames are sharded
+over the ranks (no data-path collective: intra frames are independent); times are reduced with MAX.
 """
 import argparse
 import ctypes as C
@@ -145,12 +149,40 @@ def workload_config(args, frames):
             "cache": "inputs (%.0f MB per step per GPU) are larger than the 126 MB L2; no flush needed" % (frames * args.points * 32 / 1e6)}
 
 
+def pcie_ceiling(torch, dist, world, dev, nbytes=1 << 30, reps=3):
+    """What the box gives: pinned cudaMemcpyAsync H2D and D2H at the same time, on every rank at once (the ranks of a
+    node share host memory and PCIe root complexes).  Returns per-rank GB/s (min over ranks)."""
+    h_a = torch.empty(nbytes, dtype=torch.uint8).pin_memory(); h_b = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device=dev); d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    best = [0.0, 0.0]
+    for _ in range(reps + 1):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        with torch.cuda.stream(s1):
+            e[0].record(); d_a.copy_(h_a, non_blocking=True); e[1].record()
+        with torch.cuda.stream(s2):
+            e[2].record(); h_b.copy_(d_b, non_blocking=True); e[3].record()
+        torch.cuda.synchronize()
+        best = [max(best[0], nbytes / 1e6 / e[0].elapsed_time(e[1])), max(best[1], nbytes / 1e6 / e[2].elapsed_time(e[3]))]
+    if world > 1:
+        t = torch.tensor(best, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        best = [float(t[0]), float(t[1])]
+    del h_a, h_b, d_a, d_b
+    return {"h2d_gbs": best[0], "d2h_gbs": best[1], "how": "1 GiB pinned cudaMemcpyAsync each way at the same time, all %d ranks at once, best of %d, min over ranks" % (world, reps)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--mode", default="roundtrip", choices=["roundtrip", "decode"],
+                    help="roundtrip: the headline metric (encode+decode); decode: BASELINE configs[4], decode-only on oracle-produced streams resident in device memory")
     ap.add_argument("--frames", type=int, default=int(os.environ.get("BENCH_FRAMES", "0")),
                     help="frames per step per GPU (0: as many as fit in device memory, at most 1024 -- the serial entropy stage is latency bound, so throughput grows with the frames in flight)")
     ap.add_argument("--points", type=int, default=1000000)
@@ -158,10 +190,9 @@ def main():
     ap.add_argument("--kind", default="surf", choices=["surf", "unif"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--value-api", default="separate", choices=["roundtrip", "separate"],
-                    help="device-resident step through ccv2_roundtrip_batch (default) or ccv2_encode_batch + ccv2_decode_batch")
-    ap.add_argument("--e2e-api", default="roundtrip", choices=["roundtrip", "separate"],
-                    help="e2e through ccv2_roundtrip_batch (default) or ccv2_encode_batch + ccv2_decode_batch")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--value-api", default="roundtrip", choices=["roundtrip", "separate"],
+                    help="device-resident step through pipelined ccv2_submit_roundtrip calls (default) or synchronous ccv2_encode_batch + ccv2_decode_batch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -177,16 +208,18 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.mode == "decode":
+        return run_decode_mode(args, torch, dist, K, rank, world, local, dev)
     NP = args.points
     F = args.frames
-    if F <= 0:                                   # device-resident step: clouds in and out, streams (user side, 68 B/point) + the library's workspace (~82 B/point)
+    cap = 4 * NP + (1 << 16)
+    if F <= 0:       # the caller's side of a device-resident step: cloud in, cloud out, stream (32 + 32 + 4 B/point); the library's rings take what is left (~36 B/point per frame in flight)
         free_b, _total_b = torch.cuda.mem_get_info(local)
-        F = int(max(8, min(1024, (0.9 * free_b) // (150 * NP)))) // 8 * 8
+        F = int(max(8, min(1024, (0.55 * free_b) // (2 * NP * 32 + cap)))) // 8 * 8
     codec = K.Codec(K.default_params(octree_bits=args.bits), device=local)
     lib = K.load_library()
-    cap = 4 * NP + (1 << 16)
 
-    # ---- host memory budget: the e2e leg needs pinned input + stream + output buffers on every rank of the node
+    # ---- host memory budget: the e2e leg needs pinned input + two sets of stream / cloud buffers on every rank of the node
     F_e2e = 0
     if not args.no_e2e:
         try:
@@ -194,8 +227,8 @@ def main():
             avail = psutil.virtual_memory().available
         except Exception:
             avail = 64 << 30
-        per_frame = NP * 32 * 2 + cap
-        F_e2e = int(max(8, min(F, (0.45 * avail / world) // per_frame)))
+        per_frame = NP * 32 * 3 + 2 * cap
+        F_e2e = int(max(8, min(F, (0.6 * avail / world) // per_frame)))
     h_in = K.PinnedBuffer(F_e2e * NP * 32) if F_e2e else None
 
     # ---- synthetic frames, generated in chunks and moved straight to the device (and to the pinned e2e input buffer);
@@ -233,13 +266,25 @@ def main():
         ms, launches = codec.last_device_ms, codec.last_launch_count
         ns = codec.decode_batch_raw(str_ptrs, lens, out_ptrs, [NP] * F)
         split["enc"] += ms; split["dec"] += codec.last_device_ms
-        return ms + codec.last_device_ms, launches + codec.last_launch_count, lens, ns
+        return launches + codec.last_launch_count, lens, ns
 
-    def step_device():                           # the timed step: encode -> decode of every frame in one pipelined C-ABI call
+    def run_steps(k, submit):                    # k steps, at most two in flight; returns (launches, last lens, last counts)
+        launches, pend, res = 0, [], None
+        for _ in range(k):
+            pend.append(submit())
+            if len(pend) == 2:
+                res = pend.pop(0).wait(); launches += codec.last_launch_count
+        while pend:
+            res = pend.pop(0).wait(); launches += codec.last_launch_count
+        return launches, res[0], res[1]
+
+    def device_steps(k):
         if args.value_api == "separate":
-            return step_separate()
-        lens, ns = codec.roundtrip_batch_raw(in_ptrs, [NP] * F, str_ptrs, [cap] * F, out_ptrs, [NP] * F)
-        return codec.last_device_ms, codec.last_launch_count, lens, ns
+            launches = 0
+            for _ in range(k):
+                l, lens, ns = step_separate(); launches += l
+            return launches, lens, ns
+        return run_steps(k, lambda: codec.submit_roundtrip_raw(in_ptrs, [NP] * F, str_ptrs, [cap] * F, out_ptrs, [NP] * F))
 
     def barrier():
         torch.cuda.synchronize()
@@ -247,35 +292,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        _, _, lens, ns = step_device()
+    device_steps(args.warmup)
     sampler = ClockSampler(local)
     barrier()
-    split["enc"] = split["dec"] = 0.0
     sampler.start()
+    codec.timer_start()
     t0 = time.perf_counter()
-    dev_ms, launches = 0.0, 0
-    for _ in range(args.steps):
-        ms, l, lens, ns = step_device()
-        dev_ms += ms; launches += l
+    launches, lens, ns = device_steps(args.steps)
+    dev_ms = codec.timer_stop()                  # CUDA events on the library's control stream: first submit .. completion of the last call
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
-    # device time: CUDA events recorded by the library on its own streams around each call's GPU work (max over ranks)
     t_dev = reduce_max(dev_ms / 1e3, dist if world > 1 else None, dev)
     t_wall = reduce_max(wall, dist if world > 1 else None, dev)
     value = world * F * NP * args.steps / t_dev / 1e6
 
-    # ---- encode / decode split: from the timed steps, or from two untimed steps when the timed call was the round trip
-    split_steps = args.steps
-    if args.value_api != "separate":
-        split["enc"] = split["dec"] = 0.0
-        for _ in range(2):
-            step_separate()
-        split_steps = 2
-    split_final = dict(split)                    # frozen: the extra step below is not part of it
+    # ---- encode / decode split: two untimed synchronous steps through ccv2_encode_batch + ccv2_decode_batch
+    split["enc"] = split["dec"] = 0.0
+    split_steps = 2
+    for _ in range(split_steps):
+        step_separate()
+    split_final = dict(split)
     codec.frame_id = 0
-    _, _, lens, ns = step_device()               # streams with frame ids 1..F again, for the oracle check below
+    _, lens, ns = device_steps(1)                # streams with frame ids 1..F again, for the oracle check below
 
     # ---- bit-exactness spot check against the oracle (outside the timed region, rank 0, first frame) ----
     bit_exact = None
@@ -297,43 +336,44 @@ def main():
         codec.decode_batch_raw(str_ptrs[:1], l1, out_ptrs[:1], [NP])
         lat["decode"] = min(lat["decode"], codec.last_device_ms)
 
-    # ---- e2e: same calls with pinned host buffers ----
+    # ---- e2e: the same steps with pinned host buffers ----
     e2e = None
     if F_e2e:
-        # one pinned allocation per role, sliced per frame (many separate cudaMallocHost blocks copy ~30 % slower D2H here)
         FE = F_e2e
-        del d_in, d_str, d_out, in_ptrs, str_ptrs, out_ptrs      # the library stages host buffers in its own device pools: make room
+        del d_in, d_str, d_out, in_ptrs, str_ptrs, out_ptrs      # make room: the rings now also stage host inputs and outputs
         torch.cuda.empty_cache()
-        h_str, h_out = K.PinnedBuffer(FE * cap), K.PinnedBuffer(FE * NP * 32)
-        hi = [h_in.ptr + i * NP * 32 for i in range(FE)]; hs = [h_str.ptr + i * cap for i in range(FE)]; ho = [h_out.ptr + i * NP * 32 for i in range(FE)]
+        ceiling = pcie_ceiling(torch, dist, world, dev)
+        # one pinned allocation per role, sliced per frame; two sets of result buffers (consecutive steps are in flight together)
+        h_str = [K.PinnedBuffer(FE * cap) for _ in range(2)]; h_out = [K.PinnedBuffer(FE * NP * 32) for _ in range(2)]
+        hi = [h_in.ptr + i * NP * 32 for i in range(FE)]
+        hs = [[b.ptr + i * cap for i in range(FE)] for b in h_str]; ho = [[b.ptr + i * NP * 32 for i in range(FE)] for b in h_out]
+        flip = [0]
 
-        def step_host():
-            if args.e2e_api == "roundtrip":          # one pipelined call: encode -> decode per frame, streams and clouds back on the host
-                return codec.roundtrip_batch_raw(hi, [NP] * FE, hs, [cap] * FE, ho, [NP] * FE)
-            l2 = codec.encode_batch_raw(hi, [NP] * FE, hs, [cap] * FE)
-            n2 = codec.decode_batch_raw(hs, l2, ho, [NP] * FE)
-            return l2, n2
-        for _ in range(2):
-            step_host()
+        def submit_host():
+            k = flip[0]; flip[0] ^= 1
+            return codec.submit_roundtrip_raw(hi, [NP] * FE, hs[k], [cap] * FE, ho[k], [NP] * FE)
+        run_steps(2, submit_host)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            l2, n2 = step_host()
+        _, l2, n2 = run_steps(args.steps, submit_host)
         barrier()
         t_e2e = reduce_max(time.perf_counter() - t0, dist if world > 1 else None, dev)
+        h2d_b, d2h_b = int(FE * NP * 32), int(sum(l2) + 32 * FE * NP)
+        gbs = (h2d_b / 1e9 * args.steps / t_e2e, d2h_b / 1e9 * args.steps / t_e2e)
         e2e = {"value": world * FE * NP * args.steps / t_e2e / 1e6, "unit": "Mpoints/s", "frames_per_step_per_gpu": FE,
-               "h2d_bytes_per_step": int(FE * NP * 32), "d2h_bytes_per_step": int(sum(l2) + 32 * sum(n2)),
-               "api": "ccv2_roundtrip_batch" if args.e2e_api == "roundtrip" else "ccv2_encode_batch + ccv2_decode_batch",
-               "timing": "wall clock around the C-ABI calls (synchronous), pinned host buffers in and out, max over ranks"}
-        if args.e2e_api != "roundtrip":
-            e2e["h2d_bytes_per_step"] += int(sum(l2))
-        for b in (h_in, h_str, h_out):
+               "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+               "d2h_note": "decoded clouds come down as one capacity-sized transfer per frame (32 B x %d records, of which %.0f are voxels); streams by zero-copy stores at their exact size" % (NP, float(np.mean(n2))),
+               "api": "ccv2_submit_roundtrip / ccv2_wait, two calls in flight",
+               "timing": "wall clock around K pipelined C-ABI calls, pinned host buffers in and out, max over ranks; the stream stays on the device between encoder and decoder (its 1.2 MB/frame re-upload is not part of the step)",
+               "pcie_ceiling_gbs": ceiling, "achieved_h2d_gbs": gbs[0], "achieved_d2h_gbs": gbs[1],
+               "frac_of_pcie": max(gbs[0] / ceiling["h2d_gbs"], gbs[1] / ceiling["d2h_gbs"])}
+        for b in [h_in] + h_str + h_out:
             b.close()
 
     # ---- per-kernel profile (one extra, untimed, single-stream step over one group) -> roofline of the dominant kernel ----
     roofline = None
-    if rank == 0 and hasattr(lib, "ccv2_set_profiling"):
-        roofline = profile_roofline(K, lib, args, frames, alg_bytes_frame)
+    if rank == 0 and not args.no_profile:
+        roofline = profile_roofline(K, lib, args, frames, alg_bytes_frame, F, t_dev / args.steps)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -347,7 +387,7 @@ def main():
                 "vs_baseline": None, "dtype": "u8/u32/f64 (integer codec, FP64 keys)", "data": "synthetic",
                 "config": dict(workload_config(args, F), distinct_clouds_per_gpu=U), "bit_exact_vs_oracle": bit_exact, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "value_api": "ccv2_roundtrip_batch" if args.value_api == "roundtrip" else "ccv2_encode_batch + ccv2_decode_batch",
+                "value_api": "ccv2_submit_roundtrip x K (two calls in flight), ccv2_wait" if args.value_api == "roundtrip" else "ccv2_encode_batch + ccv2_decode_batch",
                 "encode_ms_per_step": split_final["enc"] / split_steps, "decode_ms_per_step": split_final["dec"] / split_steps,
                 "encode_only_mpoints_s": F * NP * split_steps / max(split_final["enc"], 1e-9) / 1e3, "decode_only_mpoints_s": F * NP * split_steps / max(split_final["dec"], 1e-9) / 1e3,
                 "single_frame_latency_ms": lat, "stream_bytes_per_frame": S, "voxels_per_frame": V}
@@ -357,7 +397,89 @@ def main():
     return 0
 
 
-def profile_roofline(K, lib, args, frames, alg_bytes_frame):
+def run_decode_mode(args, torch, dist, K, rank, world, local, dev):
+    """BASELINE configs[4]: decode-only throughput on streams the ORACLE produced (seeds 0..63 of the config-2 inputs,
+    sharded over the ranks), resident in device memory; decoded clouds stay in device memory."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    NP = args.points
+    U = max(1, 64 // world)
+    seeds = [rank * U + i for i in range(U)]
+    op = O.default_params(octree_bits=args.bits)
+
+    def make(s):
+        fr = gen_frames(args.kind, NP, [s])[0]
+        return O.encode(fr, op, frame_id=s + 1)[0]
+    with ThreadPoolExecutor(max_workers=min(U, os.cpu_count() or 1)) as ex:
+        streams = list(ex.map(make, seeds))
+    F = args.frames
+    if F <= 0:
+        free_b, _ = torch.cuda.mem_get_info(local)
+        F = int(max(8, min(2048, (0.4 * free_b) // (NP * 32 + max(len(s) for s in streams))))) // 8 * 8
+    vox = [int.from_bytes(s[55:63], "little") for s in streams]
+    d_str = [torch.from_numpy(np.frombuffer(streams[i % U], np.uint8).copy()).to(dev) for i in range(F)]
+    d_out = [torch.empty(NP * 32, dtype=torch.uint8, device=dev) for _ in range(F)]
+    sp = [t.data_ptr() for t in d_str]; sl = [len(streams[i % U]) for i in range(F)]; op_ = [t.data_ptr() for t in d_out]
+    codec = K.Codec(K.default_params(octree_bits=args.bits), device=local)
+
+    def run(k):
+        pend, res, launches = [], None, 0
+        for _ in range(k):
+            pend.append(codec.submit_decode_raw(sp, sl, op_, [NP] * F))
+            if len(pend) == 2:
+                res = pend.pop(0).wait(); launches += codec.last_launch_count
+        while pend:
+            res = pend.pop(0).wait(); launches += codec.last_launch_count
+        return res, launches
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    run(args.warmup)
+    sampler = ClockSampler(local)
+    barrier(); sampler.start(); codec.timer_start()
+    ns, launches = run(args.steps)
+    dev_ms = codec.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    t_dev = reduce_max(dev_ms / 1e3, dist if world > 1 else None, dev)
+    ok = None
+    if rank == 0:
+        rdec, _ = O.decode(streams[0])
+        ok = bool(ns[0] == rdec.shape[0] and np.array_equal(d_out[0][:ns[0] * 32].cpu().numpy().reshape(-1, 32), rdec))
+    lat = 1e30
+    for _ in range(3):
+        codec.decode_batch_raw(sp[:1], sl[:1], op_[:1], [NP]); lat = min(lat, codec.last_device_ms)
+    if rank == 0:
+        S, V = float(np.mean(sl)), float(np.mean([vox[i % U] for i in range(F)]))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg = S + 32 * V                                                          # SURVEY 8(d): decode reads the stream, writes 32-B points
+        line = {"metric": "Mpoints/s decode-only @ depth-11 intra, oracle-produced streams (BASELINE configs[4]); points = input points the streams represent",
+                "value": world * F * NP * args.steps / t_dev / 1e6, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8/u32/f64 (integer codec, FP64 positions)", "data": "synthetic",
+                "config": {"workload": "BASELINE.json configs[4]: decode-only, streams of %d-point G-%s frames (seeds %d..%d on this rank) encoded by the CPU oracle, octree_bits %d, JPEG snake Q85; streams and decoded clouds resident in device memory"
+                           % (NP, args.kind, seeds[0], seeds[-1], args.bits), "frames_per_step_per_gpu": F, "distinct_streams_per_gpu": U,
+                           "cache": "streams + decoded clouds (%.0f MB per step per GPU) exceed the 126 MB L2" % (F * (S + 32 * V) / 1e6)},
+                "decoded_bit_exact_vs_oracle": ok, "voxels_per_s_M": world * F * V * args.steps / t_dev / 1e6, "clocks": clocks, "gpu_launches": int(launches),
+                "single_frame_latency_ms": lat, "stream_bytes_per_frame": S, "voxels_per_frame": V,
+                "roofline": {"bound": "hbm", "achieved": alg * F / (t_dev / args.steps) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg * F / (t_dev / args.steps) / 1e9 / peak,
+                             "traffic": None, "note": "step level: algorithmic decode bytes (S + 32 V) x frames per step / step time"},
+                "api": "ccv2_submit_decode x K (two calls in flight), ccv2_wait"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def profile_roofline(K, lib, args, frames, alg_bytes_frame, frames_per_step, step_s):
     """Runs one encode+decode of one group on a single stream with CUDA events around every kernel (inside the
     library, on the launching stream) and reports the dominant kernel against the measured HBM peak."""
     peaks = {}
@@ -376,7 +498,7 @@ def profile_roofline(K, lib, args, frames, alg_bytes_frame):
     total_ms = sum(r[1] for r in prof)
     traffic = None
     try:                                                        # dram bytes per launch from the committed ncu --set full capture
-        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json" if os.path.exists(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")) else "ncu_traffic_r1.json")))
         traffic = int(t[name]) * frames_per_launch if name in t else None
     except Exception:
         pass
@@ -390,7 +512,10 @@ def profile_roofline(K, lib, args, frames, alg_bytes_frame):
         if n_ in own and ms_ > 0:
             gbs = own[n_] * fpl_ / (ms_ / k_ / 1e3) / 1e9
             hbm_kernels[n_] = {"own_algorithmic_bytes_per_frame": int(own[n_]), "avg_launch_ms": ms_ / k_, "achieved_GBs": gbs, "frac": gbs / peak}
+    step_gbs = alg_bytes_frame * frames_per_step / step_s / 1e9
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "frac_step": step_gbs / peak, "achieved_step": step_gbs,
+            "frac_note": "frac / achieved: the dominant kernel's own launch in the profiling step (frames_per_launch frames, one stream; a latency-bound serial kernel, so this only reflects how few frames one launch holds). frac_step / achieved_step: algorithmic bytes x frames per step / measured ms_per_step -- the whole pipeline against the HBM peak",
             "hbm_bound_kernels_vs_own_bytes": hbm_kernels,
             "peak_source": which, "avg_launch_ms": avg_s * 1e3, "frames_per_launch": frames_per_launch,
             "algorithmic_bytes_per_frame": alg_bytes_frame, "share_of_step": tot_ms / total_ms,

@@ -39,6 +39,13 @@ class FrameInfo(C.Structure):
                 ("bb_min", C.c_double * 3), ("bb_max", C.c_double * 3), ("coded", C.c_uint64 * 3)]
 
 
+class Quality(C.Structure):
+    """ccv2_quality == QualityMetric's computed fields (quality_metrics.h:53-75)."""
+    _fields_ = [("in_point_count", C.c_uint64), ("out_point_count", C.c_uint64), ("symm_rms", C.c_float), ("symm_hausdorff", C.c_float),
+                ("left_hausdorff", C.c_float), ("right_hausdorff", C.c_float), ("left_rms", C.c_float), ("right_rms", C.c_float),
+                ("psnr_db", C.c_double), ("psnr_yuv", C.c_double * 3)]
+
+
 _lib = None
 
 
@@ -61,6 +68,14 @@ def load_library():
     L.ccv2_encode_batch.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, szp]
     L.ccv2_decode_batch.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, szp]
     L.ccv2_roundtrip_batch.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, szp, vpp, szp, szp]
+    ip = C.POINTER(C.c_int)
+    L.ccv2_submit_encode.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, szp, ip]
+    L.ccv2_submit_decode.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, szp, ip]
+    L.ccv2_submit_roundtrip.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, szp, vpp, szp, szp, ip]
+    L.ccv2_wait.argtypes = [C.c_void_p, C.c_int]
+    L.ccv2_timer_start.argtypes = [C.c_void_p]
+    L.ccv2_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.ccv2_quality_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(Quality)]
     L.ccv2_peek_point_count.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
     L.ccv2_get_metrics.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.ccv2_set_frame_id.argtypes = [C.c_void_p, C.c_uint32]
@@ -90,7 +105,8 @@ EXPORTED_SYMBOLS = ["ccv2_default_params", "ccv2_create", "ccv2_destroy", "ccv2_
                     "ccv2_encode_batch", "ccv2_decode_batch", "ccv2_roundtrip_batch", "ccv2_peek_point_count", "ccv2_get_metrics",
                     "ccv2_set_frame_id", "ccv2_get_frame_id", "ccv2_last_launch_count", "ccv2_last_device_ms",
                     "ccv2_last_error", "ccv2_status_string", "ccv2_host_alloc", "ccv2_host_free", "ccv2_debug_fetch", "ccv2_get_output_cloud",
-                    "ccv2_set_profiling", "ccv2_get_profile"]
+                    "ccv2_set_profiling", "ccv2_get_profile", "ccv2_submit_encode", "ccv2_submit_decode", "ccv2_submit_roundtrip",
+                    "ccv2_wait", "ccv2_timer_start", "ccv2_timer_stop", "ccv2_quality_metrics"]
 
 
 def _status_string(s):
@@ -162,6 +178,17 @@ def _ptr_len(x):
     raise TypeError(type(x))
 
 
+class Pending:
+    """A submitted call (ccv2_submit_*): holds the ctypes arrays the library still reads and writes."""
+
+    def __init__(self, codec, ticket, keep, result):
+        self.codec, self.ticket, self._keep, self._result = codec, ticket, keep, result
+
+    def wait(self):
+        self.codec._check(self.codec._L.ccv2_wait(self.codec._h, self.ticket))
+        return self._result()
+
+
 class Codec:
     """Thin handle over ccv2_codec: batch encode/decode with host or device buffers."""
 
@@ -226,6 +253,58 @@ class Codec:
         rc = self._L.ccv2_roundtrip_batch(self._h, n, a_in, a_n, a_str, a_scap, a_slen, a_out, a_cap, a_np)
         self._check(rc)
         return list(a_slen), list(a_np)
+
+    # ---- asynchronous forms: submit returns a Pending (keeps the argument arrays alive); wait() returns what the synchronous call returns
+    def submit_roundtrip_raw(self, in_ptrs, npts, str_ptrs, str_caps, out_ptrs, out_caps):
+        n = len(in_ptrs)
+        a_in = (C.c_void_p * n)(*in_ptrs)
+        a_n = (C.c_size_t * n)(*npts)
+        a_str = (C.c_void_p * n)(*str_ptrs) if str_ptrs is not None else None
+        a_scap = (C.c_size_t * n)(*(str_caps if str_caps is not None else [0] * n))
+        a_slen = (C.c_size_t * n)()
+        a_out = (C.c_void_p * n)(*out_ptrs)
+        a_cap = (C.c_size_t * n)(*out_caps)
+        a_np = (C.c_size_t * n)()
+        t = C.c_int()
+        self._check(self._L.ccv2_submit_roundtrip(self._h, n, a_in, a_n, a_str, a_scap, a_slen, a_out, a_cap, a_np, C.byref(t)))
+        return Pending(self, t.value, (a_in, a_n, a_str, a_scap, a_out, a_cap), lambda: (list(a_slen), list(a_np)))
+
+    def submit_encode_raw(self, in_ptrs, npts, out_ptrs, out_caps):
+        n = len(in_ptrs)
+        a_in = (C.c_void_p * n)(*in_ptrs)
+        a_n = (C.c_size_t * n)(*npts)
+        a_out = (C.c_void_p * n)(*out_ptrs)
+        a_cap = (C.c_size_t * n)(*out_caps)
+        a_len = (C.c_size_t * n)()
+        t = C.c_int()
+        self._check(self._L.ccv2_submit_encode(self._h, n, a_in, a_n, a_out, a_cap, a_len, C.byref(t)))
+        return Pending(self, t.value, (a_in, a_n, a_out, a_cap), lambda: list(a_len))
+
+    def submit_decode_raw(self, in_ptrs, in_lens, out_ptrs, out_caps):
+        n = len(in_ptrs)
+        a_in = (C.c_void_p * n)(*in_ptrs)
+        a_n = (C.c_size_t * n)(*in_lens)
+        a_out = (C.c_void_p * n)(*out_ptrs)
+        a_cap = (C.c_size_t * n)(*out_caps)
+        a_len = (C.c_size_t * n)()
+        t = C.c_int()
+        self._check(self._L.ccv2_submit_decode(self._h, n, a_in, a_n, a_out, a_cap, a_len, C.byref(t)))
+        return Pending(self, t.value, (a_in, a_n, a_out, a_cap), lambda: list(a_len))
+
+    def quality_metrics(self, cloud_a, cloud_b):
+        """computeQualityMetric(original, decoded) -> Quality (quality_metrics_impl.hpp:82-239)."""
+        a, b = np.ascontiguousarray(cloud_a), np.ascontiguousarray(cloud_b)
+        q = Quality()
+        self._check(self._L.ccv2_quality_metrics(self._h, a.ctypes.data if a.size else None, a.nbytes // 32, b.ctypes.data if b.size else None, b.nbytes // 32, C.byref(q)))
+        return q
+
+    def timer_start(self):
+        self._check(self._L.ccv2_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(self._L.ccv2_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
 
     # ---- numpy convenience API
     def encode_batch(self, clouds):

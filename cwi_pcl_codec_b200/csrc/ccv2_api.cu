@@ -1,11 +1,22 @@
 // ccv2_api.cu -- C ABI (include/ccv2.h) and host-side orchestration of the CUDA pipelines.
 //
-// Execution model: a batch of frames is cut into groups; every group runs start-to-finish on one CUDA stream of
-// a small round-robin pool (H2D of the inputs, the parallel kernels with blockIdx.y = frame, the serial
-// range coder stage -- lane-per-stream or warp-per-stream kernels, see entropy_kernels.cuh / dec_lps_kernels.cuh --
-// assembly, D2H of the results).  Groups on different streams overlap; throughput is frames in flight divided by
-// the per-frame latency of the serial entropy stage.  No host synchronisation happens
-// inside a group: all sizes (depth, V, B, J, stream length) are device-side values in the frame records.
+// Execution model (round 2): a STREAMING pipeline over two rings of device workspaces.
+//   * A call's frames are cut into groups of G <= 32 frames.  Group q (a sequence number that runs across calls) takes
+//     front-end set q mod R_fe (sort buffers, leaf arrays, JPEG scratch, staging for host inputs: ~53-85 B/point, needed
+//     for a few milliseconds) and long-lived set q mod R_ll (tree bytes, colour payload, the stream, the decoder's
+//     workspace, staging for host outputs: ~36-68 B/point, needed for the 0.1-0.4 s the serial range-coder stages take).
+//     A set is handed on by CUDA events, so the host never waits inside a call: everything is enqueued up front, and the
+//     copy engines, the parallel front-end kernels and the latency-bound serial kernels of different groups overlap.
+//   * Host inputs travel on ONE copy stream in group order (cudaMemcpyAsync from pinned or pageable memory); finished
+//     streams leave through export_kernel (device memory, or zero-copy stores into pinned host memory); decoded clouds
+//     are written straight into device destinations, or into the set's staging area and from there by ONE copy-engine
+//     transfer per frame into pinned host memory.  Pageable host destinations get a per-call staging area and are
+//     copied when the call is collected.
+//   * ccv2_submit_* enqueue a call and return a ticket; ccv2_wait collects it.  Two calls may be in flight, sharing the
+//     rings: the next call's uploads and front-ends run while the previous call's serial stages drain, which is what
+//     hides the pipeline's fill and drain (0.3-0.5 s against 0.6 s of PCIe time per 1024-frame call).
+//   * No host synchronisation inside a group: all sizes (depth, V, B, J, stream length) are device-side values in the
+//     frame records; the records come back once per call.
 #include "../../include/ccv2.h"
 #include "common.cuh"
 #include "enc_kernels.cuh"
@@ -15,6 +26,7 @@
 #include "dec_lps_kernels.cuh"
 #include "lines_kernels.cuh"
 #include "lines_dec_kernels.cuh"
+#include "quality_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -28,20 +40,13 @@ namespace {
 
 thread_local std::string g_create_error;
 
-// The batch driver keeps up to 26 streams busy (8 or 16 group streams, 8 side streams, a control and a copy stream).  CUDA maps streams onto
-// CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue serialise behind each other's
-// long serial kernels (measured: 2x on the round trip).  Ask for more queues unless the user already chose -- this only
-// takes effect if it happens before the process creates its CUDA context, so hosts that initialise CUDA first
-// (e.g. import torch; torch.cuda.init()) should export the variable themselves (bench.py and tests/conftest.py do).
-struct EnvInit { EnvInit() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); } } g_env_init;
-
 struct DevBuf {
   void *p = nullptr; size_t cap = 0;
-  cudaError_t ensure(size_t bytes) {
+  cudaError_t ensure(size_t bytes, bool slack = true) {
     if (bytes <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    size_t want = bytes + std::min(bytes / 8, (size_t)64 << 20) + 4096;   // slack so slowly growing batches do not reallocate every call
+    size_t want = bytes + (slack ? std::min(bytes / 8, (size_t)64 << 20) : 0) + 4096;   // slack so slowly growing batches do not reallocate every call
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
@@ -61,7 +66,7 @@ struct HostBuf {
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-// bump allocator over a DevBuf: first pass (base == nullptr) only measures
+// bump allocator over a device region: first pass (base == nullptr) only measures
 struct Carver {
   uint8_t *base; size_t off = 0;
   explicit Carver(void *b) : base((uint8_t *)b) {}
@@ -71,45 +76,61 @@ struct Carver {
     off += count * sizeof(T);
     return r;
   }
+  size_t end() const { return (off + 255) & ~size_t(255); }
 };
 
 constexpr int MAX_STREAMS = 16;
-constexpr int SIDE_STREAMS = 8;          // group + side + control streams stay within the 32 hardware queues
+constexpr int SIDE_STREAMS = 8;          // group + side + copy + control streams stay within 32 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, see ccv2.h)
+constexpr int MAX_GROUP = 32;            // frames per group: the lane-per-stream encoder codes 32 frames per warp
+constexpr int N_CALLS = 3;               // call contexts: two user calls in flight + one for the retry of a frame that overflowed its workspace
+
+struct DoneRc { int ticket, rc; };
+enum PtrKind : char { PK_NONE = 0, PK_DEVICE = 1, PK_PINNED = 2, PK_PAGEABLE = 3 };
+
+// A ring of equally sized workspace sets (G frames each) that groups take in sequence; ev_free[set] is recorded when the
+// set's current user is done with it, and the next user's stream (and the copy stream, if it uploads into the set) waits on it.
+struct Ring {
+  DevBuf buf; size_t frame_bytes = 0; int G = 0, nsets = 0; uint64_t seq = 0; bool mem_limited = false;
+  std::vector<cudaEvent_t> ev_free; std::vector<char> used;
+  uint8_t *frame_base(int set, int i) const { return (uint8_t *)buf.p + ((size_t)set * G + i) * frame_bytes; }
+};
+
+struct CallCtx {
+  bool busy = false; int ticket = 0, mode = 0, nframes = 0, G = 1, ngroups = 0, rc_early = 0;
+  bool boost = false, timed = false;
+  DevBuf enc_frames, dec_frames, stage;                     // frame records (+ histograms); per-call staging for pageable destinations
+  HostBuf h_frames, h_dframes;
+  cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_setup = nullptr;
+  std::vector<cudaEvent_t> ev_h2d, ev_side, ev_done, ev_fin;
+  // per-frame bookkeeping of the call (the caller's arrays must stay alive until the call is collected)
+  std::vector<char> in_kind, out_kind, pts_kind;            // PtrKind of pts[i] / in[i], out[i], pts_out[i]
+  std::vector<size_t> stage_off_stream, stage_off_pts;      // offsets into `stage` (pageable destinations)
+  std::vector<int> fe_set, ll_set;                          // ring sets of every group
+  const void *const *pts = nullptr; const size_t *npts = nullptr; void *const *out = nullptr; const size_t *out_cap = nullptr; size_t *out_len = nullptr;
+  const void *const *in = nullptr; const size_t *in_len = nullptr; void *const *pts_out = nullptr; const size_t *pts_cap = nullptr; size_t *npts_out = nullptr;
+  uint64_t launches = 0; float device_ms = 0;
+  uint64_t fe_seq0 = 0, ll_seq0 = 0; int fe_nsets = 0, ll_nsets = 0;   // ring state the call started from (is a frame's workspace still intact afterwards?)
+  struct TraceMark { int group; const char *label; };
+  std::vector<cudaEvent_t> ev_trace; std::vector<TraceMark> trace_marks;
+};
 
 }  // namespace
-
-// Per-frame results published straight into pinned host memory by a kernel (zero-copy store over PCIe): the host learns
-// the sizes from an event right after the group's last kernel instead of waiting for a D2H copy that would queue behind
-// other groups' result copies in the copy engine.
-struct FrameResult { uint64_t out_len; uint32_t enc_error, dec_error, V, _pad; };
-__global__ void publish_kernel(const EncFrame *enc, const DecFrame *dec, FrameResult *res, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  FrameResult r; r.out_len = 0; r.enc_error = 0; r.dec_error = 0; r.V = 0; r._pad = 0;
-  if (enc) { r.out_len = enc[i].out_len; r.enc_error = enc[i].error; }
-  if (dec) { r.dec_error = dec[i].error; r.V = dec[i].V; }
-  res[i] = r;
-}
 
 struct ccv2_codec {
   ccv2_params prm;
   int device = 0;
   int n_sm = 148;
-  int trace = 0;                          // CCV2_TRACE=1: print per-group timeline (ms since batch start) to stderr
-  std::vector<cudaEvent_t> ev_trace;
-  struct TraceMark { int group; const char *label; };
-  std::vector<TraceMark> trace_marks;
+  int trace = 0;                          // CCV2_TRACE=1: print per-group timeline (ms since call start) to stderr
   int use_ring = 1;                       // pipeline the DFS walk behind the range decoder (CCV2_NO_RING=1 disables: debugging)
-  int n_streams = 0, group = 0;           // streams 0 = auto (8 for device-resident calls, 16 when host buffers are involved); group 0 = auto: spread the batch over all streams
-  cudaStream_t main_stream = nullptr;
-  cudaStream_t copy_stream = nullptr;     // all host->device input copies, in group order (see run_batch)
-  std::vector<cudaEvent_t> ev_h2d;
+  int n_streams = 0, group = 0;           // CCV2_STREAMS / CCV2_GROUP overrides (0 = automatic)
+  int inflight_max = 2048;                // frames the long-lived ring may hold (CCV2_INFLIGHT); memory permitting
+  int fe_frames = 128;                    // frames the front-end ring holds (CCV2_FE_FRAMES)
+  cudaStream_t main_stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr, fin_stream = nullptr;
   cudaStream_t streams[MAX_STREAMS] = {};
   cudaStream_t side_streams[SIDE_STREAMS] = {};   // colour layer of a group, concurrent with its tree layer (lane-per-stream decoder)
-  std::vector<cudaEvent_t> ev_side;
   int lps_dec = -1;                       // lane-per-stream range decoder: -1 auto (round trips only), 0 off, 1 on (CCV2_LPS_DEC)
-  cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_fork = nullptr;
-  std::vector<cudaEvent_t> ev_group;
+  cudaEvent_t ev_id_chain = nullptr; bool id_chain_used = false;     // frame ids are sequential: a group's setup waits for the previous group's
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;                      // ccv2_timer_*
   JpegTables *d_tables = nullptr;
   uint32_t *d_frame_counter = nullptr;
   size_t lps_smem_enc = 0;                // dynamic shared memory that keeps the lane-per-stream coder CTAs one to an SM
@@ -117,17 +138,15 @@ struct ccv2_codec {
   int serial_cap = 0;                     // serial CTAs per SM; 0: ceil(frames in the call / SMs)  (CCV2_CAP overrides, -1 disables the cap)
   size_t smem_sm = 0, smem_static_enc = 0, smem_static_dec = 0;   // shared memory per SM; static use of the two serial kernels
   uint32_t frame_id = 0;
-  // encode workspaces
-  DevBuf work;                             // encode slots / decode workspaces (one arena: see run_batch)
-  int work_mode = -1;                      // mode of the call that last wrote the arena
+  Ring fe, ll;
+  CallCtx calls[N_CALLS];
+  int next_ticket = 1, user_calls = 0;
+  std::vector<DoneRc> done;              // results of collected calls, by ticket (ccv2_wait after the fact)
+  int last_mode = -1;                      // mode of the call collected last
   EncParams last_enc_params;               // of the last encode (ccv2_get_output_cloud)
   DevBuf out_cloud;                        // staging for ccv2_get_output_cloud into host memory
-  DevBuf enc_frames, enc_persist, enc_input;
-  HostBuf h_frames;
-  std::vector<EncFrame> enc_host;        // host mirror of the last batch's frame records (with device pointers)
-  // decode workspaces
-  DevBuf dec_frames, dec_input, dec_output;
-  HostBuf h_dframes, h_results;
+  std::vector<EncFrame> enc_host;          // host mirror of the last encode call's frame records (with device pointers)
+  std::vector<char> enc_host_valid;        // per frame: its ring sets were not handed on to a later group
   uint64_t metrics[3] = {0, 0, 0};
   uint64_t launches = 0;
   float device_ms = 0.f;
@@ -170,12 +189,16 @@ void prof_collect(ccv2_codec *c) {
 #define LAUNCH_S(stream, name, ...) do { prof_begin(c, stream, name); __VA_ARGS__; prof_end(c, stream); launches++; } while (0)
 #define LAUNCH(name, ...) LAUNCH_S(st, name, __VA_ARGS__)
 
-bool is_device_ptr(const void *p) {
+PtrKind ptr_kind(const void *p) {
+  if (!p) return PK_NONE;
   cudaPointerAttributes a;
   cudaError_t e = cudaPointerGetAttributes(&a, p);
-  if (e != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+  if (e != cudaSuccess) { cudaGetLastError(); return PK_PAGEABLE; }
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return PK_DEVICE;
+  if (a.type == cudaMemoryTypeHost) return PK_PINNED;
+  return PK_PAGEABLE;
 }
+bool is_device_ptr(const void *p) { return ptr_kind(p) == PK_DEVICE; }
 
 // ---- JPEG tables on the host (libjpeg std tables)
 const uint8_t ZZ_H[64] = { 0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14,
@@ -243,34 +266,36 @@ void build_jpeg_tables(int quality, JpegTables &T) {
   memcpy(T.header, h.data(), JPEG_HDR_BYTES);
 }
 
-// ---- capacity rules (bytes) for a frame of n points
-size_t tree_cap_for(size_t n) { return ((8 * n + 1024) + 255) & ~size_t(255); }
-size_t cpay_cap_for(size_t n) { return ((4 * n + 8192) + 255) & ~size_t(255); }
+// ---- capacity rules (bytes) for a frame of n points.  The defaults hold every cloud the benchmarks and tests produce
+// (uniform random 1M points at 11 bits: 3.6 tree bytes per point); a frame that overflows one (sparse deep octrees reach
+// depth * n tree bytes) is flagged on the device and encoded again, alone, with the `boost` bounds, which cannot overflow.
+size_t tree_cap_for(size_t n, bool boost) {
+  const size_t full = 22 * n + 1024;                                    // B <= depth * V, depth <= 21
+  const size_t v = boost ? full : std::max(4 * n, std::min(full, (size_t)1 << 20)) + 1024;
+  return (v + 255) & ~size_t(255);
+}
+size_t cpay_cap_for(size_t n, bool boost) { return ((boost ? 8 * n + 65536 : 3 * n + n / 4 + 8192) + 255) & ~size_t(255); }   // raw colour types need 3 n
 size_t cen_cap_for(size_t n) { return ((3 * n + 256) + 255) & ~size_t(255); }
 size_t rc_cap_for(size_t raw_cap) { return ((raw_cap + raw_cap / 8 + 4096) + 255) & ~size_t(255); }
-size_t stream_cap_for(size_t n, bool cen) {
-  return FRAME_HDR_BYTES + 8 + rc_cap_for(tree_cap_for(n)) + (cen ? 4 + rc_cap_for(cen_cap_for(n)) : 0) + 8 + rc_cap_for(cpay_cap_for(n));
+size_t stream_cap_for(size_t n, bool cen, bool boost) {
+  return FRAME_HDR_BYTES + 8 + rc_cap_for(tree_cap_for(n, boost)) + (cen ? 4 + rc_cap_for(cen_cap_for(n)) : 0) + 8 + rc_cap_for(cpay_cap_for(n, boost));
 }
 
-struct EncSlotLayout { size_t bytes; size_t zero_off, zero_bytes; };
-
-// carve the per-frame group-slot workspace; returns total bytes (measure when base == nullptr)
-size_t carve_enc_slot(uint8_t *base, size_t n, EncFrame *f, const ccv2_params &prm, size_t *zero_off, size_t *zero_bytes) {
+// front-end workspace of one frame (ring `fe`): dead once the colour payload is complete
+size_t carve_fe(uint8_t *base, size_t n, EncFrame *f, const ccv2_params &prm, bool boost, bool host_in, size_t *zero_off, size_t *zero_bytes) {
   Carver cv(base);
   const uint32_t tiles = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE) + 1;
   const uint32_t scan_tiles = (uint32_t)(n / 1024) + 8;
   const size_t img_h = n / 256 + 1, mcu_h = (img_h + 15) / 16;
   const bool lines = prm.color_coding_type == 2;
   const size_t lines_cap = n / LINE_PX + 2;
-  const size_t jbits_words = lines ? lines_cap * LINE_BITS_WORDS : (((4 * n + 8192) / 4 + 63) & ~size_t(63));
+  const size_t jbits_words = lines ? lines_cap * LINE_BITS_WORDS : ((cpay_cap_for(n, boost) / 4 + 63) & ~size_t(63));
   // --- zero-initialised region first
-  cv.off = 0;
   uint32_t *ghist = cv.take<uint32_t>(8 * 256);
-  size_t z0 = 0;
   uint32_t *sort_status = cv.take<uint32_t>((size_t)8 * tiles * 256);
   uint64_t *scan_status = cv.take<uint64_t>((size_t)3 * scan_tiles);
   uint32_t *jbits = cv.take<uint32_t>(jbits_words + 16);
-  size_t z1 = (cv.off + 255) & ~size_t(255);
+  const size_t z1 = cv.end();
   // --- rest
   uint64_t *k0 = cv.take<uint64_t>(n + 8), *k1 = cv.take<uint64_t>(n + 8);
   uint32_t *v0 = cv.take<uint32_t>(n + 8), *v1 = cv.take<uint32_t>(n + 8);
@@ -281,6 +306,7 @@ size_t carve_enc_slot(uint8_t *base, size_t n, EncFrame *f, const ccv2_params &p
   int16_t *coef = cv.take<int16_t>((lines ? (n / 16 + 260) : mcu_h * 16) * 384 + 64);
   uint8_t *line_slots = cv.take<uint8_t>(lines ? lines_cap * LINE_SLOT_BYTES : 16);
   uint32_t *line_len = cv.take<uint32_t>(lines ? lines_cap : 4), *line_off = cv.take<uint32_t>(lines ? lines_cap : 4);
+  uint8_t *pts_stage = cv.take<uint8_t>(host_in ? 32 * n + 32 : 16);
   if (f) {
     f->ghist = ghist; f->sort_status = sort_status; f->tiles_max = tiles; f->scan_status = scan_status; f->scan_tiles_max = scan_tiles;
     f->jbits_buf = jbits; f->jbits_cap_words = (uint32_t)jbits_words;
@@ -288,25 +314,70 @@ size_t carve_enc_slot(uint8_t *base, size_t n, EncFrame *f, const ccv2_params &p
     f->leaf_key = leaf_key; f->leaf_start = leaf_start; f->leaf_off = leaf_off; f->first_new = first_new;
     f->avg = avg; f->coef = coef;
     f->line_slots = line_slots; f->line_len = line_len; f->line_off = line_off; f->lines_cap = lines ? (uint32_t)lines_cap : 0;
+    if (host_in) f->pts = pts_stage;
   }
-  if (zero_off) *zero_off = z0;
-  if (zero_bytes) *zero_bytes = z1 - z0;
-  return (cv.off + 255) & ~size_t(255);
+  if (zero_off) *zero_off = 0;
+  if (zero_bytes) *zero_bytes = z1;
+  return cv.end();
 }
-size_t carve_enc_persist(uint8_t *base, size_t n, EncFrame *f, bool cen) {
+// long-lived encoder buffers of one frame (ring `ll`): the stream first (a round trip's decoder reads it while its own
+// workspace lies over the rest, which is dead once the stream is assembled); *stream_end = offset where the rest starts
+size_t carve_enc_ll(uint8_t *base, size_t n, EncFrame *f, bool cen, bool boost, size_t *stream_end) {
   Carver cv(base);
-  uint8_t *tree = cv.take<uint8_t>(tree_cap_for(n));
+  uint8_t *stream = cv.take<uint8_t>(stream_cap_for(n, cen, boost));
+  if (stream_end) *stream_end = cv.end();
+  uint8_t *tree = cv.take<uint8_t>(tree_cap_for(n, boost));
   uint8_t *cenb = cv.take<uint8_t>(cen ? cen_cap_for(n) : 256);
-  uint8_t *cpay = cv.take<uint8_t>(cpay_cap_for(n));
+  uint8_t *cpay = cv.take<uint8_t>(cpay_cap_for(n, boost));
   uint8_t *rc0 = cv.take<uint8_t>(cen ? rc_cap_for(cen_cap_for(n)) : 256);
-  uint8_t *rc1 = cv.take<uint8_t>(rc_cap_for(cpay_cap_for(n)));
-  uint8_t *stream = cv.take<uint8_t>(stream_cap_for(n, cen));
+  uint8_t *rc1 = cv.take<uint8_t>(rc_cap_for(cpay_cap_for(n, boost)));
   if (f) {
-    f->tree = tree; f->tree_cap = (uint32_t)tree_cap_for(n) - 64; f->cen = cenb; f->cpay = cpay; f->cpay_cap = (uint32_t)cpay_cap_for(n) - 64;
-    f->rc_tmp[0] = rc0; f->rc_tmp[1] = rc1; f->rc_tmp_cap[0] = (uint32_t)(cen ? rc_cap_for(cen_cap_for(n)) : 0); f->rc_tmp_cap[1] = (uint32_t)rc_cap_for(cpay_cap_for(n));
-    f->stream = stream; f->stream_cap = stream_cap_for(n, cen);
+    f->tree = tree; f->tree_cap = (uint32_t)tree_cap_for(n, boost) - 64; f->cen = cenb; f->cpay = cpay; f->cpay_cap = (uint32_t)cpay_cap_for(n, boost) - 64;
+    f->rc_tmp[0] = rc0; f->rc_tmp[1] = rc1; f->rc_tmp_cap[0] = (uint32_t)(cen ? rc_cap_for(cen_cap_for(n)) : 0); f->rc_tmp_cap[1] = (uint32_t)rc_cap_for(cpay_cap_for(n, boost));
+    f->stream = stream; f->stream_cap = stream_cap_for(n, cen, boost);
   }
-  return (cv.off + 255) & ~size_t(255);
+  return cv.end();
+}
+// decoder workspace of one frame: ncap = voxels it may hold, tcap / ccap = tree / colour payload bytes
+size_t carve_dec(uint8_t *base, size_t ncap, size_t tcap, size_t ccap, DecFrame *f, size_t *zero_bytes, bool lines) {
+  Carver cv(base);
+  const size_t lines_cap = lines ? ncap / LINE_PX + 2 : 0;
+  const size_t img_h = ncap / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = lines ? (lines_cap * LINE_MCU_STRIDE + LINE_MCU_STRIDE) * 6 : mcu_h * 16 * 6;
+  const uint32_t scan_tiles = (uint32_t)(ncap / NODE_THREADS) + 8;
+  uint64_t *scan_status = cv.take<uint64_t>(2 * (size_t)scan_tiles);
+  int16_t *coef = cv.take<int16_t>(nblocks * 64 + 64);
+  const size_t z1 = cv.end();
+  uint8_t *tree = cv.take<uint8_t>(tcap + 64);
+  uint8_t *cen = cv.take<uint8_t>(cen_cap_for(ncap));
+  uint8_t *col = cv.take<uint8_t>(ccap + 64);
+  // The pipelined walker records level depth-2 branches (l2_*), the fallback walkers bottom-level branches (node_*): a
+  // frame uses one or the other, so they share their memory.
+  const size_t rec_off = cv.end();
+  uint64_t *l2_prefix = cv.take<uint64_t>(ncap + 8);
+  uint8_t *l2_mask = cv.take<uint8_t>(ncap + 8);
+  uint32_t *l2_off = cv.take<uint32_t>(ncap + 8);
+  const size_t rec_end = cv.end();
+  cv.off = rec_off;
+  uint64_t *node_prefix = cv.take<uint64_t>(ncap + 8);
+  uint8_t *node_byte = cv.take<uint8_t>(ncap + 8);
+  cv.off = std::max(rec_end, cv.end());
+  uint8_t *planes = cv.take<uint8_t>(mcu_h * 16 * 256 * 3 / 2 + 256);
+  uint16_t *qt = cv.take<uint16_t>(128);
+  uint8_t *scan = cv.take<uint8_t>(ccap + 64);
+  uint32_t *line_off = cv.take<uint32_t>(lines_cap + 4), *line_len = cv.take<uint32_t>(lines_cap + 4), *line_w = cv.take<uint32_t>(lines_cap + 4);
+  uint16_t *line_qt = cv.take<uint16_t>(lines_cap * 128 + 128);
+  uint8_t *line_planes = cv.take<uint8_t>(lines_cap * 8192 + 256);
+  if (f) {
+    f->scan_status = scan_status; f->scan_tiles_max = scan_tiles; f->coef = coef; f->coef_cap_blocks = (uint32_t)nblocks;
+    f->tree = tree; f->tree_cap = (uint32_t)std::min(tcap, (size_t)0xFFFFFF00u); f->cen = cen; f->cen_cap = (uint32_t)cen_cap_for(ncap) - 64;
+    f->col = col; f->col_cap = (uint32_t)std::min(ccap, (size_t)0xFFFFFF00u);
+    f->node_prefix = node_prefix; f->node_byte = node_byte; f->node_cap = (uint32_t)ncap;
+    f->l2_prefix = l2_prefix; f->l2_mask = l2_mask; f->l2_off = l2_off;
+    f->planes = planes; f->planes_cap = (uint32_t)(mcu_h * 16 * 256 * 3 / 2); f->qt = qt; f->scan = scan;
+    f->lines_cap = (uint32_t)lines_cap; f->line_off = line_off; f->line_len = line_len; f->line_w = line_w; f->line_qt = line_qt; f->line_planes = line_planes;
+  }
+  if (zero_bytes) *zero_bytes = z1;
+  return cv.end();
 }
 
 int check_params(const ccv2_params *p, std::string &err) {
@@ -319,7 +390,54 @@ int check_params(const ccv2_params *p, std::string &err) {
   return CCV2_OK;
 }
 
+// syncToHeader + the fields a decoder needs to size its workspace, on a HOST copy of the first bytes of a stream
+// (impl.hpp:1660-1676).  Returns false when no header lies inside the window.
+struct PeekInfo { uint64_t point_count, B; uint8_t voxel_grid, with_color, centroid; uint32_t cct; };
+bool peek_header(const uint8_t *b, size_t len, PeekInfo &o) {
+  static const char id2[] = "<PCL-OCT-CODECV2-COMPRESSED>", id1[] = "<PCL-OCT-COMPRESSED>";
+  size_t pos = 0; unsigned hp = 0;
+  while (hp < 28) {
+    if (pos >= len) return false;
+    const uint8_t ch = b[pos++];
+    if (ch == 0xFF) return false;                           // (char)0xFF == EOF quirk, SURVEY App. C-9
+    if (ch != (uint8_t)id2[hp++]) hp = ((uint8_t)id2[0] == ch) ? 1 : 0;
+  }
+  hp = 0;
+  while (hp < 20) {
+    if (pos >= len) return false;
+    const uint8_t ch = b[pos++];
+    if (ch != (uint8_t)id1[hp++]) hp = ((uint8_t)id1[0] == ch) ? 1 : 0;
+  }
+  if (pos + 92 + 8 > len) return false;
+  const uint8_t *h = b + pos;
+  o.voxel_grid = h[5]; o.with_color = h[6];
+  memcpy(&o.point_count, h + 7, 8);
+  o.centroid = h[80];
+  memcpy(&o.cct, h + 83, 4);
+  memcpy(&o.B, h + 92, 8);
+  return true;
+}
+
 }  // namespace
+
+// ================================================================================================ handle life cycle
+static void drain(ccv2_codec *c) {                           // waits for everything the codec has enqueued
+  cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->d2h_stream);
+  for (int i = 0; i < MAX_STREAMS; i++) cudaStreamSynchronize(c->streams[i]);
+  for (int i = 0; i < SIDE_STREAMS; i++) cudaStreamSynchronize(c->side_streams[i]);
+  cudaStreamSynchronize(c->main_stream); cudaStreamSynchronize(c->fin_stream);
+}
+static int finish_call(ccv2_codec *c, CallCtx &x);
+static int finish_all(ccv2_codec *c) {                       // collects calls still in flight, oldest first
+  int rc = CCV2_OK;
+  for (;;) {
+    CallCtx *oldest = nullptr;
+    for (auto &x : c->calls) if (x.busy && (!oldest || x.ticket < oldest->ticket)) oldest = &x;
+    if (!oldest) return rc;
+    const int r = finish_call(c, *oldest);
+    if (rc == CCV2_OK) rc = r;
+  }
+}
 
 extern "C" {
 
@@ -367,26 +485,26 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   if (const char *s = getenv("CCV2_LPS_DEC")) c->lps_dec = atoi(s);
   if (const char *s = getenv("CCV2_NO_RING")) c->use_ring = atoi(s) ? 0 : 1;
   if (const char *s = getenv("CCV2_STREAMS")) c->n_streams = std::max(0, std::min(MAX_STREAMS, atoi(s)));
-  if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(1024, atoi(s)));
+  if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(MAX_GROUP, atoi(s)));
+  if (const char *s = getenv("CCV2_INFLIGHT")) c->inflight_max = std::max(1, atoi(s));
+  if (const char *s = getenv("CCV2_FE_FRAMES")) c->fe_frames = std::max(1, atoi(s));
   auto fail = [&](cudaError_t ee, const char *what) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ee); ccv2_destroy(c); return CCV2_ERR_CUDA; };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
   if ((e = cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail(e, "cudaDeviceGetAttribute");
-  if ((e = cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
-  if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
-  {
-    // optional (CCV2_PRIORITY=1): earlier groups get higher stream priority.  Measured neutral on B200 (the long serial
-    // kernels are resident anyway), so it is off by default.
-    int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);      // lo = least urgent (numerically largest)
-    const bool prio = getenv("CCV2_PRIORITY") && atoi(getenv("CCV2_PRIORITY")) != 0;
-    for (int i = 0; i < MAX_STREAMS; i++) {
-      int p = prio ? std::min(lo, hi + i * (lo - hi + 1) / MAX_STREAMS) : lo;
-      if ((e = cudaStreamCreateWithPriority(&c->streams[i], cudaStreamNonBlocking, p)) != cudaSuccess) return fail(e, "cudaStreamCreate");
-      if (i < SIDE_STREAMS && (e = cudaStreamCreateWithPriority(&c->side_streams[i], cudaStreamNonBlocking, lo)) != cudaSuccess) return fail(e, "cudaStreamCreate");
-    }
+  for (cudaStream_t *s : { &c->main_stream, &c->copy_stream, &c->d2h_stream, &c->fin_stream })
+    if ((e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+  for (int i = 0; i < MAX_STREAMS; i++) {
+    if ((e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if (i < SIDE_STREAMS && (e = cudaStreamCreateWithFlags(&c->side_streams[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
   }
-  if ((e = cudaEventCreate(&c->ev_start)) != cudaSuccess) return fail(e, "cudaEventCreate");
-  if ((e = cudaEventCreate(&c->ev_end)) != cudaSuccess) return fail(e, "cudaEventCreate");
-  if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  for (auto &x : c->calls) {
+    if ((e = cudaEventCreate(&x.ev_start)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&x.ev_end)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&x.ev_setup, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  }
+  if ((e = cudaEventCreateWithFlags(&c->ev_id_chain, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&c->ev_t0)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&c->ev_t1)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if ((e = cudaFuncSetAttribute(sort_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_BYTES)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
   JpegTables T; build_jpeg_tables(p->jpeg_quality, T);
   if ((e = cudaMalloc(&c->d_tables, sizeof T)) != cudaSuccess) return fail(e, "cudaMalloc");
@@ -423,27 +541,24 @@ void ccv2_destroy(ccv2_codec *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (auto ev : c->ev_group) cudaEventDestroy(ev);
+  for (auto &x : c->calls) {
+    for (auto *v : { &x.ev_h2d, &x.ev_side, &x.ev_done, &x.ev_fin, &x.ev_trace }) for (auto ev : *v) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : { x.ev_start, x.ev_end, x.ev_setup }) if (ev) cudaEventDestroy(ev);
+    x.enc_frames.release(); x.dec_frames.release(); x.stage.release(); x.h_frames.release(); x.h_dframes.release();
+  }
+  for (Ring *r : { &c->fe, &c->ll }) { for (auto ev : r->ev_free) cudaEventDestroy(ev); r->buf.release(); }
   for (auto ev : c->prof_pool) cudaEventDestroy(ev);
-  for (auto ev : c->ev_trace) cudaEventDestroy(ev);
-  if (c->ev_start) cudaEventDestroy(c->ev_start);
-  if (c->ev_end) cudaEventDestroy(c->ev_end);
-  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (cudaEvent_t ev : { c->ev_id_chain, c->ev_t0, c->ev_t1 }) if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < MAX_STREAMS; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
   for (int i = 0; i < SIDE_STREAMS; i++) if (c->side_streams[i]) cudaStreamDestroy(c->side_streams[i]);
-  for (auto ev : c->ev_side) cudaEventDestroy(ev);
-  if (c->main_stream) cudaStreamDestroy(c->main_stream);
-  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-  for (auto ev : c->ev_h2d) cudaEventDestroy(ev);
+  for (cudaStream_t s : { c->main_stream, c->copy_stream, c->d2h_stream, c->fin_stream }) if (s) cudaStreamDestroy(s);
   if (c->d_tables) cudaFree(c->d_tables);
   if (c->d_frame_counter) cudaFree(c->d_frame_counter);
-  c->work.release(); c->out_cloud.release(); c->enc_frames.release(); c->enc_persist.release(); c->enc_input.release();
-  c->dec_frames.release(); c->dec_input.release(); c->dec_output.release();
-  c->h_frames.release(); c->h_dframes.release(); c->h_results.release();
+  c->out_cloud.release();
   delete c;
 }
 
-size_t ccv2_max_compressed_size(size_t npts) { return stream_cap_for(npts, true); }
+size_t ccv2_max_compressed_size(size_t npts) { return stream_cap_for(npts, true, true); }
 
 void *ccv2_host_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
 void ccv2_host_free(void *p) { if (p) cudaFreeHost(p); }
@@ -452,6 +567,7 @@ int ccv2_get_metrics(ccv2_codec *c, uint64_t m[3]) { if (!c || !m) return CCV2_E
 int ccv2_set_frame_id(ccv2_codec *c, uint32_t v) {
   if (!c) return CCV2_ERR_ARG;
   cudaSetDevice(c->device);
+  finish_all(c); drain(c);
   c->frame_id = v;
   CU(cudaMemcpy(c->d_frame_counter, &v, 4, cudaMemcpyHostToDevice));
   return CCV2_OK;
@@ -460,7 +576,7 @@ uint32_t ccv2_get_frame_id(const ccv2_codec *c) { return c ? c->frame_id : 0; }
 uint64_t ccv2_last_launch_count(const ccv2_codec *c) { return c ? c->launches : 0; }
 float ccv2_last_device_ms(const ccv2_codec *c) { return c ? c->device_ms : 0.f; }
 
-int ccv2_set_profiling(ccv2_codec *c, int on) { if (!c) return CCV2_ERR_ARG; c->profiling = on != 0; c->prof_sum.clear(); return CCV2_OK; }
+int ccv2_set_profiling(ccv2_codec *c, int on) { if (!c) return CCV2_ERR_ARG; finish_all(c); c->profiling = on != 0; c->prof_sum.clear(); return CCV2_OK; }
 int ccv2_get_profile(const ccv2_codec *c, int idx, const char **name, float *total_ms, int *launches) {
   if (!c || idx < 0 || idx >= (int)c->prof_sum.size()) return CCV2_ERR_ARG;
   if (name) *name = c->prof_sum[idx].name.c_str();
@@ -471,129 +587,167 @@ int ccv2_get_profile(const ccv2_codec *c, int idx, const char **name, float *tot
 
 int ccv2_peek_point_count(const void *in_host, size_t len, uint64_t *npts) {
   if (!in_host || !npts || len < FRAME_HDR_BYTES) return CCV2_ERR_ARG;
-  const uint8_t *b = (const uint8_t *)in_host;
-  if (memcmp(b, "<PCL-OCT-CODECV2-COMPRESSED><PCL-OCT-COMPRESSED>", 48) != 0) return CCV2_ERR_STREAM;
-  memcpy(npts, b + 55, 8);
+  PeekInfo pi;
+  if (!peek_header((const uint8_t *)in_host, len, pi)) return CCV2_ERR_STREAM;
+  if (pi.point_count >= (1ull << 28)) return CCV2_ERR_STREAM;      // the codec's frame limit: a forged count must not size a caller's allocation
+  *npts = pi.point_count;
   return CCV2_OK;
 }
 
-static size_t carve_dec(uint8_t *base, size_t pcap, DecFrame *f, size_t *zero_off, size_t *zero_bytes, bool lines = false) {
-  Carver cv(base);
-  const size_t lines_cap = lines ? pcap / LINE_PX + 2 : 0;
-  const size_t img_h = pcap / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = lines ? (lines_cap * LINE_MCU_STRIDE + LINE_MCU_STRIDE) * 6 : mcu_h * 16 * 6;
-  const uint32_t scan_tiles = (uint32_t)(pcap / NODE_THREADS) + 8;
-  uint64_t *scan_status = cv.take<uint64_t>(2 * (size_t)scan_tiles);
-  int16_t *coef = cv.take<int16_t>(nblocks * 64 + 64);
-  size_t z1 = (cv.off + 255) & ~size_t(255);
-  uint8_t *tree = cv.take<uint8_t>(tree_cap_for(pcap));
-  uint8_t *cen = cv.take<uint8_t>(cen_cap_for(pcap));
-  uint8_t *col = cv.take<uint8_t>(cpay_cap_for(pcap));
-  uint64_t *node_prefix = cv.take<uint64_t>(pcap + 8);
-  uint8_t *node_byte = cv.take<uint8_t>(pcap + 8);
-  uint64_t *l2_prefix = cv.take<uint64_t>(pcap + 8);
-  uint8_t *l2_mask = cv.take<uint8_t>(pcap + 8);
-  uint32_t *l2_off = cv.take<uint32_t>(pcap + 8);
-  uint8_t *planes = cv.take<uint8_t>(mcu_h * 16 * 256 * 3 / 2 + 256);
-  uint16_t *qt = cv.take<uint16_t>(128);
-  uint8_t *scan = cv.take<uint8_t>(cpay_cap_for(pcap));
-  uint32_t *line_off = cv.take<uint32_t>(lines_cap + 4), *line_len = cv.take<uint32_t>(lines_cap + 4), *line_w = cv.take<uint32_t>(lines_cap + 4);
-  uint16_t *line_qt = cv.take<uint16_t>(lines_cap * 128 + 128);
-  uint8_t *line_planes = cv.take<uint8_t>(lines_cap * 8192 + 256);
-  if (f) {
-    f->scan_status = scan_status; f->scan_tiles_max = scan_tiles; f->coef = coef; f->coef_cap_blocks = (uint32_t)nblocks;
-    f->tree = tree; f->tree_cap = (uint32_t)tree_cap_for(pcap) - 64; f->cen = cen; f->cen_cap = (uint32_t)cen_cap_for(pcap) - 64;
-    f->col = col; f->col_cap = (uint32_t)cpay_cap_for(pcap) - 64;
-    f->node_prefix = node_prefix; f->node_byte = node_byte; f->node_cap = (uint32_t)pcap;
-    f->l2_prefix = l2_prefix; f->l2_mask = l2_mask; f->l2_off = l2_off;
-    f->planes = planes; f->planes_cap = (uint32_t)(mcu_h * 16 * 256 * 3 / 2); f->qt = qt; f->scan = scan;
-    f->lines_cap = (uint32_t)lines_cap; f->line_off = line_off; f->line_len = line_len; f->line_w = line_w; f->line_qt = line_qt; f->line_planes = line_planes;
-  }
-  if (zero_off) *zero_off = 0;
-  if (zero_bytes) *zero_bytes = z1;
-  return (cv.off + 255) & ~size_t(255);
+}  // extern "C"
+
+// ================================================================================================ rings
+// (Re)shapes a ring for sets of G frames of frame_bytes each.  An existing ring is kept when it already fits (calls of
+// the same shape share it while in flight); otherwise everything in flight is collected first.
+static int ensure_ring(ccv2_codec *c, Ring &r, size_t frame_bytes, int G, int want_sets, const char *what) {
+  const bool fits = r.G == G && r.nsets > 0 && frame_bytes <= r.frame_bytes;
+  if (fits && (r.nsets >= want_sets || r.mem_limited)) return CCV2_OK;
+  finish_all(c);
+  drain(c);
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  const size_t reserve = ((size_t)1 << 30) + total_b / 64;
+  const size_t avail = free_b + r.buf.cap > reserve ? free_b + r.buf.cap - reserve : 0;
+  const size_t set_bytes = (size_t)G * frame_bytes;
+  int nsets = (int)std::min<size_t>((size_t)want_sets, avail / set_bytes);
+  if (fits && nsets <= r.nsets) { r.mem_limited = true; return CCV2_OK; }                  // memory would not give more than there is
+  if (nsets < 1) { c->err = std::string("not enough device memory for one ") + what + " workspace set"; return CCV2_ERR_CUDA; }
+  cudaError_t e = r.buf.ensure((size_t)nsets * set_bytes, false);
+  while (e != cudaSuccess && nsets > 1) { cudaGetLastError(); nsets = (nsets + 1) / 2; e = r.buf.ensure((size_t)nsets * set_bytes, false); }
+  if (e != cudaSuccess) { cudaGetLastError(); c->err = std::string("cudaMalloc (") + what + " ring): " + cudaGetErrorString(e); return CCV2_ERR_CUDA; }
+  r.frame_bytes = frame_bytes; r.G = G; r.nsets = nsets; r.seq = 0; r.mem_limited = nsets < want_sets;
+  while ((int)r.ev_free.size() < nsets) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); r.ev_free.push_back(ev); }
+  r.used.assign(nsets, 0);
+  c->enc_host_valid.assign(c->enc_host_valid.size(), 0);     // intermediates of the last encode are gone
+  return CCV2_OK;
 }
 
-// ================================================================================================ batch driver
-// mode 0: encode, 1: decode, 2: encode -> decode round trip (decode reads the encoder's device-resident streams, so the
-// host->device copies of later groups overlap the device->host copies of earlier ones: both PCIe directions busy).
-static int run_batch(ccv2_codec *c, int mode, int nframes,
-                     const void *const *pts, const size_t *npts, void *const *out, const size_t *out_cap, size_t *out_len,
-                     const void *const *in, const size_t *in_len, void *const *pts_out, const size_t *pts_cap, size_t *npts_out) {
+static void grow_events(std::vector<cudaEvent_t> &v, size_t n, bool timing = false) {
+  while (v.size() < n) { cudaEvent_t ev; if (cudaEventCreateWithFlags(&ev, timing ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) break; v.push_back(ev); }
+}
+
+
+// ================================================================================================ submit
+// mode 0: encode, 1: decode, 2: encode -> decode round trip (the decoder reads the encoder's device-resident stream).
+static int submit_call(ccv2_codec *c, int mode, int nframes,
+                       const void *const *pts, const size_t *npts, void *const *out, const size_t *out_cap, size_t *out_len,
+                       const void *const *in, const size_t *in_len, void *const *pts_out, const size_t *pts_cap, size_t *npts_out,
+                       bool boost, uint32_t fixed_id, int *ticket_out) {
   const bool do_enc = mode != 1, do_dec = mode != 0, rt = mode == 2;
-  c->err.clear(); c->launches = 0; c->device_ms = 0;
-  if (nframes == 0) return CCV2_OK;
-  c->work_mode = mode;
+  c->err.clear();
   CU(cudaSetDevice(c->device));
   const ccv2_params &prm = c->prm;
-  const bool cen = prm.do_voxel_grid_centroid != 0, color = prm.do_color_encoding != 0;
-  // Device-resident batches run best as 8 groups (fewer, larger launches; measured 1640 against 1390 Mpoints/s with 16).
-  // When clouds or results cross PCIe the pipeline is paced by the copies, and 16 smaller groups start earlier and
-  // leave a shorter copy-back tail (end to end 900 against 820 Mpoints/s).
-  const void *first_io = do_enc ? (pts ? pts[0] : nullptr) : (in ? in[0] : nullptr);
-  const void *first_out = do_dec ? (pts_out ? pts_out[0] : nullptr) : (out ? out[0] : nullptr);
-  const bool host_io = (first_io && !is_device_ptr(first_io)) || (first_out && !is_device_ptr(first_out));
-  const int NS = c->profiling ? 1 : (c->n_streams ? c->n_streams : (host_io ? MAX_STREAMS : 8));
-  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(256, (nframes + NS - 1) / NS)));
-  const int ngroups = (nframes + G - 1) / G;
-  while ((int)c->ev_h2d.size() < ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_h2d.push_back(ev); }
-  while ((int)c->ev_side.size() < 2 * ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_side.push_back(ev); }
-  while ((int)c->ev_group.size() < 2 * ngroups) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); c->ev_group.push_back(ev); }
-  cudaStream_t ms = c->main_stream;
-  CU(c->h_results.ensure(sizeof(FrameResult) * nframes));
-  FrameResult *hres = (FrameResult *)c->h_results.p;
-  c->trace_marks.clear();
-  auto mark = [&](int g, const char *label, cudaStream_t s) {       // CCV2_TRACE: timestamp on the group's stream
-    if (!c->trace) return;
-    if (c->ev_trace.size() <= c->trace_marks.size()) { cudaEvent_t ev; if (cudaEventCreate(&ev) != cudaSuccess) return; c->ev_trace.push_back(ev); }
-    cudaEventRecord(c->ev_trace[c->trace_marks.size()], s);
-    c->trace_marks.push_back({g, label});
-  };
+  const bool cen = prm.do_voxel_grid_centroid != 0, color = prm.do_color_encoding != 0, lines = prm.color_coding_type == 2;
+  CallCtx &x = boost ? c->calls[N_CALLS - 1] : c->calls[c->user_calls++ & 1];
+  if (x.busy) finish_call(c, x);
+  const int ticket = c->next_ticket++;
+  if (ticket_out) *ticket_out = ticket;
+  x.ticket = ticket; x.mode = mode; x.nframes = nframes; x.boost = boost; x.rc_early = CCV2_OK; x.launches = 0; x.device_ms = 0;
+  x.pts = pts; x.npts = npts; x.out = out; x.out_cap = out_cap; x.out_len = out_len; x.in = in; x.in_len = in_len; x.pts_out = pts_out; x.pts_cap = pts_cap; x.npts_out = npts_out;
+  x.trace_marks.clear();
+  if (nframes == 0) { x.busy = false; x.ngroups = 0; return CCV2_OK; }
 
-  // ------------------------------------------------------------------ encode side set-up
-  size_t nmax = 1, zoff = 0, zbytes = 0, slot_bytes = 0, frames_bytes = 0;
-  std::vector<size_t> input_off(nframes + 1, 0);
-  std::vector<char> in_dev(nframes, 1), out_dev(nframes, 0);
-  EncFrame *hf = nullptr, *df = nullptr;
+  // ------------------------------------------------------------------ classify the caller's buffers, size the workspaces
+  x.in_kind.assign(nframes, PK_NONE); x.out_kind.assign(nframes, PK_NONE); x.pts_kind.assign(nframes, PK_NONE);
+  x.stage_off_stream.assign(nframes + 1, 0); x.stage_off_pts.assign(nframes + 1, 0);
+  size_t nmax = 1, ncap_max = 1, tcap_max = 0, ccap_max = 0, in_stage_max = 0, out_stage_max = 0, stage_total = 0;
+  bool host_in_any = false;
+  std::vector<size_t> dcount(nframes, 0);                  // records a pinned destination receives by one copy-engine transfer
+  for (int i = 0; i < nframes; i++) {
+    if (do_enc) {
+      if (npts[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; }
+      if (npts[i] && !pts[i]) return CCV2_ERR_ARG;
+      nmax = std::max(nmax, npts[i]);
+      x.in_kind[i] = npts[i] ? ptr_kind(pts[i]) : PK_DEVICE;
+      if (x.in_kind[i] != PK_DEVICE) host_in_any = true;
+      x.out_kind[i] = (out && out[i]) ? ptr_kind(out[i]) : PK_NONE;
+      if (x.out_kind[i] == PK_PAGEABLE) { x.stage_off_stream[i] = stage_total; stage_total += (std::min(out_cap[i], stream_cap_for(npts[i], cen, boost)) + 255) & ~size_t(255); }
+    }
+    if (do_dec) {
+      if (pts_cap[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; }
+      if ((!rt && in_len[i] && !in[i]) || (pts_cap[i] && !pts_out[i])) return CCV2_ERR_ARG;
+      x.pts_kind[i] = pts_cap[i] ? ptr_kind(pts_out[i]) : PK_DEVICE;
+      size_t ncap = pts_cap[i], tcap, ccap;
+      if (rt) { ncap = std::max<size_t>(npts[i], 1); tcap = tree_cap_for(ncap, boost); ccap = cpay_cap_for(ncap, boost); dcount[i] = std::min(pts_cap[i], npts[i]); }
+      else {
+        x.in_kind[i] = in_len[i] ? ptr_kind(in[i]) : PK_DEVICE;
+        PeekInfo pi; bool peeked = false;
+        if (x.in_kind[i] != PK_DEVICE && in_len[i]) {       // host stream: read the header here and size the workspace from it
+          peeked = peek_header((const uint8_t *)in[i], in_len[i], pi);
+          in_stage_max = std::max(in_stage_max, (in_len[i] + 64 + 255) & ~size_t(255));
+        }
+        if (peeked && pi.point_count < (1ull << 28)) {
+          ncap = std::max<size_t>(1, std::min<size_t>(pts_cap[i], pi.point_count));
+          tcap = (size_t)std::min<uint64_t>(pi.B, 22ull * ncap + 1024) + 1024;          // B <= depth * V: a larger size word is a malformed stream
+          ccap = cpay_cap_for(ncap, boost) + (boost ? 2 * in_len[i] : 0);
+          dcount[i] = ncap;
+        } else { ncap = std::max<size_t>(ncap, 1); tcap = tree_cap_for(ncap, boost); ccap = cpay_cap_for(ncap, boost) + (boost ? 2 * in_len[i] : 0); dcount[i] = pts_cap[i]; }
+      }
+      ncap_max = std::max(ncap_max, ncap); tcap_max = std::max(tcap_max, tcap); ccap_max = std::max(ccap_max, ccap);
+      if (x.pts_kind[i] == PK_PINNED) out_stage_max = std::max(out_stage_max, (32 * dcount[i] + 255) & ~size_t(255));
+      if (x.pts_kind[i] == PK_PAGEABLE) { x.stage_off_pts[i] = stage_total; stage_total += (32 * pts_cap[i] + 255) & ~size_t(255); }
+    }
+  }
+  const int NS = c->profiling ? 1 : (c->n_streams ? c->n_streams : MAX_STREAMS);
+  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(MAX_GROUP, (nframes + 31) / 32)));
+  const int ngroups = (nframes + G - 1) / G;
+  x.G = G; x.ngroups = ngroups;
+
+  size_t fe_bytes = 0, fe_zero = 0, ll_bytes = 0, stream_end = 0, enc_ll = 0, dec_ws = 0, dec_zero = 0;
+  if (do_enc) { size_t zo; fe_bytes = carve_fe(nullptr, nmax, nullptr, prm, boost, host_in_any, &zo, &fe_zero); enc_ll = carve_enc_ll(nullptr, nmax, nullptr, cen, boost, &stream_end); }
+  if (do_dec) dec_ws = carve_dec(nullptr, ncap_max, tcap_max, ccap_max, nullptr, &dec_zero, lines);
+  const size_t ws_off = rt ? stream_end : 0;                          // round trip: the decoder's workspace lies over the encoder's dead buffers
+  const size_t in_stage_off = std::max(enc_ll, ws_off + dec_ws);
+  const size_t out_stage_off = in_stage_off + in_stage_max;
+  ll_bytes = out_stage_off + out_stage_max;
+  {
+    const int want_ll = std::max(1, std::min(2 * ngroups, (c->inflight_max + G - 1) / G));
+    const int want_fe = std::max(1, std::min(2 * ngroups, std::max(4, c->fe_frames / G)));
+    int rc;
+    if (do_enc && (rc = ensure_ring(c, c->fe, fe_bytes, G, want_fe, "front-end")) != CCV2_OK) return rc;
+    if ((rc = ensure_ring(c, c->ll, ll_bytes, G, want_ll, "long-lived")) != CCV2_OK) return rc;
+  }
+  Ring &fe = c->fe, &ll = c->ll;
+  x.fe_seq0 = fe.seq; x.ll_seq0 = ll.seq; x.fe_nsets = fe.nsets; x.ll_nsets = ll.nsets;
+  x.fe_set.assign(ngroups, 0); x.ll_set.assign(ngroups, 0);
+  for (int g = 0; g < ngroups; g++) { x.fe_set[g] = do_enc ? (int)((fe.seq + g) % fe.nsets) : 0; x.ll_set[g] = (int)((ll.seq + g) % ll.nsets); }
+  if (do_enc) fe.seq += ngroups;
+  ll.seq += ngroups;
+  CU(x.stage.ensure(stage_total + 256));
+  grow_events(x.ev_h2d, ngroups); grow_events(x.ev_side, 2 * (size_t)ngroups); grow_events(x.ev_done, ngroups); grow_events(x.ev_fin, ngroups);
+  if ((int)x.ev_h2d.size() < ngroups || (int)x.ev_side.size() < 2 * ngroups || (int)x.ev_done.size() < ngroups || (int)x.ev_fin.size() < ngroups) { c->err = "cudaEventCreate failed"; return CCV2_ERR_CUDA; }
+
+  // ------------------------------------------------------------------ frame records
+  EncFrame *hf = nullptr, *df = nullptr; DecFrame *hd = nullptr, *dd = nullptr;
   EncParams P; HeaderParams H;
   memset(&P, 0, sizeof P); memset(&H, 0, sizeof H);
+  size_t frames_bytes = 0;
   if (do_enc) {
-    for (int i = 0; i < nframes; i++) { if (npts[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; } if (npts[i] && !pts[i]) return CCV2_ERR_ARG; nmax = std::max(nmax, npts[i]); }
-    // Slots: one per (stream, frame-in-group); persist + input staging: one per frame of the batch
-    slot_bytes = carve_enc_slot(nullptr, nmax, nullptr, prm, &zoff, &zbytes);
-    if (rt) {                                                        // round trip: a frame's decode workspace reuses its encode slot (dead once the stream is assembled)
-      size_t pmax = 0, zo, zz;
-      for (int i = 0; i < nframes; i++) pmax = std::max(pmax, pts_cap[i]);
-      if (pmax >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; }
-      slot_bytes = std::max(slot_bytes, carve_dec(nullptr, pmax, nullptr, &zo, &zz, prm.color_coding_type == 2));
-    }
-    const int nslots = std::min(ngroups, NS) * G;
-    CU(c->work.ensure(slot_bytes * nslots));
-    std::vector<size_t> persist_off(nframes + 1, 0);
-    for (int i = 0; i < nframes; i++) {
-      persist_off[i + 1] = persist_off[i] + carve_enc_persist(nullptr, npts[i], nullptr, cen);
-      in_dev[i] = npts[i] ? is_device_ptr(pts[i]) : 1;
-      out_dev[i] = (out && out[i]) ? is_device_ptr(out[i]) : 0;
-      input_off[i + 1] = input_off[i] + (in_dev[i] ? 0 : ((32 * npts[i] + 255) & ~size_t(255)));
-    }
-    CU(c->enc_persist.ensure(persist_off[nframes]));
-    CU(c->enc_input.ensure(input_off[nframes] + 256));
     frames_bytes = (sizeof(EncFrame) * nframes + 255) & ~size_t(255);
-    CU(c->enc_frames.ensure(frames_bytes + (size_t)nframes * 3 * 256 * 4));
-    CU(c->h_frames.ensure(sizeof(EncFrame) * nframes));
-    hf = (EncFrame *)c->h_frames.p; df = (EncFrame *)c->enc_frames.p;
+    CU(x.enc_frames.ensure(frames_bytes + (size_t)nframes * 3 * 256 * 4));
+    CU(x.h_frames.ensure(sizeof(EncFrame) * nframes));
+    hf = (EncFrame *)x.h_frames.p; df = (EncFrame *)x.enc_frames.p;
     memset(hf, 0, sizeof(EncFrame) * nframes);
     for (int i = 0; i < nframes; i++) {
       EncFrame &f = hf[i];
-      const int g = i / G, slot = (g % NS) * G + (i % G);
-      f.pts = in_dev[i] ? (const uint8_t *)pts[i] : (const uint8_t *)c->enc_input.p + input_off[i];
+      const int g = i / G, j = i % G;
       f.n = (uint32_t)npts[i];
       f.n_finite = (uint32_t)npts[i];                               // keygen subtracts the non-finite points
       f.violator = NONE_U32;
-      carve_enc_slot((uint8_t *)c->work.p + slot_bytes * slot, nmax, &f, prm, nullptr, nullptr);
-      f.zero_ptr = (uint8_t *)c->work.p + slot_bytes * slot + zoff; f.zero_bytes = zbytes;
-      carve_enc_persist((uint8_t *)c->enc_persist.p + persist_off[i], npts[i], &f, cen);
-      f.hist = (uint32_t *)((uint8_t *)c->enc_frames.p + frames_bytes) + (size_t)i * 3 * 256;
+      f.frame_id_fixed = fixed_id;
+      f.pts = (const uint8_t *)pts[i];
+      uint8_t *fb = fe.frame_base(x.fe_set[g], j);
+      carve_fe(fb, nmax, &f, prm, boost, x.in_kind[i] != PK_DEVICE, nullptr, nullptr);     // host input: f.pts = the set's staging area
+      f.zero_ptr = fb; f.zero_bytes = fe_zero;
+      carve_enc_ll(ll.frame_base(x.ll_set[g], j), nmax, &f, cen, boost, nullptr);
+      f.hist = (uint32_t *)((uint8_t *)x.enc_frames.p + frames_bytes) + (size_t)i * 3 * 256;
       if (color && (prm.color_coding_type == 0 || prm.color_coding_type == 3)) f.avg = f.cpay;   // raw averages are the colour payload
+      switch (x.out_kind[i]) {
+        case PK_DEVICE: f.out_ptr = (uint8_t *)out[i]; f.out_cap = out_cap[i]; break;
+        case PK_PINNED: { void *dp = nullptr; CU(cudaHostGetDevicePointer(&dp, out[i], 0)); f.out_ptr = (uint8_t *)dp; f.out_cap = out_cap[i]; break; }
+        case PK_PAGEABLE: f.out_ptr = (uint8_t *)x.stage.p + x.stage_off_stream[i]; f.out_cap = std::min(out_cap[i], stream_cap_for(npts[i], cen, boost)); break;
+        default: f.out_ptr = nullptr; f.out_cap = 0; break;
+      }
     }
     P.res = prm.octree_resolution;
     { int ex; double m = frexp(P.res, &ex); P.res_pow2 = (m == 0.5); P.inv_res = P.res_pow2 ? 1.0 / P.res : 0.0; }
@@ -606,86 +760,90 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
     H.color_type = prm.color_coding_type; H.macroblock = prm.macroblock_size;
     c->last_enc_params = P;
   }
-
-  // ------------------------------------------------------------------ decode side set-up
-  std::vector<size_t> work_off(nframes + 1, 0), dinput_off(nframes + 1, 0), output_off(nframes + 1, 0), zb(nframes, 0);
-  std::vector<char> din_dev(nframes, 1), dout_dev(nframes, 1);
-  DecFrame *hd = nullptr, *dd = nullptr;
   if (do_dec) {
-    for (int i = 0; i < nframes; i++) {
-      if (pts_cap[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; }
-      if ((!rt && in_len[i] && !in[i]) || (pts_cap[i] && !pts_out[i])) return CCV2_ERR_ARG;
-      size_t zo;
-      work_off[i + 1] = work_off[i] + carve_dec(nullptr, pts_cap[i], nullptr, &zo, &zb[i], prm.color_coding_type == 2);
-      din_dev[i] = rt ? 1 : (in_len[i] ? is_device_ptr(in[i]) : 1);
-      dout_dev[i] = pts_cap[i] ? is_device_ptr(pts_out[i]) : 1;
-      dinput_off[i + 1] = dinput_off[i] + (din_dev[i] ? 0 : ((in_len[i] + 64 + 255) & ~size_t(255)));
-      output_off[i + 1] = output_off[i] + (dout_dev[i] ? 0 : ((32 * pts_cap[i] + 255) & ~size_t(255)));
-    }
-    if (!rt) CU(c->work.ensure(work_off[nframes]));                  // one arena serves encode slots and decode workspaces: a call uses one or the other (or aliases them, round trip)
-    CU(c->dec_input.ensure(dinput_off[nframes] + 256));
-    CU(c->dec_output.ensure(output_off[nframes] + 256));
-    CU(c->dec_frames.ensure(sizeof(DecFrame) * nframes));
-    CU(c->h_dframes.ensure(sizeof(DecFrame) * nframes));
-    hd = (DecFrame *)c->h_dframes.p; dd = (DecFrame *)c->dec_frames.p;
+    CU(x.dec_frames.ensure(sizeof(DecFrame) * nframes));
+    CU(x.h_dframes.ensure(sizeof(DecFrame) * nframes));
+    hd = (DecFrame *)x.h_dframes.p; dd = (DecFrame *)x.dec_frames.p;
     memset(hd, 0, sizeof(DecFrame) * nframes);
     for (int i = 0; i < nframes; i++) {
       DecFrame &f = hd[i];
+      const int g = i / G, j = i % G;
+      uint8_t *lb = ll.frame_base(x.ll_set[g], j);
       if (rt) { f.in = hf[i].stream; f.in_len = 0; }       // length filled in on the device by link_kernel
       else {
-        f.in = din_dev[i] ? (const uint8_t *)in[i] : (const uint8_t *)c->dec_input.p + dinput_off[i];
+        f.in = x.in_kind[i] == PK_DEVICE ? (const uint8_t *)in[i] : lb + in_stage_off;
         f.in_len = in_len[i];
         if (in_len[i] == 0) f.error = FERR_BAD_STREAM;
       }
-      f.out_pts = dout_dev[i] ? (uint8_t *)pts_out[i] : (uint8_t *)c->dec_output.p + output_off[i];
+      switch (x.pts_kind[i]) {
+        case PK_PINNED: f.out_pts = lb + out_stage_off; break;
+        case PK_PAGEABLE: f.out_pts = (uint8_t *)x.stage.p + x.stage_off_pts[i]; break;
+        default: f.out_pts = (uint8_t *)pts_out[i]; break;
+      }
       f.out_cap = pts_cap[i];
-      uint8_t *wbase = rt ? (uint8_t *)c->work.p + slot_bytes * (((i / G) % NS) * G + (i % G)) : (uint8_t *)c->work.p + work_off[i];
-      carve_dec(wbase, pts_cap[i], &f, nullptr, nullptr, prm.color_coding_type == 2);
-      f.zero_ptr = wbase; f.zero_bytes = zb[i];
+      carve_dec(lb + ws_off, ncap_max, tcap_max, ccap_max, &f, nullptr, lines);
+      f.zero_ptr = lb + ws_off; f.zero_bytes = dec_zero;
     }
   }
 
   // ------------------------------------------------------------------ enqueue
-  CU(cudaEventRecord(c->ev_start, ms));
+  cudaStream_t ms = c->main_stream;
+  auto mark = [&](int g, const char *label, cudaStream_t s) {       // CCV2_TRACE: timestamp on the group's stream
+    if (!c->trace) return;
+    if (x.ev_trace.size() <= x.trace_marks.size()) grow_events(x.ev_trace, x.trace_marks.size() + 1, true);
+    if (x.ev_trace.size() <= x.trace_marks.size()) return;
+    cudaEventRecord(x.ev_trace[x.trace_marks.size()], s);
+    x.trace_marks.push_back({g, label});
+  };
+  x.busy = true;
+  // from here on work is in flight: an error must not leave it queued behind the caller's back
+#define CUQ(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e__); drain(c); cudaGetLastError(); x.busy = false; return CCV2_ERR_CUDA; } } while (0)
+  CUQ(cudaEventRecord(x.ev_start, ms));
   if (do_enc) {
-    CU(cudaMemcpyAsync(df, hf, sizeof(EncFrame) * nframes, cudaMemcpyHostToDevice, ms));
-    CU(cudaMemsetAsync((uint8_t *)c->enc_frames.p + frames_bytes, 0, (size_t)nframes * 3 * 256 * 4, ms));
+    CUQ(cudaMemcpyAsync(df, hf, sizeof(EncFrame) * nframes, cudaMemcpyHostToDevice, ms));
+    CUQ(cudaMemsetAsync((uint8_t *)x.enc_frames.p + frames_bytes, 0, (size_t)nframes * 3 * 256 * 4, ms));
   }
-  if (do_dec) CU(cudaMemcpyAsync(dd, hd, sizeof(DecFrame) * nframes, cudaMemcpyHostToDevice, ms));
+  if (do_dec) CUQ(cudaMemcpyAsync(dd, hd, sizeof(DecFrame) * nframes, cudaMemcpyHostToDevice, ms));
   // serial CTAs reserve enough shared memory (1 KB per CTA is the system's) that only serial_cap of them fit on an SM
-  const int serial_cap = c->serial_cap ? c->serial_cap : (nframes + c->n_sm - 1) / c->n_sm;
+  const int serial_cap = c->serial_cap ? c->serial_cap : (std::min(nframes, ll.nsets * G) + c->n_sm - 1) / c->n_sm;
   size_t serial_smem_enc = 0, serial_smem_dec = 0;
   if (serial_cap > 0 && serial_cap <= 14 && !c->profiling) {
     const size_t per_cta = (c->smem_sm / 1024 / (size_t)(serial_cap + 1) + 1) * 1024;
     if (per_cta > c->smem_static_enc + 1024) serial_smem_enc = per_cta - c->smem_static_enc - 1024;
     if (per_cta > c->smem_static_dec + 1024) serial_smem_dec = per_cta - c->smem_static_dec - 1024;
   }
-  cudaEvent_t ev_setup = c->ev_fork;
-  CU(cudaEventRecord(ev_setup, ms));
+  CUQ(cudaEventRecord(x.ev_setup, ms));
+  bool host_io = host_in_any;
+  for (int i = 0; i < nframes && !host_io; i++) host_io = (x.out_kind[i] != PK_NONE && x.out_kind[i] != PK_DEVICE) || (do_dec && x.pts_kind[i] != PK_DEVICE);
+  const bool use_lps_dec = c->lps_dec < 0 ? (rt && !host_io) : c->lps_dec != 0;
   uint64_t launches = 0;
   uint32_t *counter = c->d_frame_counter;
+  bool copy_waits_setup = false;
   for (int g = 0; g < ngroups; g++) {
-    cudaStream_t st = c->streams[g % NS];
+    const int sl = x.ll_set[g], sf = x.fe_set[g];
+    cudaStream_t st = c->streams[(x.ll_seq0 + g) % NS];
     const int f0 = g * G, gf = std::min(G, nframes - f0);
     const unsigned steered_grid = (unsigned)((gf + c->n_sm - 1) / c->n_sm * c->n_sm);
-    CU(cudaStreamWaitEvent(st, ev_setup, 0));
+    CUQ(cudaStreamWaitEvent(st, x.ev_setup, 0));
+    bool any_h2d = false;
+    for (int i = 0; i < gf; i++) any_h2d |= do_enc ? (x.in_kind[f0 + i] != PK_DEVICE && npts[f0 + i]) : (x.in_kind[f0 + i] != PK_DEVICE && in_len[f0 + i]);
+    // take the sets: the previous users' streams (and copies) must be done with them
+    if (do_enc && fe.used[sf]) { CUQ(cudaStreamWaitEvent(st, fe.ev_free[sf], 0)); if (any_h2d) CUQ(cudaStreamWaitEvent(c->copy_stream, fe.ev_free[sf], 0)); }
+    if (ll.used[sl]) { CUQ(cudaStreamWaitEvent(st, ll.ev_free[sl], 0)); if (any_h2d && !do_enc) CUQ(cudaStreamWaitEvent(c->copy_stream, ll.ev_free[sl], 0)); }
+    if (any_h2d && !copy_waits_setup) { CUQ(cudaStreamWaitEvent(c->copy_stream, x.ev_setup, 0)); copy_waits_setup = true; }
     if (do_enc) {
       EncFrame *dg = df + f0;
       size_t gn = 1;
       // Host inputs go through ONE copy stream in group order: copies issued on the group streams would be
       // interleaved by the copy engine and every group's input would land at the very end (measured), which defeats
       // the pipeline.  This way group g can start as soon as its own clouds are on the device.
-      bool any_h2d = false;
       for (int i = 0; i < gf; i++) {
         gn = std::max(gn, npts[f0 + i]);
-        if (!in_dev[f0 + i] && npts[f0 + i]) {
-          if (!any_h2d && g == 0) CU(cudaStreamWaitEvent(c->copy_stream, ev_setup, 0));
-          CU(cudaMemcpyAsync((void *)hf[f0 + i].pts, pts[f0 + i], 32 * npts[f0 + i], cudaMemcpyHostToDevice, c->copy_stream));
-          any_h2d = true;
-        }
+        if (x.in_kind[f0 + i] != PK_DEVICE && npts[f0 + i])
+          CUQ(cudaMemcpyAsync((void *)hf[f0 + i].pts, pts[f0 + i], 32 * npts[f0 + i], cudaMemcpyHostToDevice, c->copy_stream));
       }
       LAUNCH("zero_region_kernel", zero_region_kernel<EncFrame><<<dim3(128, gf), 256, 0, st>>>(dg));
-      if (any_h2d) { CU(cudaEventRecord(c->ev_h2d[g], c->copy_stream)); CU(cudaStreamWaitEvent(st, c->ev_h2d[g], 0)); }
+      if (any_h2d) { CUQ(cudaEventRecord(x.ev_h2d[g], c->copy_stream)); CUQ(cudaStreamWaitEvent(st, x.ev_h2d[g], 0)); }
       mark(g, "inputs", st);
       const unsigned gx256 = (unsigned)((gn + 255) / 256), gtiles = (unsigned)((gn + SORT_TILE - 1) / SORT_TILE);
       LAUNCH("bbox_kernel", bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 0));
@@ -693,19 +851,19 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       LAUNCH("keygen_kernel", keygen_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P, 0));
       LAUNCH("bbox_kernel(slow path)", bbox_kernel<<<gf, 1024, 0, st>>>(dg, P, 1));
       LAUNCH("keygen_kernel(rekey)", keygen_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P, 1));
-      // frame ids are sequential over the batch: group g's setup needs group g-1's setup kernel to have run
-      if (g > 0) CU(cudaStreamWaitEvent(st, c->ev_group[g - 1], 0));
+      // frame ids are sequential over the batch (and over calls): a group's setup waits for the previous group's
+      if (c->id_chain_used) CUQ(cudaStreamWaitEvent(st, c->ev_id_chain, 0));
       LAUNCH("frame_setup_kernel", frame_setup_kernel<<<1, 32, 0, st>>>(dg, gf, counter));
-      CU(cudaEventRecord(c->ev_group[g], st));
+      CUQ(cudaEventRecord(c->ev_id_chain, st)); c->id_chain_used = true;
       LAUNCH("sort_hist_kernel", sort_hist_kernel<<<dim3(gtiles, gf), 256, 0, st>>>(dg));
       for (int p = 0; p < 8; p++) LAUNCH("sort_pass_kernel", sort_pass_kernel<<<dim3(gtiles, gf), SORT_THREADS, SORT_SMEM_BYTES, st>>>(dg, p));
-      LAUNCH("leaf_scan_kernel", leaf_scan_kernel<<<dim3((unsigned)((gn + LEAF_TILE - 1) / LEAF_TILE), gf), LEAF_THREADS, 0, st>>>(dg));
+      LAUNCH("leaf_scan_kernel", leaf_scan_kernel<<<dim3((unsigned)((gn + LEAF_TILE - 1) / LEAF_TILE), gf), LEAF_THREADS, 0, st>>>(dg, color && prm.color_coding_type == 1));
       LAUNCH("leaf_emit_kernel", leaf_emit_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P));
       if (color && prm.color_coding_type == 1) {
         const size_t img_h = gn / 256 + 1, mcu_h = (img_h + 15) / 16, nblk = mcu_h * 16 * 6;
         LAUNCH("jpeg_mcu_kernel", jpeg_mcu_kernel<<<dim3((unsigned)(mcu_h * 16), gf), 256, 0, st>>>(dg, c->d_tables));
         LAUNCH("jpeg_huff_kernel", jpeg_huff_kernel<<<dim3((unsigned)((nblk + HUFF_THREADS - 1) / HUFF_THREADS), gf), HUFF_THREADS, 0, st>>>(dg, c->d_tables));
-        const size_t jb = 4 * gn + 8192;
+        const size_t jb = cpay_cap_for(gn, boost);
         LAUNCH("jpeg_stuff_kernel", jpeg_stuff_kernel<<<dim3((unsigned)((jb + STUFF_THREADS * STUFF_BYTES - 1) / (STUFF_THREADS * STUFF_BYTES)), gf), STUFF_THREADS, 0, st>>>(dg, c->d_tables));
       }
       if (color && prm.color_coding_type == 2) {
@@ -715,54 +873,51 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
         LAUNCH("lines_offsets_kernel", lines_offsets_kernel<<<gf, 1024, 0, st>>>(dg));
         LAUNCH("lines_copy_kernel", lines_copy_kernel<<<dim3(lines_max, gf), 256, 0, st>>>(dg));
       }
-      const size_t hmax = std::max(tree_cap_for(gn), cpay_cap_for(gn));
+      // the front-end set goes to the next group: everything from here on lives in the long-lived set
+      CUQ(cudaEventRecord(fe.ev_free[sf], st)); fe.used[sf] = 1;
+      const size_t hmax = std::max(tree_cap_for(gn, boost), cpay_cap_for(gn, boost));
       mark(g, "leaves", st);
       LAUNCH("hist_kernel", hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), 3, gf), 256, 0, st>>>(dg));
       if (c->lps_enc) LAUNCH("rc_encode_lps_kernel", rc_encode_lps_kernel<<<dim3((unsigned)((gf + 31) / 32), 3), 32, c->lps_smem_enc, st>>>(dg, gf, cen, color));
       else LAUNCH("rc_encode_kernel", rc_encode_kernel<<<gf, 96, serial_smem_enc, st>>>(dg, cen, color));
       LAUNCH("assemble_kernel", assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H));
+      if (out) LAUNCH("export_kernel", export_kernel<<<dim3(2, gf), 256, 0, st>>>(dg));
       mark(g, "encoded", st);
     }
     if (do_dec) {
       DecFrame *dg = dd + f0;
       size_t pmax = 1;
-      bool any_h2d = false;
       for (int i = 0; i < gf; i++) {
         const int k = f0 + i;
-        pmax = std::max(pmax, pts_cap[k]);
-        if (!rt && !din_dev[k] && in_len[k]) {
-          if (!any_h2d && g == 0) CU(cudaStreamWaitEvent(c->copy_stream, ev_setup, 0));
-          CU(cudaMemcpyAsync((void *)hd[k].in, in[k], in_len[k], cudaMemcpyHostToDevice, c->copy_stream));
-          any_h2d = true;
-        }
+        pmax = std::max(pmax, rt ? std::max<size_t>(npts[k], 1) : std::min(ncap_max, std::max<size_t>(pts_cap[k], 1)));
+        if (!rt && x.in_kind[k] != PK_DEVICE && in_len[k])
+          CUQ(cudaMemcpyAsync((void *)hd[k].in, in[k], in_len[k], cudaMemcpyHostToDevice, c->copy_stream));
       }
       LAUNCH("zero_region_kernel", zero_region_kernel<DecFrame><<<dim3(64, gf), 256, 0, st>>>(dg));
-      if (any_h2d) { CU(cudaEventRecord(c->ev_h2d[g], c->copy_stream)); CU(cudaStreamWaitEvent(st, c->ev_h2d[g], 0)); }
+      if (!rt && any_h2d) { CUQ(cudaEventRecord(x.ev_h2d[g], c->copy_stream)); CUQ(cudaStreamWaitEvent(st, x.ev_h2d[g], 0)); }
       if (rt) LAUNCH("link_kernel", link_kernel<<<(gf + 63) / 64, 64, 0, st>>>(df + f0, dg, gf));
-      // Two entropy stages.  dec_entropy_kernel (a CTA per frame) is the faster one when nothing else runs (decode-only
-      // calls: 374 ms against 414 ms for 1024 frames) and when the copies pace the pipeline (host buffers: 935 against
-      // 896 Mpoints/s end to end); in a device-resident round trip its 7 CTAs per SM compete with the other groups'
-      // encode kernels and the lane-per-stream decoder, 8 frames to a warp on an SM of its own, wins (677 ms against 753 ms).
-      if (c->lps_dec < 0 ? (rt && !host_io) : c->lps_dec != 0) {
+      // Two entropy stages.  dec_entropy_kernel (a CTA per frame) has the shorter latency; the lane-per-stream decoder
+      // (8 frames to a warp) executes a third of the instructions and wins when the SMs' issue slots are the limit.
+      if (use_lps_dec) {
         // tree layers on the group's stream, speculated colour layers on a side stream at the same time
-        cudaStream_t s2 = c->profiling ? st : c->side_streams[g % SIDE_STREAMS];
+        cudaStream_t s2 = c->profiling ? st : c->side_streams[(x.ll_seq0 + g) % SIDE_STREAMS];
         const unsigned lps_ctas = (unsigned)((gf + LPS_DEC_FRAMES - 1) / LPS_DEC_FRAMES);
         LAUNCH("dec_head_kernel", dec_head_kernel<<<gf, 32, 0, st>>>(dg));
-        if (s2 != st) { CU(cudaEventRecord(c->ev_side[2 * g], st)); CU(cudaStreamWaitEvent(s2, c->ev_side[2 * g], 0)); }
+        if (s2 != st) { CUQ(cudaEventRecord(x.ev_side[2 * g], st)); CUQ(cudaStreamWaitEvent(s2, x.ev_side[2 * g], 0)); }
         LAUNCH("rc_decode_lps_kernel<tree>", rc_decode_lps_kernel<true><<<lps_ctas, 32 * (1 + LPS_DEC_FRAMES), sizeof(LpsSmem), st>>>(dg, gf, c->use_ring));
         LAUNCH_S(s2, "rc_decode_lps_kernel<colour>", rc_decode_lps_kernel<false><<<lps_ctas, 32, offsetof(LpsSmem, rg), s2>>>(dg, gf, 0));
         mark(g, "tree", st);
         mark(g, "colour-rc", s2);
         LAUNCH_S(s2, "dec_jpeg_kernel", dec_jpeg_kernel<<<gf, 32, 0, s2>>>(dg));
         mark(g, "jpeg", s2);
-        if (s2 != st) { CU(cudaEventRecord(c->ev_side[2 * g + 1], s2)); CU(cudaStreamWaitEvent(st, c->ev_side[2 * g + 1], 0)); }
+        if (s2 != st) { CUQ(cudaEventRecord(x.ev_side[2 * g + 1], s2)); CUQ(cudaStreamWaitEvent(st, x.ev_side[2 * g + 1], 0)); }
         LAUNCH("dec_finish_kernel", dec_finish_kernel<<<gf, 32, 0, st>>>(dg));
       } else
       LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<gf, 96, serial_smem_dec, st>>>(dg, c->use_ring));
       mark(g, "entropy", st);
       LAUNCH("jpeg_destuff_kernel", jpeg_destuff_kernel<<<gf, 1024, 0, st>>>(dg));
       LAUNCH("dec_serial_kernel", dec_serial_kernel<<<steered_grid, 64, 0, st>>>(dg, f0, gf));
-      if (prm.color_coding_type == 2) {
+      if (lines) {
         const unsigned lines_max = (unsigned)(pmax / LINE_PX + 2);
         LAUNCH("lines_index_kernel", lines_index_kernel<<<gf, 32, 0, st>>>(dg));
         LAUNCH("lines_decode_kernel", lines_decode_kernel<<<dim3(lines_max, gf), 32, 0, st>>>(dg));
@@ -774,123 +929,242 @@ static int run_batch(ccv2_codec *c, int mode, int nframes,
       LAUNCH("dec_points_kernel", dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg));
       mark(g, "decoded", st);
     }
-    LAUNCH("publish_kernel", publish_kernel<<<(gf + 63) / 64, 64, 0, st>>>(do_enc ? df + f0 : nullptr, do_dec ? dd + f0 : nullptr, hres + f0, gf));
-    CU(cudaEventRecord(c->ev_group[ngroups + g], st));
-    CU(cudaGetLastError());
-  }
-
-  // ------------------------------------------------------------------ collect: per group wait for its record copies,
-  // then move the results out with exact sizes (later groups keep running meanwhile)
-  int rc = CCV2_OK;
-  for (int g = 0; g < ngroups; g++) {
-    cudaStream_t st = c->streams[g % NS];
-    cudaEvent_t ev = c->ev_group[ngroups + g];
-    CU(cudaEventSynchronize(ev));                            // the group's kernels are done and its FrameResults are in host memory
-    const int f0 = g * G, gf = std::min(G, nframes - f0);
-    for (int i = 0; i < gf; i++) {
-      const int k = f0 + i;
-      const FrameResult &r = hres[k];
-      bool enc_ok = true;
-      if (do_enc) {
-        if (out_len) out_len[k] = 0;
-        if (r.enc_error) {
-          enc_ok = false;
-          if (rc == CCV2_OK) {
-            rc = (r.enc_error & FERR_DEPTH) ? CCV2_ERR_DEPTH : CCV2_ERR_WORKSPACE;
-            char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x (encode)", k, r.enc_error); c->err = b;
-          }
-        } else if (r.out_len && out && out[k]) {
-          if (r.out_len > out_cap[k]) { if (rc == CCV2_OK) { rc = CCV2_ERR_CAPACITY; c->err = "output buffer too small"; } }
-          else {
-            CU(cudaMemcpyAsync(out[k], hf[k].stream, r.out_len, out_dev[k] ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-            out_len[k] = r.out_len;
-          }
-        } else if (r.out_len && !rt) { if (rc == CCV2_OK) { rc = CCV2_ERR_CAPACITY; c->err = "output buffer too small"; } }
-        else if (r.out_len && out_len) out_len[k] = r.out_len;      // round trip without a stream buffer: report the size only
+    CUQ(cudaEventRecord(x.ev_done[g], st));
+    // decoded clouds for pinned host destinations: one copy-engine transfer per frame out of the set's staging area, on
+    // the D2H stream in group order; the set is free once they have left
+    bool any_d2h = false;
+    if (do_dec) for (int i = 0; i < gf; i++) any_d2h |= x.pts_kind[f0 + i] == PK_PINNED && dcount[f0 + i] > 0;
+    if (any_d2h) {
+      CUQ(cudaStreamWaitEvent(c->d2h_stream, x.ev_done[g], 0));
+      for (int i = 0; i < gf; i++) {
+        const int k = f0 + i;
+        if (x.pts_kind[k] == PK_PINNED && dcount[k]) CUQ(cudaMemcpyAsync(pts_out[k], hd[k].out_pts, 32 * dcount[k], cudaMemcpyDeviceToHost, c->d2h_stream));
       }
-      if (do_dec) {
-        npts_out[k] = 0;
-        if (rt && (!enc_ok || r.out_len == 0)) continue;           // empty frame: nothing was written, nothing to decode
-        if (r.dec_error) {
-          if (rc == CCV2_OK) {
-            rc = (r.dec_error & FERR_OUT_CAP) ? CCV2_ERR_CAPACITY : (r.dec_error & FERR_DEPTH) ? CCV2_ERR_DEPTH : (r.dec_error & FERR_UNSUPPORTED) ? CCV2_ERR_UNSUPPORTED
-               : (r.dec_error & (FERR_TREE_CAP | FERR_JPEG_CAP)) ? CCV2_ERR_WORKSPACE : CCV2_ERR_STREAM;
-            char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x (decode)", k, r.dec_error); c->err = b;
-          }
-          continue;
+      mark(g, "copied", c->d2h_stream);
+      CUQ(cudaEventRecord(ll.ev_free[sl], c->d2h_stream));
+      CUQ(cudaEventRecord(x.ev_fin[g], c->d2h_stream));
+    } else {
+      CUQ(cudaEventRecord(ll.ev_free[sl], st));
+      CUQ(cudaEventRecord(x.ev_fin[g], st));
+    }
+    ll.used[sl] = 1;
+    CUQ(cudaGetLastError());
+  }
+  for (int g = 0; g < ngroups; g++) CUQ(cudaStreamWaitEvent(ms, x.ev_fin[g], 0));
+  CUQ(cudaEventRecord(x.ev_end, ms));
+#undef CUQ
+  x.launches = launches;
+  return CCV2_OK;
+}
+
+// ================================================================================================ collect
+
+static int retry_frame(ccv2_codec *c, CallCtx &x, int k, uint32_t fixed_id);
+
+static int finish_call(ccv2_codec *c, CallCtx &x) {
+  if (!x.busy) return CCV2_OK;
+  x.busy = false;                                             // first: a retry below may come back here through ensure_ring
+  const int mode = x.mode, nframes = x.nframes;
+  const bool do_enc = mode != 1, do_dec = mode != 0, rt = mode == 2;
+  int rc = CCV2_OK;
+  auto store = [&](int r) { auto &v = c->done; v.push_back({x.ticket, r}); if (v.size() > 16) v.erase(v.begin()); return r; };
+  cudaSetDevice(c->device);
+  cudaError_t e = cudaEventSynchronize(x.ev_end);
+  EncFrame *hf = (EncFrame *)x.h_frames.p; DecFrame *hd = (DecFrame *)x.h_dframes.p;
+  if (e == cudaSuccess && do_enc) e = cudaMemcpyAsync(hf, x.enc_frames.p, sizeof(EncFrame) * nframes, cudaMemcpyDeviceToHost, c->fin_stream);
+  if (e == cudaSuccess && do_dec) e = cudaMemcpyAsync(hd, x.dec_frames.p, sizeof(DecFrame) * nframes, cudaMemcpyDeviceToHost, c->fin_stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->fin_stream);
+  if (e != cudaSuccess) { c->err = std::string("collect: ") + cudaGetErrorString(e); drain(c); cudaGetLastError(); return store(CCV2_ERR_CUDA); }
+  cudaEventElapsedTime(&x.device_ms, x.ev_start, x.ev_end);
+  c->device_ms = x.device_ms; c->launches = x.launches;
+  const uint32_t retry_bits = FERR_TREE_CAP | FERR_STREAM_CAP | FERR_JPEG_CAP;
+  std::vector<int> retry;
+  for (int k = 0; k < nframes; k++) {
+    bool enc_ok = true;
+    uint64_t slen = 0;
+    if (do_enc) {
+      const EncFrame &f = hf[k];
+      if (x.out_len) x.out_len[k] = 0;
+      slen = f.out_len;
+      const uint32_t eb = f.error;
+      if (eb & ~FERR_CALLER_CAP) {
+        enc_ok = false;
+        if ((eb & retry_bits) && !(eb & (FERR_DEPTH | FERR_UNSUPPORTED)) && !x.boost) { retry.push_back(k); if (do_dec) x.npts_out[k] = 0; continue; }
+        if (rc == CCV2_OK) {
+          rc = (eb & FERR_DEPTH) ? CCV2_ERR_DEPTH : (eb & FERR_UNSUPPORTED) ? CCV2_ERR_UNSUPPORTED : CCV2_ERR_WORKSPACE;
+          char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x (encode)", k, eb); c->err = b;
         }
-        npts_out[k] = r.V;
-        if (!dout_dev[k] && r.V) CU(cudaMemcpyAsync(pts_out[k], hd[k].out_pts, 32ull * r.V, cudaMemcpyDeviceToHost, st));
+      } else if (slen && x.out && x.out[k]) {
+        if ((eb & FERR_CALLER_CAP) || slen > x.out_cap[k]) { if (rc == CCV2_OK) { rc = CCV2_ERR_CAPACITY; c->err = "output buffer too small"; } }
+        else {
+          if (x.out_kind[k] == PK_PAGEABLE) {
+            e = cudaMemcpy(x.out[k], (uint8_t *)x.stage.p + x.stage_off_stream[k], slen, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { c->err = std::string("cudaMemcpy (stream): ") + cudaGetErrorString(e); return store(CCV2_ERR_CUDA); }
+          }
+          x.out_len[k] = slen;
+        }
+      } else if (slen && !rt) { if (rc == CCV2_OK) { rc = CCV2_ERR_CAPACITY; c->err = "output buffer too small"; } }
+      else if (slen && x.out_len) x.out_len[k] = slen;        // round trip without a stream buffer: report the size only
+    }
+    if (do_dec) {
+      x.npts_out[k] = 0;
+      if (rt && (!enc_ok || slen == 0)) continue;              // empty frame: nothing was written, nothing to decode
+      const DecFrame &f = hd[k];
+      if (f.error) {
+        if ((f.error & (FERR_TREE_CAP | FERR_JPEG_CAP)) && !(f.error & (FERR_OUT_CAP | FERR_DEPTH | FERR_UNSUPPORTED)) && !x.boost) { retry.push_back(k); continue; }
+        if (rc == CCV2_OK) {
+          rc = (f.error & FERR_OUT_CAP) ? CCV2_ERR_CAPACITY : (f.error & FERR_DEPTH) ? CCV2_ERR_DEPTH : (f.error & FERR_UNSUPPORTED) ? CCV2_ERR_UNSUPPORTED
+             : (f.error & (FERR_TREE_CAP | FERR_JPEG_CAP)) ? CCV2_ERR_WORKSPACE : CCV2_ERR_STREAM;
+          char b[96]; snprintf(b, sizeof b, "frame %d: device error bits 0x%x (decode)", k, f.error); c->err = b;
+        }
+        continue;
+      }
+      x.npts_out[k] = f.V;
+      if (x.pts_kind[k] == PK_PAGEABLE && f.V) {
+        e = cudaMemcpy(x.pts_out[k], (uint8_t *)x.stage.p + x.stage_off_pts[k], 32ull * f.V, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { c->err = std::string("cudaMemcpy (points): ") + cudaGetErrorString(e); return store(CCV2_ERR_CUDA); }
       }
     }
-    // full frame records (metrics, debug hook) come back last on this stream
-    if (do_enc) CU(cudaMemcpyAsync(hf + f0, df + f0, sizeof(EncFrame) * gf, cudaMemcpyDeviceToHost, st));
-    if (do_dec) CU(cudaMemcpyAsync(hd + f0, dd + f0, sizeof(DecFrame) * gf, cudaMemcpyDeviceToHost, st));
-    mark(g, "copied", st);
-    CU(cudaEventRecord(ev, st));
-    CU(cudaStreamWaitEvent(ms, ev, 0));
   }
-  CU(cudaEventRecord(c->ev_end, ms));
-  CU(cudaEventSynchronize(c->ev_end));
-  CU(cudaEventElapsedTime(&c->device_ms, c->ev_start, c->ev_end));
   if (c->trace) {
-    fprintf(stderr, "ccv2 trace mode=%d frames=%d groups=%d total %.1f ms\n", mode, nframes, ngroups, c->device_ms);
-    for (int g = 0; g < ngroups; g++) {
+    fprintf(stderr, "ccv2 trace ticket=%d mode=%d frames=%d groups=%d (G %d, fe sets %d, ll sets %d) total %.1f ms\n", x.ticket, mode, nframes, x.ngroups, x.G, x.fe_nsets, x.ll_nsets, x.device_ms);
+    for (int g = 0; g < x.ngroups; g++) {
       fprintf(stderr, "  group %2d:", g);
-      for (size_t k = 0; k < c->trace_marks.size(); k++) if (c->trace_marks[k].group == g) {
-        float t = -1; cudaEventElapsedTime(&t, c->ev_start, c->ev_trace[k]);
-        fprintf(stderr, " %s %.1f |", c->trace_marks[k].label, t);
+      for (size_t k = 0; k < x.trace_marks.size(); k++) if (x.trace_marks[k].group == g) {
+        float t = -1; cudaEventElapsedTime(&t, x.ev_start, x.ev_trace[k]);
+        fprintf(stderr, " %s %.1f |", x.trace_marks[k].label, t);
       }
       fprintf(stderr, "\n");
     }
-  }
-  if (c->trace) {                                            // how evenly did the serial CTAs spread?  (frame records are back on the host)
-    for (int dir = 0; dir < 2; dir++) {
+    for (int dir = 0; dir < 2; dir++) {                       // how evenly did the serial CTAs spread?
       if (dir == 0 ? !do_enc : !do_dec) continue;
       std::vector<int> per_sm(256, 0);
       for (int i = 0; i < nframes; i++) per_sm[(dir == 0 ? hf[i].serial_sm : hd[i].serial_sm) & 255]++;
       std::vector<int> hist(64, 0); int mx = 0;
       for (int s2 = 0; s2 < c->n_sm; s2++) { hist[std::min(63, per_sm[s2])]++; mx = std::max(mx, std::min(63, per_sm[s2])); }
-      fprintf(stderr, "  %s serial CTAs per SM (cap %d):", dir == 0 ? "encode" : "decode", serial_cap);
+      fprintf(stderr, "  %s serial CTAs per SM:", dir == 0 ? "encode" : "decode");
       for (int k = 0; k <= mx; k++) fprintf(stderr, " %dx%d", hist[k], k);
       fprintf(stderr, "\n");
     }
   }
   prof_collect(c);
-  c->launches = launches;
-  if (do_enc) {
-    CU(cudaMemcpy(&c->frame_id, counter, 4, cudaMemcpyDeviceToHost));
-    c->enc_host.assign(hf, hf + nframes);
-    for (int i = nframes - 1; i >= 0; i--) if (hf[i].out_len) { for (int k = 0; k < 3; k++) c->metrics[k] = hf[i].coded[k]; break; }
-  } else {
-    for (int i = nframes - 1; i >= 0; i--) if (!hd[i].error) { for (int k = 0; k < 3; k++) c->metrics[k] = hd[i].coded[k]; c->frame_id = hd[i].frame_id; break; }
+  c->last_mode = mode;
+  if (!x.boost) {
+    if (do_enc) {
+      c->enc_host.assign(hf, hf + nframes);
+      c->enc_host_valid.assign(nframes, 0);
+      // a frame's intermediates are intact while no later group took its ring sets
+      const uint64_t fe_end = x.fe_seq0 + x.ngroups, ll_end = x.ll_seq0 + x.ngroups;
+      for (int i = 0; i < nframes; i++) {
+        const uint64_t g = (uint64_t)(i / x.G);
+        c->enc_host_valid[i] = mode == 0 && c->fe.seq == fe_end && c->ll.seq == ll_end && c->fe.nsets == x.fe_nsets && c->ll.nsets == x.ll_nsets &&
+                               x.fe_seq0 + g + x.fe_nsets >= fe_end && x.ll_seq0 + g + x.ll_nsets >= ll_end;
+      }
+      for (int i = nframes - 1; i >= 0; i--) if (hf[i].out_len) { for (int k = 0; k < 3; k++) c->metrics[k] = hf[i].coded[k]; c->frame_id = hf[i].frame_id; break; }
+    } else {
+      for (int i = nframes - 1; i >= 0; i--) if (!hd[i].error) { for (int k = 0; k < 3; k++) c->metrics[k] = hd[i].coded[k]; c->frame_id = hd[i].frame_id; break; }
+    }
+  }
+  // frames whose workspace bound was exceeded: once more, alone, with bounds that cannot be (sparse deep octrees)
+  for (int k : retry) {
+    const int r = retry_frame(c, x, k, do_enc ? hf[k].frame_id : 0);
+    if (r != CCV2_OK && rc == CCV2_OK) rc = r;
+  }
+  return store(rc);
+}
+
+static int retry_frame(ccv2_codec *c, CallCtx &x, int k, uint32_t fixed_id) {
+  // x's arrays are the caller's; the sub-call writes frame k's results straight into them
+  const void *p1 = x.pts ? x.pts[k] : nullptr; size_t n1 = x.npts ? x.npts[k] : 0;
+  void *o1 = (x.out && x.out[k]) ? x.out[k] : nullptr; size_t oc1 = x.out_cap ? x.out_cap[k] : 0, ol1 = 0;
+  const void *i1 = x.in ? x.in[k] : nullptr; size_t il1 = x.in_len ? x.in_len[k] : 0;
+  void *po1 = x.pts_out ? x.pts_out[k] : nullptr; size_t pc1 = x.pts_cap ? x.pts_cap[k] : 0, np1 = 0;
+  const bool want_out = x.out != nullptr;
+  const uint32_t saved_id = c->frame_id; const uint64_t m0 = c->metrics[0], m1 = c->metrics[1], m2 = c->metrics[2];
+  int rc = submit_call(c, x.mode, 1, x.pts ? &p1 : nullptr, x.npts ? &n1 : nullptr, want_out ? &o1 : nullptr, &oc1, &ol1,
+                       x.in ? &i1 : nullptr, x.in_len ? &il1 : nullptr, x.pts_out ? &po1 : nullptr, x.pts_cap ? &pc1 : nullptr, &np1, true, fixed_id ? fixed_id : 0, nullptr);
+  if (rc == CCV2_OK) rc = finish_call(c, c->calls[N_CALLS - 1]);
+  if (x.out_len) x.out_len[k] = ol1;
+  if (x.npts_out) x.npts_out[k] = np1;
+  if (k != x.nframes - 1) { c->frame_id = saved_id; c->metrics[0] = m0; c->metrics[1] = m1; c->metrics[2] = m2; }
+  else if (rc == CCV2_OK) {                                    // the last frame of the call defines the codec's metrics
+    CallCtx &y = c->calls[N_CALLS - 1];
+    if (x.mode != 1) { const EncFrame &f = ((EncFrame *)y.h_frames.p)[0]; if (f.out_len) { for (int q = 0; q < 3; q++) c->metrics[q] = f.coded[q]; c->frame_id = f.frame_id; } }
+    else { const DecFrame &f = ((DecFrame *)y.h_dframes.p)[0]; if (!f.error) { for (int q = 0; q < 3; q++) c->metrics[q] = f.coded[q]; c->frame_id = f.frame_id; } }
   }
   return rc;
 }
 
+static int wait_ticket(ccv2_codec *c, int ticket) {
+  for (auto &x : c->calls) if (x.busy && x.ticket == ticket) return finish_call(c, x);
+  for (auto &d : c->done) if (d.ticket == ticket) return d.rc;
+  return CCV2_OK;
+}
+
+extern "C" {
+
+int ccv2_submit_encode(ccv2_codec *c, int nframes, const void *const *pts, const size_t *npts,
+                       void *const *out, const size_t *out_cap, size_t *out_len, int *ticket) {
+  if (!c || !ticket || nframes < 0 || (nframes && (!pts || !npts || !out || !out_cap || !out_len))) return CCV2_ERR_ARG;
+  return submit_call(c, 0, nframes, pts, npts, out, out_cap, out_len, nullptr, nullptr, nullptr, nullptr, nullptr, false, 0, ticket);
+}
+int ccv2_submit_decode(ccv2_codec *c, int nframes, const void *const *in, const size_t *in_len,
+                       void *const *pts_out, const size_t *pts_cap, size_t *npts_out, int *ticket) {
+  if (!c || !ticket || nframes < 0 || (nframes && (!in || !in_len || !pts_out || !pts_cap || !npts_out))) return CCV2_ERR_ARG;
+  return submit_call(c, 1, nframes, nullptr, nullptr, nullptr, nullptr, nullptr, in, in_len, pts_out, pts_cap, npts_out, false, 0, ticket);
+}
+int ccv2_submit_roundtrip(ccv2_codec *c, int nframes, const void *const *pts, const size_t *npts,
+                          void *const *out, const size_t *out_cap, size_t *out_len,
+                          void *const *pts_out, const size_t *pts_cap, size_t *npts_out, int *ticket) {
+  if (!c || !ticket || nframes < 0 || (nframes && (!pts || !npts || !pts_out || !pts_cap || !npts_out))) return CCV2_ERR_ARG;
+  if (out && (!out_cap || !out_len)) return CCV2_ERR_ARG;
+  return submit_call(c, 2, nframes, pts, npts, out, out_cap, out_len, nullptr, nullptr, pts_out, pts_cap, npts_out, false, 0, ticket);
+}
+int ccv2_wait(ccv2_codec *c, int ticket) { if (!c) return CCV2_ERR_ARG; return wait_ticket(c, ticket); }
+
 int ccv2_encode_batch(ccv2_codec *c, int nframes, const void *const *pts, const size_t *npts,
                       void *const *out, const size_t *out_cap, size_t *out_len) {
-  if (!c || nframes < 0 || (nframes && (!pts || !npts || !out || !out_cap || !out_len))) return CCV2_ERR_ARG;
-  return run_batch(c, 0, nframes, pts, npts, out, out_cap, out_len, nullptr, nullptr, nullptr, nullptr, nullptr);
+  int t = 0;
+  const int rc = ccv2_submit_encode(c, nframes, pts, npts, out, out_cap, out_len, &t);
+  return rc ? rc : wait_ticket(c, t);
 }
-
 int ccv2_decode_batch(ccv2_codec *c, int nframes, const void *const *in, const size_t *in_len,
                       void *const *pts_out, const size_t *pts_cap, size_t *npts_out) {
-  if (!c || nframes < 0 || (nframes && (!in || !in_len || !pts_out || !pts_cap || !npts_out))) return CCV2_ERR_ARG;
-  return run_batch(c, 1, nframes, nullptr, nullptr, nullptr, nullptr, nullptr, in, in_len, pts_out, pts_cap, npts_out);
+  int t = 0;
+  const int rc = ccv2_submit_decode(c, nframes, in, in_len, pts_out, pts_cap, npts_out, &t);
+  return rc ? rc : wait_ticket(c, t);
 }
-
 int ccv2_roundtrip_batch(ccv2_codec *c, int nframes, const void *const *pts, const size_t *npts,
                          void *const *out, const size_t *out_cap, size_t *out_len,
                          void *const *pts_out, const size_t *pts_cap, size_t *npts_out) {
-  if (!c || nframes < 0 || (nframes && (!pts || !npts || !pts_out || !pts_cap || !npts_out))) return CCV2_ERR_ARG;
-  if (out && (!out_cap || !out_len)) return CCV2_ERR_ARG;
-  return run_batch(c, 2, nframes, pts, npts, out, out_cap, out_len, nullptr, nullptr, pts_out, pts_cap, npts_out);
+  int t = 0;
+  const int rc = ccv2_submit_roundtrip(c, nframes, pts, npts, out, out_cap, out_len, pts_out, pts_cap, npts_out, &t);
+  return rc ? rc : wait_ticket(c, t);
+}
+
+// Device-side stopwatch over any number of calls: start marks the codec's control stream (everything submitted earlier is
+// collected first), stop collects what is in flight and returns the time between the mark and the end of the last call.
+int ccv2_timer_start(ccv2_codec *c) {
+  if (!c) return CCV2_ERR_ARG;
+  CU(cudaSetDevice(c->device));
+  finish_all(c); drain(c);
+  CU(cudaEventRecord(c->ev_t0, c->main_stream));
+  return CCV2_OK;
+}
+int ccv2_timer_stop(ccv2_codec *c, float *ms) {
+  if (!c || !ms) return CCV2_ERR_ARG;
+  CU(cudaSetDevice(c->device));
+  const int rc = finish_all(c);
+  CU(cudaEventRecord(c->ev_t1, c->main_stream));             // behind the last call's end on the control stream
+  CU(cudaEventSynchronize(c->ev_t1));
+  CU(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+  return rc;
 }
 
 int ccv2_get_output_cloud(ccv2_codec *c, int frame, void *points_out, size_t cap_points, size_t *npoints) {
   if (!c || frame < 0 || frame >= (int)c->enc_host.size() || !npoints) return CCV2_ERR_ARG;
-  if (c->work_mode != 0) { c->err = "the output cloud is only available right after ccv2_encode_batch"; return CCV2_ERR_UNSUPPORTED; }
+  finish_all(c);
+  if (c->last_mode != 0 || !c->enc_host_valid[frame]) { c->err = "the output cloud is only available right after ccv2_encode_batch (and while the frame's workspace has not been handed on)"; return CCV2_ERR_UNSUPPORTED; }
   CU(cudaSetDevice(c->device));
   const EncFrame &f = c->enc_host[frame];
   if (f.error) { *npoints = 0; return CCV2_OK; }
@@ -900,19 +1174,59 @@ int ccv2_get_output_cloud(ccv2_codec *c, int frame, void *points_out, size_t cap
   const bool dev = is_device_ptr(points_out);
   uint8_t *dst = (uint8_t *)points_out;
   if (!dev) { CU(c->out_cloud.ensure(32ull * f.V)); dst = (uint8_t *)c->out_cloud.p; }
-  output_cloud_kernel<<<(f.V + 255) / 256, 256, 0, c->main_stream>>>(f, c->last_enc_params, dst);
+  output_cloud_kernel<<<(f.V + 255) / 256, 256, 0, c->fin_stream>>>(f, c->last_enc_params, dst);
   CU(cudaGetLastError());
-  if (!dev) CU(cudaMemcpyAsync(points_out, dst, 32ull * f.V, cudaMemcpyDeviceToHost, c->main_stream));
-  CU(cudaStreamSynchronize(c->main_stream));
+  if (!dev) CU(cudaMemcpyAsync(points_out, dst, 32ull * f.V, cudaMemcpyDeviceToHost, c->fin_stream));
+  CU(cudaStreamSynchronize(c->fin_stream));
+  return CCV2_OK;
+}
+
+// computeQualityMetric (quality_metrics_impl.hpp:82-239): exact nearest neighbours both ways, see quality_kernels.cuh
+int ccv2_quality_metrics(ccv2_codec *c, const void *cloud_a, size_t na, const void *cloud_b, size_t nb, ccv2_quality *out) {
+  if (!c || !out || (na && !cloud_a) || (nb && !cloud_b) || na >= (1u << 28) || nb >= (1u << 28)) return CCV2_ERR_ARG;
+  CU(cudaSetDevice(c->device));
+  finish_all(c);
+  memset(out, 0, sizeof *out);
+  out->in_point_count = na; out->out_point_count = nb;
+  if (na == 0 || nb == 0) return CCV2_OK;
+  const bool da = is_device_ptr(cloud_a), db = is_device_ptr(cloud_b);
+  const size_t sa = da ? 0 : (32 * na + 255) & ~size_t(255), sb = db ? 0 : (32 * nb + 255) & ~size_t(255);
+  CU(c->out_cloud.ensure(sa + sb + 2 * sizeof(QualityAccum) + 256));
+  uint8_t *w = (uint8_t *)c->out_cloud.p;
+  const uint8_t *pa = da ? (const uint8_t *)cloud_a : w, *pb = db ? (const uint8_t *)cloud_b : w + sa;
+  QualityAccum *acc = (QualityAccum *)(w + sa + sb);
+  cudaStream_t st = c->fin_stream;
+  if (!da) CU(cudaMemcpyAsync(w, cloud_a, 32 * na, cudaMemcpyHostToDevice, st));
+  if (!db) CU(cudaMemcpyAsync(w + sa, cloud_b, 32 * nb, cudaMemcpyHostToDevice, st));
+  QualityAccum h[2]; memset(h, 0, sizeof h);
+  for (int d = 0; d < 2; d++) for (int k = 0; k < 3; k++) h[d].max_xyz[k] = -3.0e38f;
+  CU(cudaMemcpyAsync(acc, h, sizeof h, cudaMemcpyHostToDevice, st));
+  quality_nn_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(pa, (uint32_t)na, pb, (uint32_t)nb, acc, 1);
+  quality_nn_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(pb, (uint32_t)nb, pa, (uint32_t)na, acc + 1, 0);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(h, acc, sizeof h, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  // quality_metrics_impl.hpp:160-238
+  float max_a, max_b; memcpy(&max_a, &h[0].max_d2_bits, 4); memcpy(&max_b, &h[1].max_d2_bits, 4);
+  max_a = std::sqrt(max_a); max_b = std::sqrt(max_b);
+  const double rms_a = std::sqrt(h[0].sum_d2 / (double)na), rms_b = std::sqrt(h[1].sum_d2 / (double)nb);
+  const float dist_h = std::max(max_a, max_b);
+  const float dist_rms = (float)std::max(rms_a, rms_b);
+  const float energy = h[0].max_xyz[0] * h[0].max_xyz[0] + h[0].max_xyz[1] * h[0].max_xyz[1] + h[0].max_xyz[2] * h[0].max_xyz[2];
+  out->left_hausdorff = max_a; out->right_hausdorff = max_b; out->symm_hausdorff = dist_h;
+  out->left_rms = (float)rms_a; out->right_rms = (float)rms_b; out->symm_rms = dist_rms;
+  out->psnr_db = (float)(10 * std::log10(energy / (dist_rms * dist_rms)));
+  for (int k = 0; k < 3; k++) out->psnr_yuv[k] = 10 * std::log10(1.0 / (h[0].mse_yuv[k] / (double)na));
   return CCV2_OK;
 }
 
 int ccv2_debug_fetch(ccv2_codec *c, int frame, int what, void *host_buf, size_t cap, size_t *len) {
   if (!c || frame < 0 || frame >= (int)c->enc_host.size() || !len) return CCV2_ERR_ARG;
+  finish_all(c);
   CU(cudaSetDevice(c->device));
   const EncFrame &f = c->enc_host[frame];
   const void *src = nullptr; size_t n = 0;
-  if ((what == 0 || what == 2 || what == 4) && c->work_mode != 0) { c->err = "encode intermediates are only available right after ccv2_encode_batch"; return CCV2_ERR_UNSUPPORTED; }
+  if (what != 5 && (c->last_mode != 0 || !c->enc_host_valid[frame])) { c->err = "encode intermediates are only available right after ccv2_encode_batch"; return CCV2_ERR_UNSUPPORTED; }
   ccv2_frame_info info;
   switch (what) {
     case 0: src = f.leaf_key; n = (size_t)f.V * 8; break;

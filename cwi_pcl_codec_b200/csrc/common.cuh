@@ -19,7 +19,8 @@ enum : uint32_t {
   FERR_JPEG_CAP = 1u << 3,    // jpeg buffers exceeded
   FERR_BAD_STREAM = 1u << 4,  // decoder: malformed input
   FERR_OUT_CAP = 1u << 5,     // decoder: caller's point buffer too small
-  FERR_UNSUPPORTED = 1u << 6, // decoder: stream uses a mode outside the implemented scope
+  FERR_UNSUPPORTED = 1u << 6, // stream / cloud needs something outside the implemented scope (e.g. a SNAKE image higher than libjpeg's 65500 rows)
+  FERR_CALLER_CAP = 1u << 7,  // encoder: the caller's stream buffer is too small
 };
 
 enum : int { TK_SORT0 = 0, TK_LEAF = 8, TK_HUFF = 9, TK_STUFF = 10, TK_NODES = 11, TK_EXPAND = 12, TK_COUNT = 16 };
@@ -64,6 +65,8 @@ struct EncFrame {
   uint32_t ticket[TK_COUNT];
   // results
   uint32_t error, frame_id;
+  uint32_t frame_id_fixed, _padf;   // != 0: a retried frame keeps the id it was given the first time (frame_setup_kernel)
+  uint8_t *out_ptr; uint64_t out_cap;   // where the finished stream goes (caller's device buffer, the device alias of a pinned host buffer, or a staging area); may be null
   uint64_t out_len; uint64_t coded[3];
   uint32_t rc_len[3];          // coded bytes per layer incl. table (tree, centroid, colour)
   uint32_t _pad1;

@@ -195,7 +195,7 @@ __global__ void frame_setup_kernel(EncFrame *frames, int nframes, uint32_t *fram
   for (int k = 0; k < nframes; k++) {
     EncFrame &f = frames[k];
     if ((f.error & FERR_DEPTH) || !f.defined) { f.n_finite = 0; }   // no finite point at all: empty frame
-    if (f.n_finite > 0) { id++; f.frame_id = id; f.npasses = (frame_sort_bits(f) + 7) / 8; }
+    if (f.n_finite > 0) { if (f.frame_id_fixed) f.frame_id = f.frame_id_fixed; else { id++; f.frame_id = id; } f.npasses = (frame_sort_bits(f) + 7) / 8; }
     else { f.npasses = 0; f.V = 0; f.B = 0; }
   }
   *frame_counter = id;
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pass_kernel(EncFrame *frame
 #define LEAF_ITEMS 4
 #define LEAF_TILE (LEAF_THREADS * LEAF_ITEMS)
 
-__global__ void __launch_bounds__(LEAF_THREADS) leaf_scan_kernel(EncFrame *frames) {
+__global__ void __launch_bounds__(LEAF_THREADS) leaf_scan_kernel(EncFrame *frames, int snake) {
   EncFrame &f = frames[blockIdx.y];
   const uint32_t nf = f.n_finite;
   const uint32_t ntiles = (nf + LEAF_TILE - 1) / LEAF_TILE;
@@ -384,6 +384,9 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf_scan_kernel(EncFrame *frame
         f.B = (uint32_t)B;
         f.img_h = V / 256 + 1;                         // cjpeg.h:197-198
         f.mcu_h = (f.img_h + 15) / 16;
+        // libjpeg refuses images higher than JPEG_MAX_DIMENSION (65500): the reference's jpeg_io fails there, a 16-bit
+        // SOF0 height would silently wrap here.  V >= 16.7 M voxels with SNAKE colour is reported, not encoded.
+        if (snake && f.img_h > 65500u) { f.error |= FERR_UNSUPPORTED; f.V = 0; f.B = 0; }
       }
     }
   }

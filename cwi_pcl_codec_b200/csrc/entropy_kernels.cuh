@@ -314,6 +314,23 @@ __global__ void __launch_bounds__(256) assemble_kernel(EncFrame *frames, HeaderP
   if (H.with_color) for (uint64_t k = gtid; k < l2; k += gsz) s[off_col + 8 + k] = f.rc_tmp[1][k];
 }
 
+// ---- stream export: the assembled frame leaves the codec's slot for the caller's buffer (device memory, or pinned
+// host memory through its device alias: zero-copy stores over PCIe -- few CTAs on purpose, measured 52 GB/s with
+// 8-32 CTAs and 13 GB/s with 592, profiles/mb_pcie_r2.txt).  grid (blocks, frames)
+__global__ void __launch_bounds__(256) export_kernel(EncFrame *frames) {
+  EncFrame &f = frames[blockIdx.y];
+  const uint64_t n = f.out_len;
+  if (n == 0 || f.error || !f.out_ptr) return;
+  if (n > f.out_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&f.error, FERR_CALLER_CAP); return; }
+  const uint8_t *s = f.stream; uint8_t *d = f.out_ptr;
+  const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (uint64_t)gridDim.x * blockDim.x;
+  if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+    const uint64_t n16 = n / 16;
+    for (uint64_t k = gtid; k < n16; k += gsz) ((uint4 *)d)[k] = ((const uint4 *)s)[k];
+    for (uint64_t k = n16 * 16 + gtid; k < n; k += gsz) d[k] = s[k];
+  } else for (uint64_t k = gtid; k < n; k += gsz) d[k] = s[k];
+}
+
 // ================================================================================================
 // decode side
 // ================================================================================================

@@ -13,6 +13,22 @@
  * detects which.  All functions return 0 on success or a negative ccv2_status.  No exceptions cross the ABI.
  * A codec handle owns its CUDA streams and workspaces and is not thread-safe (like the reference object).
  * There is no CPU fallback: without a CUDA device ccv2_create fails with CCV2_ERR_CUDA.
+ *
+ * Memory kinds.  Device pointers are read and written in place.  Pinned host memory (ccv2_host_alloc / cudaMallocHost /
+ * cudaHostRegister) takes the fast path: clouds go up and decoded clouds come down through the copy engines, streams
+ * leave by zero-copy stores, nothing waits on the host inside a call.  Pageable host memory works everywhere but is
+ * staged (uploads block the calling thread, results are copied when the call is collected).
+ * A decoded-cloud buffer in pinned memory receives ONE transfer of min(capacity, points that can come out) records:
+ * records beyond the reported count are unspecified.
+ *
+ * Process-wide CUDA settings are the host's business: the library keeps up to 28 streams busy and runs best with
+ * CUDA_DEVICE_MAX_CONNECTIONS=32 exported before the process creates its CUDA context (with the default of 8 the
+ * streams share hardware queues and the long serial kernels serialise, measured 2x on a round trip); it does not touch
+ * the environment itself.
+ *
+ * Limits: frames below 2^28 points; realised octree depth <= 21; SNAKE colour images at most 65500 rows (V < 16.7 M
+ * voxels: libjpeg's own limit, CCV2_ERR_UNSUPPORTED beyond); LINES colour mode stages at most 16 KiB of entropy-coded
+ * bits per line (the last line may hold 4095 voxels: ~4 bytes per voxel, CCV2_ERR_WORKSPACE beyond).
  */
 #ifndef CCV2_H
 #define CCV2_H
@@ -92,8 +108,31 @@ int ccv2_roundtrip_batch(ccv2_codec *c, int nframes, const void *const *pts, con
                          void *const *out, const size_t *out_cap, size_t *out_len,
                          void *const *pts_out, const size_t *pts_cap, size_t *npts_out);
 
+/* Asynchronous forms of the three calls above: enqueue the whole batch and return a ticket; ccv2_wait(ticket) blocks until
+ * the results are in the caller's buffers and returns the call's status.  Two calls may be in flight on one handle (a third
+ * submit collects the oldest first): they share the codec's workspace rings, so the uploads and parallel kernels of the
+ * next call overlap the serial entropy stages of the previous one -- a continuous pipeline over consecutive batches,
+ * which the synchronous calls cannot give (each pays the pipeline's fill and drain).  All arrays passed to a submit call
+ * (pointer tables, sizes, out_len / npts_out) must stay alive until the ticket has been waited for.  A call that consumes
+ * another call's output (decode of streams an in-flight encode is still writing) must wait for that ticket first. */
+int ccv2_submit_encode(ccv2_codec *c, int nframes, const void *const *pts, const size_t *npts,
+                       void *const *out, const size_t *out_cap, size_t *out_len, int *ticket);
+int ccv2_submit_decode(ccv2_codec *c, int nframes, const void *const *in, const size_t *in_len,
+                       void *const *pts_out, const size_t *pts_cap, size_t *npts_out, int *ticket);
+int ccv2_submit_roundtrip(ccv2_codec *c, int nframes, const void *const *pts, const size_t *npts,
+                          void *const *out, const size_t *out_cap, size_t *out_len,
+                          void *const *pts_out, const size_t *pts_cap, size_t *npts_out, int *ticket);
+int ccv2_wait(ccv2_codec *c, int ticket);
+
+/* Device-side stopwatch across calls (bench.py): start collects everything in flight and marks the codec's control stream;
+ * stop collects again and returns the milliseconds between the mark and the completion of the last call (CUDA events). */
+int ccv2_timer_start(ccv2_codec *c);
+int ccv2_timer_stop(ccv2_codec *c, float *ms);
+
 /* Reads point_count from a frame header in HOST memory (SURVEY App. A offset 55) so a caller can size
- * pts_out before decoding.  Replaces nothing in the reference (its decoder grows a std::vector). */
+ * pts_out before decoding (scans for the magic like syncToHeader; a count of 2^28 or more -- the codec's frame limit --
+ * is reported as CCV2_ERR_STREAM, so a forged header cannot size an allocation).  Replaces nothing in the reference
+ * (its decoder grows a std::vector). */
 int ccv2_peek_point_count(const void *in_host, size_t len, uint64_t *npts);
 
 /* Replaces: getPerformanceMetrics() (codec.h:193-197): coded bytes of {octree, centroid, colour} layers of
@@ -106,7 +145,7 @@ uint32_t ccv2_get_frame_id(const ccv2_codec *c);
 
 /* Number of kernel launches issued by the last encode/decode batch call (bench.py's gpu_launches). */
 uint64_t ccv2_last_launch_count(const ccv2_codec *c);
-/* Device time of the last batch call's kernel region (CUDA events on the codec's stream), milliseconds. */
+/* Device time of the batch call collected last (CUDA events on the codec's control stream, submit to completion), milliseconds. */
 float ccv2_last_device_ms(const ccv2_codec *c);
 
 /* Profiling hook used by bench.py's roofline leg: when on, a batch call runs all its frames as one group on ONE
@@ -124,11 +163,25 @@ const char *ccv2_status_string(int status);
  * (eval.hpp:862): the encoder's simplified cloud output_ (impl.hpp:96, filled at impl.hpp:1549-1576) -- one 32-byte
  * PointXYZRGB per occupied voxel in stream (DFS) order, at the voxel centre `corner + 0.5 * resolution` (or the float
  * centroid of the voxel's points when doVoxelGridCentroid is set), carrying the voxel's average colour before JPEG.
- * Valid for frame `frame` of the LAST ccv2_encode_batch call, until the next call on the handle (centroid mode
+ * Valid for frame `frame` of the LAST ccv2_encode_batch call, until the next call on the handle and only while the frame's
+ * workspace has not been handed on to a later group of the same call (always true for the last 128 frames of a call; centroid mode
  * re-reads the input cloud, which must still be alive if it was passed as a device pointer).  points_out: host or
  * device memory for cap_points records; *npoints receives the voxel count (also when cap_points is too small:
  * CCV2_ERR_CAPACITY). */
 int ccv2_get_output_cloud(ccv2_codec *c, int frame, void *points_out, size_t cap_points, size_t *npoints);
+
+/* Replaces: computeQualityMetric(cloud_a, cloud_b, QualityMetric&) of evaluate_compression
+ * (apps/evaluate_compression/include/pcl/apps/evaluate_compression/impl/quality_metrics_impl.hpp:82-239; struct
+ * quality_metrics.h:53-75): cloud_a = original, cloud_b = decoded, both 32-byte PointXYZRGB records in host or device
+ * memory.  Nearest neighbours are exact (exhaustive search on the GPU instead of two kd-trees); geometry is symmetric,
+ * colour PSNR is A -> B on a 0..1 YUV scale like the reference's.  Non-finite points take no part. */
+typedef struct ccv2_quality {
+  uint64_t in_point_count, out_point_count;
+  float symm_rms, symm_hausdorff, left_hausdorff, right_hausdorff, left_rms, right_rms;
+  double psnr_db;
+  double psnr_yuv[3];
+} ccv2_quality;
+int ccv2_quality_metrics(ccv2_codec *c, const void *cloud_a, size_t na, const void *cloud_b, size_t nb, ccv2_quality *out);
 
 /* Pinned host memory helpers (cudaMallocHost / cudaFreeHost) for callers that want full-speed PCIe copies. */
 void *ccv2_host_alloc(size_t bytes);

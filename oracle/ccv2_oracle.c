@@ -1120,3 +1120,59 @@ int orc_decode(const uint8_t *in, size_t len, void **pts_out, size_t *n_out, orc
   *pts_out = outp; *n_out = np;
   return 0;
 }
+
+/* ------------------------------------------------------------------ computeQualityMetric
+ * apps/evaluate_compression/include/pcl/apps/evaluate_compression/impl/quality_metrics_impl.hpp:63-70 (YUV), :82-239.
+ * The reference asks two kd-trees for nearest neighbours; this restatement searches exhaustively (exact, O(na * nb):
+ * test sizes only).  Distances: float sum of float squares in x, y, z order ([PCL] KdTreeFLANN, FLANN L2_Simple). */
+static void yuv_of(const uint8_t *rec, float yuv[3]) {
+  double b = rec[16], g = rec[17], r = rec[18];
+  yuv[0] = (float)((0.299 * r + 0.587 * g + 0.114 * b) / 255.0);
+  yuv[1] = (float)((-0.147 * r - 0.289 * g + 0.436 * b) / 255.0);
+  yuv[2] = (float)((0.615 * r - 0.515 * g - 0.100 * b) / 255.0);
+}
+static void nn_pass(const uint8_t *q, size_t nq, const uint8_t *t, size_t nt, double *sum, float *mx, double mse[3]) {
+  *sum = 0; *mx = -3.4028235e38f; if (mse) mse[0] = mse[1] = mse[2] = 0;
+  for (size_t i = 0; i < nq; i++) {
+    float p[3]; memcpy(p, q + 32 * i, 12);
+    if (!(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]))) continue;
+    float best = 3.0e38f; size_t bj = (size_t)-1;
+    for (size_t j = 0; j < nt; j++) {
+      float c[3]; memcpy(c, t + 32 * j, 12);
+      if (!(isfinite(c[0]) && isfinite(c[1]) && isfinite(c[2]))) continue;
+      float dx = p[0] - c[0], dy = p[1] - c[1], dz = p[2] - c[2];
+      float d = dx * dx; d += dy * dy; d += dz * dz;
+      if (d < best) { best = d; bj = j; }
+    }
+    if (bj == (size_t)-1) continue;
+    if (best > *mx) *mx = best;
+    *sum += best;
+    if (mse) {
+      float a[3], b[3]; yuv_of(q + 32 * i, a); yuv_of(t + 32 * bj, b);
+      for (int k = 0; k < 3; k++) mse[k] += (a[k] - b[k]) * (a[k] - b[k]);
+    }
+  }
+}
+int orc_quality_metrics(const void *cloud_a, size_t na, const void *cloud_b, size_t nb, orc_quality *out) {
+  memset(out, 0, sizeof *out);
+  out->in_point_count = na; out->out_point_count = nb;
+  if (!na || !nb) return 0;
+  double sa, sb, mse[3]; float ma, mb;
+  nn_pass((const uint8_t *)cloud_a, na, (const uint8_t *)cloud_b, nb, &sa, &ma, mse);
+  nn_pass((const uint8_t *)cloud_b, nb, (const uint8_t *)cloud_a, na, &sb, &mb, NULL);
+  ma = sqrtf(ma); mb = sqrtf(mb);
+  double ra = sqrt(sa / (double)na), rb = sqrt(sb / (double)nb);
+  float dist_h = ma > mb ? ma : mb, dist_rms = (float)(ra > rb ? ra : rb);
+  float mxs[3] = { -3.4028235e38f, -3.4028235e38f, -3.4028235e38f };        /* getMinMax3D(cloud_a): finite points */
+  for (size_t i = 0; i < na; i++) {
+    float p[3]; memcpy(p, (const uint8_t *)cloud_a + 32 * i, 12);
+    if (!(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]))) continue;
+    for (int k = 0; k < 3; k++) if (p[k] > mxs[k]) mxs[k] = p[k];
+  }
+  float energy = mxs[0] * mxs[0] + mxs[1] * mxs[1] + mxs[2] * mxs[2];
+  out->left_hausdorff = ma; out->right_hausdorff = mb; out->symm_hausdorff = dist_h;
+  out->left_rms = (float)ra; out->right_rms = (float)rb; out->symm_rms = dist_rms;
+  out->psnr_db = (float)(10 * log10(energy / (dist_rms * dist_rms)));
+  for (int k = 0; k < 3; k++) out->psnr_yuv[k] = 10 * log10(1.0 / (mse[k] / (double)na));
+  return 0;
+}

@@ -106,6 +106,15 @@ int orc_bbox_keys(const void *pts, size_t n, double resolution, double bb_min[3]
  * (used to cross-check the sort-based emission) */
 int orc_dfs_recursive(const uint64_t *leaf_codes, size_t v, uint32_t depth, uint8_t **bytes, size_t *nbytes);
 
+/* computeQualityMetric (quality_metrics_impl.hpp:82-239), exhaustive nearest neighbours: test sizes only */
+typedef struct orc_quality {
+  uint64_t in_point_count, out_point_count;
+  float symm_rms, symm_hausdorff, left_hausdorff, right_hausdorff, left_rms, right_rms;
+  double psnr_db;
+  double psnr_yuv[3];
+} orc_quality;
+int orc_quality_metrics(const void *cloud_a, size_t na, const void *cloud_b, size_t nb, orc_quality *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,12 @@ class OrcDebug(C.Structure):
                 ("centroid_bytes", C.POINTER(C.c_uint8)), ("output_cloud", C.POINTER(C.c_uint8))]
 
 
+class OrcQuality(C.Structure):
+    _fields_ = [("in_point_count", C.c_uint64), ("out_point_count", C.c_uint64), ("symm_rms", C.c_float), ("symm_hausdorff", C.c_float),
+                ("left_hausdorff", C.c_float), ("right_hausdorff", C.c_float), ("left_rms", C.c_float), ("right_rms", C.c_float),
+                ("psnr_db", C.c_double), ("psnr_yuv", C.c_double * 3)]
+
+
 def build(force=False):
     """Compile the oracle with gcc (oracle/Makefile)."""
     src = os.path.join(_HERE, "ccv2_oracle.c")
@@ -67,6 +73,7 @@ def lib():
         L.orc_bbox_keys.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
         L.orc_dfs_recursive.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(u8p), szp]
+        L.orc_quality_metrics.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(OrcQuality)]
         _lib = L
     return _lib
 
@@ -220,3 +227,11 @@ def dfs_recursive(leaf_codes, depth):
     r = _take(out, ol.value)
     L.orc_free(out)
     return r
+
+
+def quality_metrics(cloud_a, cloud_b):
+    """computeQualityMetric(original, decoded) (quality_metrics_impl.hpp:82-239); O(na * nb), test sizes only."""
+    a, b = np.ascontiguousarray(cloud_a), np.ascontiguousarray(cloud_b)
+    q = OrcQuality()
+    lib().orc_quality_metrics(a.ctypes.data, a.nbytes // 32, b.ctypes.data, b.nbytes // 32, C.byref(q))
+    return q

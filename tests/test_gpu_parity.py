@@ -159,6 +159,40 @@ def test_batch_spanning_groups_and_streams_matches_one_by_one(K, oracle):
     assert one == streams
 
 
+def kparams_from_golden(K, prm):
+    """oracle parameter names of stream_hashes.json -> ccv2_params."""
+    kw = dict(prm)
+    m = {"do_centroid": "do_voxel_grid_centroid", "do_voxel_grid": "do_voxel_grid_downsampling", "do_color": "do_color_encoding",
+         "color_bit_resolution": "color_bit_resolution"}
+    out = {}
+    if "octree_bits" in kw:
+        out["octree_bits"] = kw.pop("octree_bits"); out["enh_bits"] = kw.pop("enh_bits", 0)
+    for k, v in kw.items():
+        out[m.get(k, k)] = v
+    return K.default_params(**out)
+
+
+def test_golden_stream_hashes_frozen_inputs(K, golden_dir):
+    """GPU streams and decoded clouds against the committed SHA-256 for the frozen input FILES (no generator involved)."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    import cases
+    table = json.load(open(os.path.join(golden_dir, "stream_hashes.json")))
+    checked = 0
+    for name in cases.frozen_names():
+        e = table[name]
+        if e["params"].get("do_voxel_grid", 1) == 0 and not hasattr(K.load_library(), "ccv2_detail_mode_supported"):
+            continue                                               # detail mode: see test_detail_mode_* once the row is built
+        c = K.Codec(kparams_from_golden(K, e["params"]))
+        s = c.encode_batch([cases.load_case(name)])[0]
+        assert len(s) == e["stream_bytes"] and hashlib.sha256(s).hexdigest() == e["stream_sha256"], name
+        d = c.decode_batch([s])[0]
+        assert hashlib.sha256(d.tobytes()).hexdigest() == e["decoded_sha256"], name
+        c.close()
+        checked += 1
+    assert checked >= 10
+
+
 def test_golden_stream_hashes_full_size(K, golden_dir):
     """BASELINE configs[1] size (1M points, depth 11, Q85): GPU streams against the committed SHA-256."""
     table = json.load(open(os.path.join(golden_dir, "stream_hashes.json")))
@@ -349,4 +383,131 @@ def test_many_frames_in_one_call_all_groups_and_streams(K, oracle):
         assert streams[i] == ref
         assert np.array_equal(dec[i], oracle.decode(ref)[0])
     assert c.frame_id == 70
+    c.close()
+
+
+def test_pinned_host_buffers_and_async_calls_share_the_rings(K, oracle):
+    """The fast path of the C ABI: pinned host memory in and out (copy engines up and down, zero-copy stream export) and
+    two calls in flight on one handle (ccv2_submit_* / ccv2_wait) -- same bytes as the synchronous, pageable calls."""
+    clouds = [synth.gen_surface(30000 + 700 * (i % 5), 300 + i) for i in range(40)] + [np.zeros(0, synth.POINT_DTYPE)]
+    kp = K.default_params(octree_bits=9)
+    c = K.Codec(kp)
+    ref_streams = c.encode_batch(clouds)
+    ref_dec = c.decode_batch([s for s in ref_streams if s])
+    ns = [cl.shape[0] for cl in clouds]
+    cap = 6 * max(ns) + 65536
+    F = len(clouds)
+    h_in = K.PinnedBuffer(sum(ns) * 32 + 32)
+    offs = np.concatenate([[0], np.cumsum(ns)]) * 32
+    for i, cl in enumerate(clouds):
+        h_in.array[offs[i]:offs[i + 1]] = np.ascontiguousarray(cl).view(np.uint8).reshape(-1)
+    bufs = []
+    pend = []
+    c.frame_id = 0
+    for rep in range(3):                                   # three calls back to back, at most two in flight
+        h_str, h_out = K.PinnedBuffer(F * cap), K.PinnedBuffer(F * max(ns) * 32)
+        bufs.append((h_str, h_out))
+        pend.append(c.submit_roundtrip_raw([h_in.ptr + int(offs[i]) if ns[i] else None for i in range(F)], ns,
+                                           [h_str.ptr + i * cap for i in range(F)], [cap] * F,
+                                           [h_out.ptr + i * max(ns) * 32 for i in range(F)], [max(n, 1) for n in ns]))
+    live = 0
+    for rep, p in enumerate(pend):
+        lens, cnts = p.wait()
+        h_str, h_out = bufs[rep]
+        j = 0
+        for i in range(F):
+            got = h_str.array[i * cap:i * cap + lens[i]].tobytes()
+            if not ref_streams[i]:
+                assert lens[i] == 0 and cnts[i] == 0
+                continue
+            assert got[:48] == ref_streams[i][:48] and got[52:] == ref_streams[i][52:]        # frame ids run on over the three calls
+            assert int.from_bytes(got[48:52], "little") == int.from_bytes(ref_streams[i][48:52], "little") + rep * 40
+            d = h_out.array[i * max(ns) * 32:i * max(ns) * 32 + cnts[i] * 32].reshape(-1, 32)
+            assert np.array_equal(d, ref_dec[j])
+            j += 1
+            live += 1
+    assert live == 120
+    # decode-only from pinned streams into pinned clouds, asynchronously, while an encode of other frames is in flight
+    h_str, h_out = bufs[0]
+    lens = [len(s) for s in ref_streams]
+    for i, s in enumerate(ref_streams):
+        h_str.array[i * cap:i * cap + len(s)] = np.frombuffer(s, np.uint8)
+    h_out.array[:] = 0
+    h_str2 = K.PinnedBuffer(F * cap)
+    pe = c.submit_encode_raw([h_in.ptr + int(offs[i]) if ns[i] else None for i in range(F)], ns, [h_str2.ptr + i * cap for i in range(F)], [cap] * F)
+    pd = c.submit_decode_raw([h_str.ptr + i * cap for i in range(F - 1)], lens[:-1], [h_out.ptr + i * max(ns) * 32 for i in range(F - 1)], [int.from_bytes(s[55:63], "little") for s in ref_streams[:-1]])
+    cnts = pd.wait()
+    lens2 = pe.wait()
+    for i in range(F - 1):
+        assert np.array_equal(h_out.array[i * max(ns) * 32:i * max(ns) * 32 + cnts[i] * 32].reshape(-1, 32), ref_dec[i])
+        assert h_str2.array[i * cap + 52:i * cap + lens2[i]].tobytes() == ref_streams[i][52:]
+    c.close()
+
+
+def test_sparse_deep_octree_overflows_the_default_workspace_and_is_retried(K, oracle):
+    """Sparse clouds in a deep octree have up to depth x V tree bytes (here ~10 per point against a default bound of 4):
+    the frame is flagged on the device and encoded again with bounds that cannot overflow; decoding sizes its workspace
+    from the stream's own header, so reference-produced streams of such clouds decode as well."""
+    clouds = [synth.gen_uniform(300000, 31), synth.gen_surface(20000, 32), synth.gen_uniform(60000, 33)]
+    kp = K.default_params(octree_bits=16)
+    streams = check_batch(K, oracle, clouds, kp)
+    assert int.from_bytes(streams[0][140:148], "little") > 4 * 300000 + 1024          # B beyond the default tree bound
+    # the same through a round trip (device-side link between encoder and decoder) and with device-resident streams
+    c = K.Codec(kp)
+    arrs = [np.ascontiguousarray(cl) for cl in clouds]
+    caps = [len(s) + 64 for s in streams]
+    strs = [np.zeros(cp, np.uint8) for cp in caps]
+    outs = [np.zeros((a.shape[0], 32), np.uint8) for a in arrs]
+    lens, cnts = c.roundtrip_batch_raw([a.ctypes.data for a in arrs], [a.shape[0] for a in arrs], [s.ctypes.data for s in strs], caps,
+                                       [o.ctypes.data for o in outs], [a.shape[0] for a in arrs])
+    for i in range(3):
+        assert strs[i][:lens[i]].tobytes() == streams[i]
+        assert np.array_equal(outs[i][:cnts[i]], oracle.decode(streams[i])[0])
+    torch = pytest.importorskip("torch")
+    d_str = [torch.from_numpy(np.frombuffer(s, np.uint8).copy()).cuda() for s in streams]
+    d_out = [torch.empty(a.shape[0] * 32, dtype=torch.uint8, device="cuda") for a in arrs]
+    ns = c.decode_batch_raw([t.data_ptr() for t in d_str], [len(s) for s in streams], [t.data_ptr() for t in d_out], [a.shape[0] for a in arrs])
+    for i in range(3):
+        assert np.array_equal(d_out[i][:ns[i] * 32].cpu().numpy().reshape(-1, 32), oracle.decode(streams[i])[0])
+    c.close()
+
+
+def test_quality_metrics_and_the_stated_colour_tolerance(K, oracle):
+    """computeQualityMetric on the GPU (exact exhaustive nearest neighbours) against the oracle's, and the colour
+    tolerance the build states: the decoded colours are BYTE-IDENTICAL to the reference algorithm's
+    lossy JPEG path (libjpeg-turbo's ISLOW decoder with fancy upsampling, restated and pinned to its golden vectors), so
+    the PSNR of the GPU-decoded cloud equals the PSNR of the oracle-decoded cloud: tolerance 0 dB."""
+    cl = synth.gen_surface(9000, 1)
+    kp = K.default_params(octree_bits=7)
+    c = K.Codec(kp)
+    s = c.encode_batch([cl])[0]
+    d = c.decode_batch([s])[0]
+    rd, _ = oracle.decode(s)
+    assert np.array_equal(d[:, 16:20], rd[:, 16:20])                  # the tolerance is zero: same bytes
+    qg, qo = c.quality_metrics(cl, d), oracle.quality_metrics(cl, rd)
+    assert (qg.in_point_count, qg.out_point_count) == (qo.in_point_count, qo.out_point_count)
+    for f in ("symm_rms", "symm_hausdorff", "left_hausdorff", "right_hausdorff", "left_rms", "right_rms"):
+        assert abs(getattr(qg, f) - getattr(qo, f)) <= 1e-7 * max(1.0, abs(getattr(qo, f))), f
+    assert abs(qg.psnr_db - qo.psnr_db) < 1e-4
+    assert max(abs(a - b) for a, b in zip(qg.psnr_yuv, qo.psnr_yuv)) < 1e-6
+    # device-resident clouds, a cloud with non-finite points, and a larger pair (tiles of 2048 candidates, partial last tile)
+    torch = pytest.importorskip("torch")
+    big = synth.gen_surface(70001, 2)
+    big["x"][7] = np.nan
+    s2 = c.encode_batch([big])[0]
+    d2 = c.decode_batch([s2])[0]
+    q_host = c.quality_metrics(big, d2)
+    ta, tb = torch.from_numpy(big.view(np.uint8).reshape(-1)).cuda(), torch.from_numpy(d2.reshape(-1)).cuda()
+    q_dev = K.Quality()
+    c._check(c._L.ccv2_quality_metrics(c._h, ta.data_ptr(), 70001, tb.data_ptr(), d2.shape[0], __import__("ctypes").byref(q_dev)))
+    assert q_dev.symm_rms == q_host.symm_rms and list(q_dev.psnr_yuv) == list(q_host.psnr_yuv)
+    scipy_spatial = pytest.importorskip("scipy.spatial")
+    fin = np.isfinite(big["x"])
+    a = np.stack([big["x"], big["y"], big["z"]], 1)[fin].astype(np.float64)
+    b = d2[:, :12].copy().view(np.float32).reshape(-1, 3).astype(np.float64)
+    da, _ = scipy_spatial.cKDTree(b).query(a)
+    db, _ = scipy_spatial.cKDTree(a).query(b)
+    assert abs(q_host.left_rms - np.sqrt((da ** 2).sum() / 70001)) < 1e-6 and abs(q_host.right_rms - np.sqrt((db ** 2).mean())) < 1e-6
+    assert abs(q_host.symm_hausdorff - max(da.max(), db.max())) < 1e-6
+    assert q_host.psnr_yuv[0] > 20.0                                  # Q85 JPEG of a Morton-ordered colour strip: sanity floor, not the tolerance
     c.close()
