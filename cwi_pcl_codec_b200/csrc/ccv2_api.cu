@@ -79,9 +79,9 @@ struct Carver {
   size_t end() const { return (off + 255) & ~size_t(255); }
 };
 
-constexpr int MAX_STREAMS = 16;
-constexpr int SIDE_STREAMS = 8;          // group + side + copy + control streams stay within 32 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, see ccv2.h)
-constexpr int MAX_GROUP = 32;            // frames per group: the lane-per-stream encoder codes 32 frames per warp
+constexpr int MAX_STREAMS = 20;         // work streams: every STAGE of a group (encode, decode) takes the next one, so a group's decoder does not sit behind its encoder's queue
+constexpr int SIDE_STREAMS = 6;          // group + side + copy + control streams stay within 32 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, see ccv2.h)
+constexpr int MAX_GROUP = 64;            // frames per group (the lane-per-stream encoder codes 32 frames per warp: two warps per layer)
 constexpr int N_CALLS = 3;               // call contexts: two user calls in flight + one for the retry of a frame that overflowed its workspace
 
 struct DoneRc { int ticket, rc; };
@@ -101,7 +101,7 @@ struct CallCtx {
   DevBuf enc_frames, dec_frames, stage;                     // frame records (+ histograms); per-call staging for pageable destinations
   HostBuf h_frames, h_dframes;
   cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_setup = nullptr;
-  std::vector<cudaEvent_t> ev_h2d, ev_side, ev_done, ev_fin;
+  std::vector<cudaEvent_t> ev_h2d, ev_side, ev_done, ev_fin, ev_enc;
   // per-frame bookkeeping of the call (the caller's arrays must stay alive until the call is collected)
   std::vector<char> in_kind, out_kind, pts_kind;            // PtrKind of pts[i] / in[i], out[i], pts_out[i]
   std::vector<size_t> stage_off_stream, stage_off_pts;      // offsets into `stage` (pageable destinations)
@@ -140,7 +140,7 @@ struct ccv2_codec {
   uint32_t frame_id = 0;
   Ring fe, ll;
   CallCtx calls[N_CALLS];
-  int next_ticket = 1, user_calls = 0;
+  int next_ticket = 1, user_calls = 0; uint64_t stage_seq = 0;
   std::vector<DoneRc> done;              // results of collected calls, by ticket (ccv2_wait after the fact)
   int last_mode = -1;                      // mode of the call collected last
   EncParams last_enc_params;               // of the last encode (ccv2_get_output_cloud)
@@ -542,7 +542,7 @@ void ccv2_destroy(ccv2_codec *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (auto &x : c->calls) {
-    for (auto *v : { &x.ev_h2d, &x.ev_side, &x.ev_done, &x.ev_fin, &x.ev_trace }) for (auto ev : *v) cudaEventDestroy(ev);
+    for (auto *v : { &x.ev_h2d, &x.ev_side, &x.ev_done, &x.ev_fin, &x.ev_enc, &x.ev_trace }) for (auto ev : *v) cudaEventDestroy(ev);
     for (cudaEvent_t ev : { x.ev_start, x.ev_end, x.ev_setup }) if (ev) cudaEventDestroy(ev);
     x.enc_frames.release(); x.dec_frames.release(); x.stage.release(); x.h_frames.release(); x.h_dframes.release();
   }
@@ -689,7 +689,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
     }
   }
   const int NS = c->profiling ? 1 : (c->n_streams ? c->n_streams : MAX_STREAMS);
-  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(MAX_GROUP, (nframes + 31) / 32)));
+  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(MAX_GROUP, (nframes + 15) / 16)));
   const int ngroups = (nframes + G - 1) / G;
   x.G = G; x.ngroups = ngroups;
 
@@ -714,8 +714,8 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
   if (do_enc) fe.seq += ngroups;
   ll.seq += ngroups;
   CU(x.stage.ensure(stage_total + 256));
-  grow_events(x.ev_h2d, ngroups); grow_events(x.ev_side, 2 * (size_t)ngroups); grow_events(x.ev_done, ngroups); grow_events(x.ev_fin, ngroups);
-  if ((int)x.ev_h2d.size() < ngroups || (int)x.ev_side.size() < 2 * ngroups || (int)x.ev_done.size() < ngroups || (int)x.ev_fin.size() < ngroups) { c->err = "cudaEventCreate failed"; return CCV2_ERR_CUDA; }
+  grow_events(x.ev_h2d, ngroups); grow_events(x.ev_side, 2 * (size_t)ngroups); grow_events(x.ev_done, ngroups); grow_events(x.ev_fin, ngroups); grow_events(x.ev_enc, ngroups);
+  if ((int)x.ev_h2d.size() < ngroups || (int)x.ev_side.size() < 2 * ngroups || (int)x.ev_done.size() < ngroups || (int)x.ev_fin.size() < ngroups || (int)x.ev_enc.size() < ngroups) { c->err = "cudaEventCreate failed"; return CCV2_ERR_CUDA; }
 
   // ------------------------------------------------------------------ frame records
   EncFrame *hf = nullptr, *df = nullptr; DecFrame *hd = nullptr, *dd = nullptr;
@@ -821,7 +821,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
   bool copy_waits_setup = false;
   for (int g = 0; g < ngroups; g++) {
     const int sl = x.ll_set[g], sf = x.fe_set[g];
-    cudaStream_t st = c->streams[(x.ll_seq0 + g) % NS];
+    cudaStream_t st = c->streams[c->stage_seq++ % NS];
     const int f0 = g * G, gf = std::min(G, nframes - f0);
     const unsigned steered_grid = (unsigned)((gf + c->n_sm - 1) / c->n_sm * c->n_sm);
     CUQ(cudaStreamWaitEvent(st, x.ev_setup, 0));
@@ -885,6 +885,13 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
       mark(g, "encoded", st);
     }
     if (do_dec) {
+      // the decode stage of a round trip moves to the next work stream: its 0.2-0.4 s must not hold up the encode stage of
+      // the group that comes next on this one
+      if (rt && NS > 1) {
+        cudaStream_t sd = c->streams[c->stage_seq++ % NS];
+        CUQ(cudaEventRecord(x.ev_enc[g], st)); CUQ(cudaStreamWaitEvent(sd, x.ev_enc[g], 0));
+        st = sd;
+      }
       DecFrame *dg = dd + f0;
       size_t pmax = 1;
       for (int i = 0; i < gf; i++) {
@@ -900,7 +907,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
       // (8 frames to a warp) executes a third of the instructions and wins when the SMs' issue slots are the limit.
       if (use_lps_dec) {
         // tree layers on the group's stream, speculated colour layers on a side stream at the same time
-        cudaStream_t s2 = c->profiling ? st : c->side_streams[(x.ll_seq0 + g) % SIDE_STREAMS];
+        cudaStream_t s2 = c->profiling ? st : c->side_streams[c->stage_seq % SIDE_STREAMS];
         const unsigned lps_ctas = (unsigned)((gf + LPS_DEC_FRAMES - 1) / LPS_DEC_FRAMES);
         LAUNCH("dec_head_kernel", dec_head_kernel<<<gf, 32, 0, st>>>(dg));
         if (s2 != st) { CUQ(cudaEventRecord(x.ev_side[2 * g], st)); CUQ(cudaStreamWaitEvent(s2, x.ev_side[2 * g], 0)); }

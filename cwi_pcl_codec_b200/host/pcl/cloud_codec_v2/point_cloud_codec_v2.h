@@ -7,8 +7,12 @@
 #include "../pcl_shim.h"
 #include "../../../../include/ccv2.h"
 
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <iostream>
 #include <iterator>
+#include <unordered_map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -16,6 +20,9 @@
 namespace pcl { namespace io {
 
 template <typename PointT> class OctreePointCloudCodecV2;
+
+// pcl::io::BoundingBox of the reference (point_cloud_codec_v2.h:62-66: two Eigen::Vector4f); plain floats here
+struct BoundingBox { float min_xyz[4]; float max_xyz[4]; };
 
 template <>
 class OctreePointCloudCodecV2<pcl::PointXYZRGB> {
@@ -73,7 +80,8 @@ public:
     std::string s((std::istreambuf_iterator<char>(compressed_tree_data_in_arg)), std::istreambuf_iterator<char>());
     uint64_t cnt = 0;
     if (ccv2_peek_point_count(s.data(), s.size(), &cnt) != CCV2_OK) return;
-    cloud_arg->points.resize(cnt ? cnt : 1);
+    try { cloud_arg->points.resize(cnt ? cnt : 1); }
+    catch (const std::bad_alloc &) { last_error_ = "decodePointCloud: cannot allocate the decoded cloud"; cloud_arg->points.clear(); return; }
     const void *i = s.data();
     size_t il = s.size(), cap = cloud_arg->points.size(), n = 0;
     void *o = cloud_arg->points.data();
@@ -99,9 +107,97 @@ public:
 
   // codec.h:193-197
   uint64_t *getPerformanceMetrics() { return metrics_; }
+
+  // ---- the three statics evaluate_compression calls around the codec (codec.h:216-227, impl.hpp:1840-1986).  Host-side
+  // float arithmetic in the reference's order: they run once per group on the caller's clouds, outside the hot path.
+  // impl.hpp:1871-1966: the first frame's bounding box, expanded by bb_expand_factor on every side, is kept until a frame
+  // does not fit strictly inside it; every frame is mapped to (p - min) / (max - min) in float; the LAST box is returned.
+  static BoundingBox normalize_pointclouds(std::vector<PointCloudPtr> &point_clouds, std::vector<BoundingBox> &bounding_boxes,
+                                           double bb_expand_factor, unsigned int debug_level = 0) {
+    float mn_bb[3] = {1000.f, 1000.f, 1000.f}, mx_bb[3] = {-1000.f, -1000.f, -1000.f};
+    bool is_bb_init = false;
+    bounding_boxes.resize(point_clouds.size());
+    for (size_t k = 0; k < point_clouds.size(); k++) {
+      float mn[3], mx[3];
+      min_max_3d(*point_clouds[k], mn, mx);
+      if (!((mn[0] > mn_bb[0]) && (mn[1] > mn_bb[1]) && (mn[2] > mn_bb[2]))) is_bb_init = false;
+      if (!((mx[0] < mx_bb[0]) && (mx[1] < mx_bb[1]) && (mx[2] < mx_bb[2]))) is_bb_init = false;
+      if (!is_bb_init) {
+        for (int a = 0; a < 3; a++) {                                       // float - double * float, stored as float (impl.hpp:1917-1923)
+          const float ext = std::fabs(mx[a] - mn[a]);
+          mn_bb[a] = (float)((double)mn[a] - bb_expand_factor * (double)ext);
+          mx_bb[a] = (float)((double)mx[a] + bb_expand_factor * (double)ext);
+        }
+        is_bb_init = true;
+        if (debug_level > 0) std::cout << "re-intialized bounding box !!! " << std::endl;
+      }
+      float dyn[3];
+      for (int a = 0; a < 3; a++) { dyn[a] = mx_bb[a] - mn_bb[a]; bounding_boxes[k].min_xyz[a] = mn_bb[a]; bounding_boxes[k].max_xyz[a] = mx_bb[a]; }
+      bounding_boxes[k].min_xyz[3] = bounding_boxes[k].max_xyz[3] = 0.f;
+      for (auto &p : point_clouds[k]->points) {                            // impl.hpp:1936-1946: offset, then dynamic range
+        p.x -= mn_bb[0]; p.y -= mn_bb[1]; p.z -= mn_bb[2];
+        p.x /= dyn[0]; p.y /= dyn[1]; p.z /= dyn[2];
+      }
+    }
+    BoundingBox bb;
+    for (int a = 0; a < 3; a++) { bb.min_xyz[a] = mn_bb[a]; bb.max_xyz[a] = mx_bb[a]; }
+    bb.min_xyz[3] = 0.f; bb.max_xyz[3] = 0.f;
+    return bb;
+  }
+  // impl.hpp:1968-1986
+  static void restore_scaling(PointCloudPtr &point_cloud, const BoundingBox &bb) {
+    const float dyn[3] = {bb.max_xyz[0] - bb.min_xyz[0], bb.max_xyz[1] - bb.min_xyz[1], bb.max_xyz[2] - bb.min_xyz[2]};
+    for (auto &p : point_cloud->points) {
+      p.x *= dyn[0]; p.y *= dyn[1]; p.z *= dyn[2];
+      p.x += bb.min_xyz[0]; p.y += bb.min_xyz[1]; p.z += bb.min_xyz[2];
+    }
+  }
+  // impl.hpp:1840-1866 -> [PCL] RadiusOutlierRemoval(setRadiusSearch(radius), setMinNeighborsInRadius(min_points)): a point
+  // stays when MORE than min_points points (itself included) lie within `radius`.  Exact, through a uniform grid of
+  // radius-sized cells; non-finite points are dropped like PCL's filter does.
+  static void remove_outliers(std::vector<PointCloudPtr> &point_clouds, int min_points, double radius, unsigned int debug_level = 0) {
+    if (min_points <= 0) return;
+    for (auto &pc : point_clouds) {
+      const auto &pts = pc->points;
+      std::unordered_map<uint64_t, std::vector<uint32_t> > grid;
+      auto cell = [&](float v) { return (int64_t)std::floor((double)v / radius); };
+      auto key = [](int64_t x, int64_t y, int64_t z) { return ((uint64_t)(x & 0x1FFFFF) << 42) | ((uint64_t)(y & 0x1FFFFF) << 21) | (uint64_t)(z & 0x1FFFFF); };
+      for (uint32_t i = 0; i < pts.size(); i++) if (std::isfinite(pts[i].x) && std::isfinite(pts[i].y) && std::isfinite(pts[i].z)) grid[key(cell(pts[i].x), cell(pts[i].y), cell(pts[i].z))].push_back(i);
+      PointCloudPtr out(new PointCloud());
+      const float r2 = (float)(radius * radius);
+      for (uint32_t i = 0; i < pts.size(); i++) {
+        const auto &p = pts[i];
+        if (!(std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z))) continue;
+        int k = 0;
+        const int64_t cx = cell(p.x), cy = cell(p.y), cz = cell(p.z);
+        for (int64_t dx = -1; dx <= 1 && k <= min_points; dx++) for (int64_t dy = -1; dy <= 1; dy++) for (int64_t dz = -1; dz <= 1; dz++) {
+          auto it = grid.find(key(cx + dx, cy + dy, cz + dz));
+          if (it == grid.end()) continue;
+          for (uint32_t j : it->second) { const float ex = p.x - pts[j].x, ey = p.y - pts[j].y, ez = p.z - pts[j].z; if (ex * ex + ey * ey + ez * ez <= r2) k++; }
+        }
+        if (k > min_points) out->points.push_back(p);
+      }
+      if (debug_level > 2) std::cout << "filtered out a total of: " << pts.size() - out->points.size() << " outliers" << std::endl;
+      out->width = (uint32_t)out->points.size(); out->height = 1; out->is_dense = false;
+      pc = out;
+    }
+  }
+  // computeQualityMetric (quality_metrics_impl.hpp:82-239) on this codec's device
+  bool computeQuality(const PointCloud &cloud_a, const PointCloud &cloud_b, ccv2_quality &q) {
+    ensure();
+    return ccv2_quality_metrics(h_, cloud_a.points.data(), cloud_a.points.size(), cloud_b.points.data(), cloud_b.points.size(), &q) == CCV2_OK;
+  }
   const std::string &lastError() const { return last_error_; }
 
 private:
+  static void min_max_3d(const PointCloud &c, float mn[3], float mx[3]) {   // [PCL] getMinMax3D: finite points only
+    mn[0] = mn[1] = mn[2] = 3.4028235e38f; mx[0] = mx[1] = mx[2] = -3.4028235e38f;
+    for (const auto &p : c.points) {
+      if (!(std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z))) continue;
+      mn[0] = std::min(mn[0], p.x); mn[1] = std::min(mn[1], p.y); mn[2] = std::min(mn[2], p.z);
+      mx[0] = std::max(mx[0], p.x); mx[1] = std::max(mx[1], p.y); mx[2] = std::max(mx[2], p.z);
+    }
+  }
   void ensure() {
     if (h_) return;
     if (ccv2_create(&p_, device_, &h_) != CCV2_OK) throw std::runtime_error(std::string("ccv2_create: ") + ccv2_last_error(nullptr));
