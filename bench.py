@@ -181,8 +181,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--mode", default="roundtrip", choices=["roundtrip", "decode"],
-                    help="roundtrip: the headline metric (encode+decode); decode: BASELINE configs[4], decode-only on oracle-produced streams resident in device memory")
+    ap.add_argument("--mode", default="roundtrip", choices=["roundtrip", "decode", "tiles"],
+                    help="roundtrip: the headline metric (encode+decode); decode: BASELINE configs[4], decode-only on oracle-produced streams resident in device memory; "
+                         "tiles: BASELINE configs[3], one dense 4M-point frame at octree_bits 12 cut into root-octant tiles (sharded over the ranks, streams gathered on rank 0)")
+    ap.add_argument("--tile-bits", type=int, default=3, choices=[3, 6])
     ap.add_argument("--frames", type=int, default=int(os.environ.get("BENCH_FRAMES", "0")),
                     help="frames per step per GPU (0: as many as fit in device memory, at most 1024 -- the serial entropy stage is latency bound, so throughput grows with the frames in flight)")
     ap.add_argument("--points", type=int, default=1000000)
@@ -210,6 +212,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.mode == "decode":
         return run_decode_mode(args, torch, dist, K, rank, world, local, dev)
+    if args.mode == "tiles":
+        return run_tiles_mode(args, torch, dist, K, rank, world, local, dev)
     NP = args.points
     F = args.frames
     cap = 4 * NP + (1 << 16)
@@ -473,6 +477,94 @@ def run_decode_mode(args, torch, dist, K, rank, world, local, dev):
                 "roofline": {"bound": "hbm", "achieved": alg * F / (t_dev / args.steps) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg * F / (t_dev / args.steps) / 1e9 / peak,
                              "traffic": None, "note": "step level: algorithmic decode bytes (S + 32 V) x frames per step / step time"},
                 "api": "ccv2_submit_decode x K (two calls in flight), ccv2_wait"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_tiles_mode(args, torch, dist, K, rank, world, local, dev):
+    """BASELINE configs[3]: a dense 4M-point frame (G-surf), octree_bits 12, JPEG quality sweep 60..95, cut into root-octant
+    tiles.  A step = one frame: every rank partitions the frame (device resident), encodes ITS tiles (tile t on rank
+    t mod world), the streams are gathered on rank 0 (all_gather of sizes + point-to-point payloads over NCCL), and every
+    rank decodes its own tiles again.  Strong scaling of ONE frame: what is reported is the frame's latency."""
+    from cwi_pcl_codec_b200 import tiles as T
+    NP = args.points if args.points != 1000000 else 4000000
+    bits = args.bits if args.bits != 11 else 12
+    tb = args.tile_bits
+    nt = 1 << tb
+    fr = gen_frames(args.kind, NP, [0])[0]
+    d_in = torch.from_numpy(fr.view(np.uint8).reshape(-1)).to(dev)
+    cap = 2 * NP + (1 << 20)
+    mine = T.owned_tiles(tb, rank, world)
+    d_str = {t: torch.empty(cap // max(1, nt // 8) + (1 << 20), dtype=torch.uint8, device=dev) for t in mine}
+    d_out = {t: torch.empty(NP * 32 // max(1, nt // 4) + (1 << 20), dtype=torch.uint8, device=dev) for t in mine}
+    results = {}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for q in (85, 60, 65, 70, 75, 80, 90, 95):
+        codec = K.Codec(K.default_params(octree_bits=bits, jpeg_quality=q), device=local)
+        outp = [d_str[t].data_ptr() if t in d_str else None for t in range(nt)]
+        caps = [d_str[t].numel() if t in d_str else 0 for t in range(nt)]
+
+        def step():
+            lens, npts = codec.encode_tiles_raw(d_in.data_ptr(), NP, tb, outp, caps, rank, world)
+            launches = codec.last_launch_count
+            if world > 1:                                           # the exchange step: variable-length streams to the writer rank
+                T.gather_tile_streams({t: d_str[t][:lens[t]].cpu().numpy().tobytes() for t in mine if lens[t]}, tb, dist, device=dev)
+            live = [t for t in mine if lens[t]]
+            ns = codec.decode_batch_raw([d_str[t].data_ptr() for t in live], [lens[t] for t in live], [d_out[t].data_ptr() for t in live], [d_out[t].numel() // 32 for t in live]) if live else []
+            return lens, npts, sum(ns), launches + codec.last_launch_count
+        steps = args.steps if q == 85 else 2
+        for _ in range(args.warmup if q == 85 else 1):
+            step()
+        sampler = ClockSampler(local) if q == 85 else None
+        barrier()
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        launches = 0
+        for _ in range(steps):
+            lens, npts, nvox, l = step(); launches += l
+        barrier()
+        wall = reduce_max(time.perf_counter() - t0, dist if world > 1 else None, dev)
+        clocks = sampler.stop() if sampler else None
+        tot = torch.tensor([float(sum(lens[t] for t in mine)), float(nvox)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        results[q] = {"ms_per_frame": wall / steps * 1e3, "stream_bytes": float(tot[0]), "voxels": float(tot[1]), "launches": launches, "clocks": clocks, "steps": steps}
+        codec.close()
+    # the same frame as ONE stream (no tiles), for the latency comparison (rank 0 only, Q85)
+    plain = None
+    if rank == 0:
+        codec = K.Codec(K.default_params(octree_bits=bits, jpeg_quality=85), device=local)
+        s1 = torch.empty(cap, dtype=torch.uint8, device=dev); o1 = torch.empty(NP * 32, dtype=torch.uint8, device=dev)
+        best = [1e30, 1e30]
+        for _ in range(3):
+            l1 = codec.encode_batch_raw([d_in.data_ptr()], [NP], [s1.data_ptr()], [cap]); best[0] = min(best[0], codec.last_device_ms)
+            codec.decode_batch_raw([s1.data_ptr()], l1, [o1.data_ptr()], [NP]); best[1] = min(best[1], codec.last_device_ms)
+        plain = {"encode_ms": best[0], "decode_ms": best[1], "stream_bytes": l1[0]}
+        codec.close()
+    if rank == 0:
+        r = results[85]
+        line = {"metric": "Mpoints/s encode+decode of ONE dense frame in root-octant tile mode (BASELINE configs[3]); every tile stream bit-exact vs the reference encoder on that tile",
+                "value": NP / (r["ms_per_frame"] / 1e3) / 1e6, "unit": "Mpoints/s", "n_gpus": world, "steps": r["steps"], "warmup": args.warmup,
+                "ms_per_step": r["ms_per_frame"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/u32/f64 (integer codec, FP64 keys)", "data": "synthetic",
+                "config": {"workload": "BASELINE.json configs[3]: one %d-point G-%s frame, octree_bits %d, JPEG snake Q85 (sweep 60..95 below), %d tiles (tile t on rank t mod %d), streams gathered on rank 0, every rank decodes its tiles"
+                           % (NP, args.kind, bits, nt, world), "tile_bits": tb, "points_per_frame": NP,
+                           "cache": "the frame (%.0f MB) exceeds the 126 MB L2" % (NP * 32 / 1e6)},
+                "timing": "wall clock per frame (synchronous calls: partition + encode + gather + decode), max over ranks",
+                "single_frame_latency_ms": {"tiled_encode_plus_decode": r["ms_per_frame"], "untiled_encode": plain["encode_ms"], "untiled_decode": plain["decode_ms"]},
+                "speedup_vs_untiled": (plain["encode_ms"] + plain["decode_ms"]) / r["ms_per_frame"],
+                "stream_bytes_tiled": r["stream_bytes"], "stream_bytes_untiled": plain["stream_bytes"], "voxels": r["voxels"],
+                "jpeg_quality_sweep": {str(q): {"ms_per_frame": results[q]["ms_per_frame"], "stream_bytes": results[q]["stream_bytes"]} for q in sorted(results)},
+                "clocks": r["clocks"], "gpu_launches": int(r["launches"])}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

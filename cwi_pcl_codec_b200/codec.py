@@ -75,6 +75,8 @@ def load_library():
     L.ccv2_wait.argtypes = [C.c_void_p, C.c_int]
     L.ccv2_timer_start.argtypes = [C.c_void_p]
     L.ccv2_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.ccv2_split_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, szp]
+    L.ccv2_encode_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, vpp, szp, szp, szp]
     L.ccv2_quality_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(Quality)]
     L.ccv2_peek_point_count.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
     L.ccv2_get_metrics.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
@@ -106,7 +108,7 @@ EXPORTED_SYMBOLS = ["ccv2_default_params", "ccv2_create", "ccv2_destroy", "ccv2_
                     "ccv2_set_frame_id", "ccv2_get_frame_id", "ccv2_last_launch_count", "ccv2_last_device_ms",
                     "ccv2_last_error", "ccv2_status_string", "ccv2_host_alloc", "ccv2_host_free", "ccv2_debug_fetch", "ccv2_get_output_cloud",
                     "ccv2_set_profiling", "ccv2_get_profile", "ccv2_submit_encode", "ccv2_submit_decode", "ccv2_submit_roundtrip",
-                    "ccv2_wait", "ccv2_timer_start", "ccv2_timer_stop", "ccv2_quality_metrics"]
+                    "ccv2_wait", "ccv2_timer_start", "ccv2_timer_stop", "ccv2_quality_metrics", "ccv2_split_tiles", "ccv2_encode_tiles"]
 
 
 def _status_string(s):
@@ -290,6 +292,35 @@ class Codec:
         t = C.c_int()
         self._check(self._L.ccv2_submit_decode(self._h, n, a_in, a_n, a_out, a_cap, a_len, C.byref(t)))
         return Pending(self, t.value, (a_in, a_n, a_out, a_cap), lambda: list(a_len))
+
+    # ---- tile mode (BASELINE configs[3]): one frame -> one reference-format stream per spatial tile
+    def split_tiles(self, cloud, tile_bits):
+        """Stable partition of a frame into 2^tile_bits tiles: (points grouped by tile, offsets[2^tile_bits + 1])."""
+        a = np.ascontiguousarray(cloud)
+        n = a.nbytes // 32
+        out = np.zeros((max(n, 1), 32), np.uint8)
+        offs = (C.c_size_t * ((1 << tile_bits) + 1))()
+        self._check(self._L.ccv2_split_tiles(self._h, a.ctypes.data if n else None, n, tile_bits, out.ctypes.data, offs))
+        return out[:n], list(offs)
+
+    def encode_tiles_raw(self, ptr, n, tile_bits, out_ptrs, out_caps, first_tile=0, tile_step=1):
+        nt = 1 << tile_bits
+        a_out = (C.c_void_p * nt)(*out_ptrs)
+        a_cap = (C.c_size_t * nt)(*out_caps)
+        a_len = (C.c_size_t * nt)()
+        a_np = (C.c_size_t * nt)()
+        self._check(self._L.ccv2_encode_tiles(self._h, ptr, n, tile_bits, first_tile, tile_step, a_out, a_cap, a_len, a_np))
+        return list(a_len), list(a_np)
+
+    def encode_tiles(self, cloud, tile_bits, first_tile=0, tile_step=1):
+        """Streams of the tiles first_tile, first_tile + tile_step, ... of one frame: ({tile: bytes}, points per tile)."""
+        a = np.ascontiguousarray(cloud)
+        n = a.nbytes // 32
+        nt = 1 << tile_bits
+        cap = min(self._L.ccv2_max_compressed_size(n), 6 * n + (1 << 16))
+        bufs = [np.empty(cap, np.uint8) if (t >= first_tile and (t - first_tile) % tile_step == 0) else None for t in range(nt)]
+        lens, npts = self.encode_tiles_raw(a.ctypes.data if n else None, n, tile_bits, [b.ctypes.data if b is not None else None for b in bufs], [cap] * nt, first_tile, tile_step)
+        return {t: bufs[t][:lens[t]].tobytes() for t in range(nt) if bufs[t] is not None and lens[t]}, npts
 
     def quality_metrics(self, cloud_a, cloud_b):
         """computeQualityMetric(original, decoded) -> Quality (quality_metrics_impl.hpp:82-239)."""

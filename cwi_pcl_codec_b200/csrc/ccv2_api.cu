@@ -27,6 +27,10 @@
 #include "lines_kernels.cuh"
 #include "lines_dec_kernels.cuh"
 #include "quality_kernels.cuh"
+#include "tile_kernels.cuh"
+#include "detail_kernels.cuh"
+
+#include <cuda.h>
 
 #include <algorithm>
 #include <cmath>
@@ -79,9 +83,11 @@ struct Carver {
   size_t end() const { return (off + 255) & ~size_t(255); }
 };
 
-constexpr int MAX_STREAMS = 20;         // work streams: every STAGE of a group (encode, decode) takes the next one, so a group's decoder does not sit behind its encoder's queue
+constexpr int MAX_STREAMS = 20;         // work streams: long-lived set s always runs on stream s mod 20 -- a group waits for the previous user of its set anyway,
+                                         // so with at most 20 sets no group ever queues behind a stream that is busy with an unrelated one
 constexpr int SIDE_STREAMS = 6;          // group + side + copy + control streams stay within 32 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, see ccv2.h)
-constexpr int MAX_GROUP = 64;            // frames per group (the lane-per-stream encoder codes 32 frames per warp: two warps per layer)
+constexpr int MAX_GROUP = 128;           // frames per group.  The serial range-coder kernels are latency bound (0.1-0.4 s per launch whatever the frame count),
+                                         // so throughput = frames per launch x launches in flight: large groups, one stream each (measured: 32-frame groups 650, 64 1040-1270 Mpoints/s)
 constexpr int N_CALLS = 3;               // call contexts: two user calls in flight + one for the retry of a frame that overflowed its workspace
 
 struct DoneRc { int ticket, rc; };
@@ -101,7 +107,8 @@ struct CallCtx {
   DevBuf enc_frames, dec_frames, stage;                     // frame records (+ histograms); per-call staging for pageable destinations
   HostBuf h_frames, h_dframes;
   cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_setup = nullptr;
-  std::vector<cudaEvent_t> ev_h2d, ev_side, ev_done, ev_fin, ev_enc;
+  cudaStream_t end_stream = nullptr;                        // gathers the call's group events; the control stream must stay free for the next call's set-up
+  std::vector<cudaEvent_t> ev_h2d, ev_side, ev_done, ev_fin, ev_enc, ev_hop;
   // per-frame bookkeeping of the call (the caller's arrays must stay alive until the call is collected)
   std::vector<char> in_kind, out_kind, pts_kind;            // PtrKind of pts[i] / in[i], out[i], pts_out[i]
   std::vector<size_t> stage_off_stream, stage_off_pts;      // offsets into `stage` (pageable destinations)
@@ -124,9 +131,14 @@ struct ccv2_codec {
   int use_ring = 1;                       // pipeline the DFS walk behind the range decoder (CCV2_NO_RING=1 disables: debugging)
   int n_streams = 0, group = 0;           // CCV2_STREAMS / CCV2_GROUP overrides (0 = automatic)
   int inflight_max = 2048;                // frames the long-lived ring may hold (CCV2_INFLIGHT); memory permitting
-  int fe_frames = 128;                    // frames the front-end ring holds (CCV2_FE_FRAMES)
+  int fe_frames = 256;                    // frames the front-end ring holds (CCV2_FE_FRAMES); at least two sets
   cudaStream_t main_stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr, fin_stream = nullptr;
   cudaStream_t streams[MAX_STREAMS] = {};
+  cudaStream_t ser_streams[MAX_STREAMS] = {};     // green contexts on: the same slots on the serial partition's SMs; off: aliases of streams[]
+  int green_sms = 0;                      // SMs set aside for the latency-bound range-coder kernels (CCV2_GREEN; 0 = no partition)
+  CUgreenCtx green_ser = nullptr, green_par = nullptr;
+  CUresult (*drv_green_stream_create)(CUstream *, CUgreenCtx, unsigned int, int) = nullptr;
+  CUresult (*drv_green_destroy)(CUgreenCtx) = nullptr;
   cudaStream_t side_streams[SIDE_STREAMS] = {};   // colour layer of a group, concurrent with its tree layer (lane-per-stream decoder)
   int lps_dec = -1;                       // lane-per-stream range decoder: -1 auto (round trips only), 0 off, 1 on (CCV2_LPS_DEC)
   cudaEvent_t ev_id_chain = nullptr; bool id_chain_used = false;     // frame ids are sequential: a group's setup waits for the previous group's
@@ -145,6 +157,7 @@ struct ccv2_codec {
   int last_mode = -1;                      // mode of the call collected last
   EncParams last_enc_params;               // of the last encode (ccv2_get_output_cloud)
   DevBuf out_cloud;                        // staging for ccv2_get_output_cloud into host memory
+  DevBuf tile_pts, tile_aux;               // tile mode: the partitioned frame, counters
   std::vector<EncFrame> enc_host;          // host mirror of the last encode call's frame records (with device pointers)
   std::vector<char> enc_host_valid;        // per frame: its ring sets were not handed on to a later group
   uint64_t metrics[3] = {0, 0, 0};
@@ -277,8 +290,13 @@ size_t tree_cap_for(size_t n, bool boost) {
 size_t cpay_cap_for(size_t n, bool boost) { return ((boost ? 8 * n + 65536 : 3 * n + n / 4 + 8192) + 255) & ~size_t(255); }   // raw colour types need 3 n
 size_t cen_cap_for(size_t n) { return ((3 * n + 256) + 255) & ~size_t(255); }
 size_t rc_cap_for(size_t raw_cap) { return ((raw_cap + raw_cap / 8 + 4096) + 255) & ~size_t(255); }
-size_t stream_cap_for(size_t n, bool cen, bool boost) {
-  return FRAME_HDR_BYTES + 8 + rc_cap_for(tree_cap_for(n, boost)) + (cen ? 4 + rc_cap_for(cen_cap_for(n)) : 0) + 8 + rc_cap_for(cpay_cap_for(n, boost));
+// detail mode: int-coder table entries (u64) and the coded counts; 65536 entries hold voxels of up to 32767 points
+size_t itab_cap_for(size_t n, bool boost) { return boost ? 4 * (n + 2) : std::min<size_t>(4 * (n + 2), 65536); }
+size_t rc_int_cap_for(size_t n, bool boost) { return ((9 + 8 * itab_cap_for(n, boost) + 8 * n + 64) + 255) & ~size_t(255); }
+size_t diff_cap_for(size_t n) { return ((3 * n + 64) + 255) & ~size_t(255); }
+size_t stream_cap_for(size_t n, bool cen, bool boost, bool detail = false) {
+  return FRAME_HDR_BYTES + 8 + rc_cap_for(tree_cap_for(n, boost)) + (cen ? 4 + rc_cap_for(cen_cap_for(n)) : 0) + 8 + rc_cap_for(cpay_cap_for(n, boost)) +
+         (detail ? 8 + rc_int_cap_for(n, boost) + 2 * (8 + rc_cap_for(diff_cap_for(n))) : 0);
 }
 
 // front-end workspace of one frame (ring `fe`): dead once the colour payload is complete
@@ -293,7 +311,7 @@ size_t carve_fe(uint8_t *base, size_t n, EncFrame *f, const ccv2_params &prm, bo
   // --- zero-initialised region first
   uint32_t *ghist = cv.take<uint32_t>(8 * 256);
   uint32_t *sort_status = cv.take<uint32_t>((size_t)8 * tiles * 256);
-  uint64_t *scan_status = cv.take<uint64_t>((size_t)3 * scan_tiles);
+  uint64_t *scan_status = cv.take<uint64_t>((size_t)4 * scan_tiles);
   uint32_t *jbits = cv.take<uint32_t>(jbits_words + 16);
   const size_t z1 = cv.end();
   // --- rest
@@ -306,8 +324,10 @@ size_t carve_fe(uint8_t *base, size_t n, EncFrame *f, const ccv2_params &prm, bo
   int16_t *coef = cv.take<int16_t>((lines ? (n / 16 + 260) : mcu_h * 16) * 384 + 64);
   uint8_t *line_slots = cv.take<uint8_t>(lines ? lines_cap * LINE_SLOT_BYTES : 16);
   uint32_t *line_len = cv.take<uint32_t>(lines ? lines_cap : 4), *line_off = cv.take<uint32_t>(lines ? lines_cap : 4);
+  uint32_t *cd_off = cv.take<uint32_t>(prm.do_voxel_grid_downsampling ? 4 : n + 8);
   uint8_t *pts_stage = cv.take<uint8_t>(host_in ? 32 * n + 32 : 16);
   if (f) {
+    f->cd_off = cd_off;
     f->ghist = ghist; f->sort_status = sort_status; f->tiles_max = tiles; f->scan_status = scan_status; f->scan_tiles_max = scan_tiles;
     f->jbits_buf = jbits; f->jbits_cap_words = (uint32_t)jbits_words;
     f->keys[0] = k0; f->keys[1] = k1; f->vals[0] = v0; f->vals[1] = v1;
@@ -322,29 +342,37 @@ size_t carve_fe(uint8_t *base, size_t n, EncFrame *f, const ccv2_params &prm, bo
 }
 // long-lived encoder buffers of one frame (ring `ll`): the stream first (a round trip's decoder reads it while its own
 // workspace lies over the rest, which is dead once the stream is assembled); *stream_end = offset where the rest starts
-size_t carve_enc_ll(uint8_t *base, size_t n, EncFrame *f, bool cen, bool boost, size_t *stream_end) {
+size_t carve_enc_ll(uint8_t *base, size_t n, EncFrame *f, bool cen, bool boost, size_t *stream_end, bool detail) {
   Carver cv(base);
-  uint8_t *stream = cv.take<uint8_t>(stream_cap_for(n, cen, boost));
+  uint8_t *stream = cv.take<uint8_t>(stream_cap_for(n, cen, boost, detail));
   if (stream_end) *stream_end = cv.end();
   uint8_t *tree = cv.take<uint8_t>(tree_cap_for(n, boost));
   uint8_t *cenb = cv.take<uint8_t>(cen ? cen_cap_for(n) : 256);
   uint8_t *cpay = cv.take<uint8_t>(cpay_cap_for(n, boost));
   uint8_t *rc0 = cv.take<uint8_t>(cen ? rc_cap_for(cen_cap_for(n)) : 256);
   uint8_t *rc1 = cv.take<uint8_t>(rc_cap_for(cpay_cap_for(n, boost)));
+  uint32_t *counts = cv.take<uint32_t>(detail ? n + 8 : 4);
+  uint8_t *pdiff = cv.take<uint8_t>(detail ? diff_cap_for(n) : 16), *cdiff = cv.take<uint8_t>(detail ? diff_cap_for(n) : 16);
+  uint64_t *itab = cv.take<uint64_t>(detail ? itab_cap_for(n, boost) + 8 : 2);
+  uint8_t *rc_int = cv.take<uint8_t>(detail ? rc_int_cap_for(n, boost) : 16);
+  uint8_t *rc2 = cv.take<uint8_t>(detail ? rc_cap_for(diff_cap_for(n)) : 16), *rc3 = cv.take<uint8_t>(detail ? rc_cap_for(diff_cap_for(n)) : 16);
   if (f) {
+    f->counts = counts; f->pdiff = pdiff; f->cdiff = cdiff; f->itab = itab; f->itab_cap = detail ? (uint32_t)itab_cap_for(n, boost) : 0;
+    f->rc_int = rc_int; f->rc_int_cap = detail ? (uint32_t)rc_int_cap_for(n, boost) : 0;
+    f->rc_tmp[2] = rc2; f->rc_tmp[3] = rc3; f->rc_tmp_cap[2] = f->rc_tmp_cap[3] = detail ? (uint32_t)rc_cap_for(diff_cap_for(n)) : 0;
     f->tree = tree; f->tree_cap = (uint32_t)tree_cap_for(n, boost) - 64; f->cen = cenb; f->cpay = cpay; f->cpay_cap = (uint32_t)cpay_cap_for(n, boost) - 64;
     f->rc_tmp[0] = rc0; f->rc_tmp[1] = rc1; f->rc_tmp_cap[0] = (uint32_t)(cen ? rc_cap_for(cen_cap_for(n)) : 0); f->rc_tmp_cap[1] = (uint32_t)rc_cap_for(cpay_cap_for(n, boost));
-    f->stream = stream; f->stream_cap = stream_cap_for(n, cen, boost);
+    f->stream = stream; f->stream_cap = stream_cap_for(n, cen, boost, detail);
   }
   return cv.end();
 }
 // decoder workspace of one frame: ncap = voxels it may hold, tcap / ccap = tree / colour payload bytes
-size_t carve_dec(uint8_t *base, size_t ncap, size_t tcap, size_t ccap, DecFrame *f, size_t *zero_bytes, bool lines) {
+size_t carve_dec(uint8_t *base, size_t ncap, size_t tcap, size_t ccap, DecFrame *f, size_t *zero_bytes, bool lines, size_t dpts /* detail mode: points the frame may hold, 0 = no detail buffers */, bool boost) {
   Carver cv(base);
   const size_t lines_cap = lines ? ncap / LINE_PX + 2 : 0;
   const size_t img_h = ncap / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = lines ? (lines_cap * LINE_MCU_STRIDE + LINE_MCU_STRIDE) * 6 : mcu_h * 16 * 6;
   const uint32_t scan_tiles = (uint32_t)(ncap / NODE_THREADS) + 8;
-  uint64_t *scan_status = cv.take<uint64_t>(2 * (size_t)scan_tiles);
+  uint64_t *scan_status = cv.take<uint64_t>(3 * (size_t)scan_tiles);
   int16_t *coef = cv.take<int16_t>(nblocks * 64 + 64);
   const size_t z1 = cv.end();
   uint8_t *tree = cv.take<uint8_t>(tcap + 64);
@@ -367,7 +395,13 @@ size_t carve_dec(uint8_t *base, size_t ncap, size_t tcap, size_t ccap, DecFrame 
   uint32_t *line_off = cv.take<uint32_t>(lines_cap + 4), *line_len = cv.take<uint32_t>(lines_cap + 4), *line_w = cv.take<uint32_t>(lines_cap + 4);
   uint16_t *line_qt = cv.take<uint16_t>(lines_cap * 128 + 128);
   uint8_t *line_planes = cv.take<uint8_t>(lines_cap * 8192 + 256);
+  uint32_t *counts = cv.take<uint32_t>(dpts ? ncap + 8 : 4);
+  uint64_t *dleaf_key = cv.take<uint64_t>(dpts ? ncap + 8 : 2);
+  uint8_t *pdiff = cv.take<uint8_t>(dpts ? diff_cap_for(dpts) : 16), *cdiff = cv.take<uint8_t>(dpts ? diff_cap_for(dpts) : 16);
+  uint64_t *itab = cv.take<uint64_t>(dpts ? itab_cap_for(dpts, boost) + 8 : 2);
   if (f) {
+    f->counts = counts; f->counts_cap = dpts ? (uint32_t)ncap : 0; f->dleaf_key = dleaf_key; f->pdiff = pdiff; f->cdiff = cdiff; f->pdiff_cap = dpts ? 3 * dpts : 0;
+    f->itab = itab; f->itab_cap = dpts ? (uint32_t)itab_cap_for(dpts, boost) : 0;
     f->scan_status = scan_status; f->scan_tiles_max = scan_tiles; f->coef = coef; f->coef_cap_blocks = (uint32_t)nblocks;
     f->tree = tree; f->tree_cap = (uint32_t)std::min(tcap, (size_t)0xFFFFFF00u); f->cen = cen; f->cen_cap = (uint32_t)cen_cap_for(ncap) - 64;
     f->col = col; f->col_cap = (uint32_t)std::min(ccap, (size_t)0xFFFFFF00u);
@@ -383,7 +417,6 @@ size_t carve_dec(uint8_t *base, size_t ncap, size_t tcap, size_t ccap, DecFrame 
 int check_params(const ccv2_params *p, std::string &err) {
   if (!p) { err = "null params"; return CCV2_ERR_ARG; }
   if (p->profile != CCV2_MANUAL_CONFIGURATION) { err = "only MANUAL_CONFIGURATION is implemented"; return CCV2_ERR_UNSUPPORTED; }
-  if (!p->do_voxel_grid_downsampling) { err = "detail mode (doVoxelGridDownDownSampling=false) is not implemented"; return CCV2_ERR_UNSUPPORTED; }
   if (!(p->octree_resolution > 0)) { err = "octree_resolution must be > 0"; return CCV2_ERR_ARG; }
   if (p->color_coding_type > 3) { err = "unknown colorCodingType"; return CCV2_ERR_ARG; }
   if (p->color_bit_resolution > 8) { err = "colorBitResolution > 8"; return CCV2_ERR_ARG; }
@@ -422,8 +455,9 @@ bool peek_header(const uint8_t *b, size_t len, PeekInfo &o) {
 
 // ================================================================================================ handle life cycle
 static void drain(ccv2_codec *c) {                           // waits for everything the codec has enqueued
+  for (auto &x : c->calls) if (x.end_stream) cudaStreamSynchronize(x.end_stream);
   cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->d2h_stream);
-  for (int i = 0; i < MAX_STREAMS; i++) cudaStreamSynchronize(c->streams[i]);
+  for (int i = 0; i < MAX_STREAMS; i++) { cudaStreamSynchronize(c->streams[i]); if (c->ser_streams[i] != c->streams[i]) cudaStreamSynchronize(c->ser_streams[i]); }
   for (int i = 0; i < SIDE_STREAMS; i++) cudaStreamSynchronize(c->side_streams[i]);
   cudaStreamSynchronize(c->main_stream); cudaStreamSynchronize(c->fin_stream);
 }
@@ -485,7 +519,7 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   if (const char *s = getenv("CCV2_LPS_DEC")) c->lps_dec = atoi(s);
   if (const char *s = getenv("CCV2_NO_RING")) c->use_ring = atoi(s) ? 0 : 1;
   if (const char *s = getenv("CCV2_STREAMS")) c->n_streams = std::max(0, std::min(MAX_STREAMS, atoi(s)));
-  if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(MAX_GROUP, atoi(s)));
+  if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(256, atoi(s)));
   if (const char *s = getenv("CCV2_INFLIGHT")) c->inflight_max = std::max(1, atoi(s));
   if (const char *s = getenv("CCV2_FE_FRAMES")) c->fe_frames = std::max(1, atoi(s));
   auto fail = [&](cudaError_t ee, const char *what) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ee); ccv2_destroy(c); return CCV2_ERR_CUDA; };
@@ -493,11 +527,44 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   if ((e = cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail(e, "cudaDeviceGetAttribute");
   for (cudaStream_t *s : { &c->main_stream, &c->copy_stream, &c->d2h_stream, &c->fin_stream })
     if ((e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+  // SM partition (CUDA green contexts): the serial range-coder kernels are latency bound -- one warp per 8-32 frames, a few
+  // hundred warps in all -- and lose up to half their speed when bandwidth-bound front-end kernels of other groups share
+  // their SMs' schedulers.  With CCV2_GREEN=n they get n SMs of their own and everything else runs on the rest.
+  if (const char *s = getenv("CCV2_GREEN")) c->green_sms = std::max(0, std::min(c->n_sm - 16, atoi(s)));
+  if (c->green_sms > 0) {
+    cudaFree(0);
+    // driver entry points through the runtime (the library does not link libcuda: it must load on hosts without a driver)
+    struct Drv {
+      CUresult (*DeviceGet)(CUdevice *, int); CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource *, CUdevResourceType);
+      CUresult (*SplitByCount)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int);
+      CUresult (*GenerateDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int); CUresult (*GreenCtxCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
+    } drv = {};
+    auto sym = [](const char *name, void **fp) { cudaDriverEntryPointQueryResult q; return cudaGetDriverEntryPoint(name, fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fp; };
+    CUdevice dev; CUdevResource all, grp, rest; unsigned int ng = 1; CUdevResourceDesc d0, d1;
+    bool ok = sym("cuDeviceGet", (void **)&drv.DeviceGet) && sym("cuDeviceGetDevResource", (void **)&drv.DeviceGetDevResource) && sym("cuDevSmResourceSplitByCount", (void **)&drv.SplitByCount) &&
+              sym("cuDevResourceGenerateDesc", (void **)&drv.GenerateDesc) && sym("cuGreenCtxCreate", (void **)&drv.GreenCtxCreate) &&
+              sym("cuGreenCtxStreamCreate", (void **)&c->drv_green_stream_create) && sym("cuGreenCtxDestroy", (void **)&c->drv_green_destroy);
+    ok = ok && drv.DeviceGet(&dev, device) == CUDA_SUCCESS && drv.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
+         drv.SplitByCount(&grp, &ng, &all, &rest, 0, (unsigned)c->green_sms) == CUDA_SUCCESS && ng == 1 &&
+         drv.GenerateDesc(&d0, &grp, 1) == CUDA_SUCCESS && drv.GenerateDesc(&d1, &rest, 1) == CUDA_SUCCESS &&
+         drv.GreenCtxCreate(&c->green_ser, d0, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS && drv.GreenCtxCreate(&c->green_par, d1, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
+    if (!ok) { g_create_error = "CCV2_GREEN: the device could not be split into two SM partitions (green contexts)"; ccv2_destroy(c); return CCV2_ERR_CUDA; }
+    c->green_sms = (int)grp.sm.smCount;
+  }
   for (int i = 0; i < MAX_STREAMS; i++) {
+    if (c->green_sms > 0) {
+      CUstream a = nullptr, b = nullptr;
+      if (c->drv_green_stream_create(&a, c->green_par, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS || c->drv_green_stream_create(&b, c->green_ser, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) { g_create_error = "cuGreenCtxStreamCreate failed"; ccv2_destroy(c); return CCV2_ERR_CUDA; }
+      c->streams[i] = (cudaStream_t)a; c->ser_streams[i] = (cudaStream_t)b;
+      if (i < SIDE_STREAMS) { CUstream s2 = nullptr; if (c->drv_green_stream_create(&s2, c->green_ser, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) { g_create_error = "cuGreenCtxStreamCreate failed"; ccv2_destroy(c); return CCV2_ERR_CUDA; } c->side_streams[i] = (cudaStream_t)s2; }
+      continue;
+    }
     if ((e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    c->ser_streams[i] = c->streams[i];
     if (i < SIDE_STREAMS && (e = cudaStreamCreateWithFlags(&c->side_streams[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
   }
   for (auto &x : c->calls) {
+    if ((e = cudaStreamCreateWithFlags(&x.end_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaEventCreate(&x.ev_start)) != cudaSuccess) return fail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&x.ev_end)) != cudaSuccess) return fail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&x.ev_setup, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
@@ -542,23 +609,26 @@ void ccv2_destroy(ccv2_codec *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (auto &x : c->calls) {
-    for (auto *v : { &x.ev_h2d, &x.ev_side, &x.ev_done, &x.ev_fin, &x.ev_enc, &x.ev_trace }) for (auto ev : *v) cudaEventDestroy(ev);
+    for (auto *v : { &x.ev_h2d, &x.ev_side, &x.ev_done, &x.ev_fin, &x.ev_enc, &x.ev_hop, &x.ev_trace }) for (auto ev : *v) cudaEventDestroy(ev);
     for (cudaEvent_t ev : { x.ev_start, x.ev_end, x.ev_setup }) if (ev) cudaEventDestroy(ev);
+    if (x.end_stream) cudaStreamDestroy(x.end_stream);
     x.enc_frames.release(); x.dec_frames.release(); x.stage.release(); x.h_frames.release(); x.h_dframes.release();
   }
   for (Ring *r : { &c->fe, &c->ll }) { for (auto ev : r->ev_free) cudaEventDestroy(ev); r->buf.release(); }
   for (auto ev : c->prof_pool) cudaEventDestroy(ev);
   for (cudaEvent_t ev : { c->ev_id_chain, c->ev_t0, c->ev_t1 }) if (ev) cudaEventDestroy(ev);
-  for (int i = 0; i < MAX_STREAMS; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+  for (int i = 0; i < MAX_STREAMS; i++) { if (c->ser_streams[i] && c->ser_streams[i] != c->streams[i]) cudaStreamDestroy(c->ser_streams[i]); if (c->streams[i]) cudaStreamDestroy(c->streams[i]); }
   for (int i = 0; i < SIDE_STREAMS; i++) if (c->side_streams[i]) cudaStreamDestroy(c->side_streams[i]);
   for (cudaStream_t s : { c->main_stream, c->copy_stream, c->d2h_stream, c->fin_stream }) if (s) cudaStreamDestroy(s);
+  if (c->green_ser && c->drv_green_destroy) c->drv_green_destroy(c->green_ser);
+  if (c->green_par && c->drv_green_destroy) c->drv_green_destroy(c->green_par);
   if (c->d_tables) cudaFree(c->d_tables);
   if (c->d_frame_counter) cudaFree(c->d_frame_counter);
-  c->out_cloud.release();
+  c->out_cloud.release(); c->tile_pts.release(); c->tile_aux.release();
   delete c;
 }
 
-size_t ccv2_max_compressed_size(size_t npts) { return stream_cap_for(npts, true, true); }
+size_t ccv2_max_compressed_size(size_t npts) { return stream_cap_for(npts, true, true, true); }
 
 void *ccv2_host_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
 void ccv2_host_free(void *p) { if (p) cudaFreeHost(p); }
@@ -638,6 +708,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
   CU(cudaSetDevice(c->device));
   const ccv2_params &prm = c->prm;
   const bool cen = prm.do_voxel_grid_centroid != 0, color = prm.do_color_encoding != 0, lines = prm.color_coding_type == 2;
+  const bool detail = prm.do_voxel_grid_downsampling == 0;           // the encoder's mode; a decoder learns it from the stream
   CallCtx &x = boost ? c->calls[N_CALLS - 1] : c->calls[c->user_calls++ & 1];
   if (x.busy) finish_call(c, x);
   const int ticket = c->next_ticket++;
@@ -650,7 +721,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
   // ------------------------------------------------------------------ classify the caller's buffers, size the workspaces
   x.in_kind.assign(nframes, PK_NONE); x.out_kind.assign(nframes, PK_NONE); x.pts_kind.assign(nframes, PK_NONE);
   x.stage_off_stream.assign(nframes + 1, 0); x.stage_off_pts.assign(nframes + 1, 0);
-  size_t nmax = 1, ncap_max = 1, tcap_max = 0, ccap_max = 0, in_stage_max = 0, out_stage_max = 0, stage_total = 0;
+  size_t nmax = 1, ncap_max = 1, tcap_max = 0, ccap_max = 0, in_stage_max = 0, out_stage_max = 0, stage_total = 0, dpts_max = 0;
   bool host_in_any = false;
   std::vector<size_t> dcount(nframes, 0);                  // records a pinned destination receives by one copy-engine transfer
   for (int i = 0; i < nframes; i++) {
@@ -661,14 +732,14 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
       x.in_kind[i] = npts[i] ? ptr_kind(pts[i]) : PK_DEVICE;
       if (x.in_kind[i] != PK_DEVICE) host_in_any = true;
       x.out_kind[i] = (out && out[i]) ? ptr_kind(out[i]) : PK_NONE;
-      if (x.out_kind[i] == PK_PAGEABLE) { x.stage_off_stream[i] = stage_total; stage_total += (std::min(out_cap[i], stream_cap_for(npts[i], cen, boost)) + 255) & ~size_t(255); }
+      if (x.out_kind[i] == PK_PAGEABLE) { x.stage_off_stream[i] = stage_total; stage_total += (std::min(out_cap[i], stream_cap_for(npts[i], cen, boost, detail)) + 255) & ~size_t(255); }
     }
     if (do_dec) {
       if (pts_cap[i] >= (1u << 28)) { c->err = "frame too large"; return CCV2_ERR_ARG; }
       if ((!rt && in_len[i] && !in[i]) || (pts_cap[i] && !pts_out[i])) return CCV2_ERR_ARG;
       x.pts_kind[i] = pts_cap[i] ? ptr_kind(pts_out[i]) : PK_DEVICE;
       size_t ncap = pts_cap[i], tcap, ccap;
-      if (rt) { ncap = std::max<size_t>(npts[i], 1); tcap = tree_cap_for(ncap, boost); ccap = cpay_cap_for(ncap, boost); dcount[i] = std::min(pts_cap[i], npts[i]); }
+      if (rt) { ncap = std::max<size_t>(npts[i], 1); tcap = tree_cap_for(ncap, boost); ccap = cpay_cap_for(ncap, boost); dcount[i] = std::min(pts_cap[i], npts[i]); if (detail) dpts_max = std::max(dpts_max, ncap); }
       else {
         x.in_kind[i] = in_len[i] ? ptr_kind(in[i]) : PK_DEVICE;
         PeekInfo pi; bool peeked = false;
@@ -681,7 +752,8 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
           tcap = (size_t)std::min<uint64_t>(pi.B, 22ull * ncap + 1024) + 1024;          // B <= depth * V: a larger size word is a malformed stream
           ccap = cpay_cap_for(ncap, boost) + (boost ? 2 * in_len[i] : 0);
           dcount[i] = ncap;
-        } else { ncap = std::max<size_t>(ncap, 1); tcap = tree_cap_for(ncap, boost); ccap = cpay_cap_for(ncap, boost) + (boost ? 2 * in_len[i] : 0); dcount[i] = pts_cap[i]; }
+          if (!pi.voxel_grid) dpts_max = std::max(dpts_max, ncap);               // detail-mode stream: room for the enhancement vectors
+        } else { ncap = std::max<size_t>(ncap, 1); tcap = tree_cap_for(ncap, boost); ccap = cpay_cap_for(ncap, boost) + (boost ? 2 * in_len[i] : 0); dcount[i] = pts_cap[i]; if (boost) dpts_max = std::max(dpts_max, ncap); }   // header not read here: detail buffers only on the retry
       }
       ncap_max = std::max(ncap_max, ncap); tcap_max = std::max(tcap_max, tcap); ccap_max = std::max(ccap_max, ccap);
       if (x.pts_kind[i] == PK_PINNED) out_stage_max = std::max(out_stage_max, (32 * dcount[i] + 255) & ~size_t(255));
@@ -689,20 +761,20 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
     }
   }
   const int NS = c->profiling ? 1 : (c->n_streams ? c->n_streams : MAX_STREAMS);
-  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(MAX_GROUP, (nframes + 15) / 16)));
+  const int G = c->profiling ? std::max(1, std::min(nframes, 64)) : (c->group ? c->group : std::max(1, std::min(MAX_GROUP, (nframes + 7) / 8)));
   const int ngroups = (nframes + G - 1) / G;
   x.G = G; x.ngroups = ngroups;
 
   size_t fe_bytes = 0, fe_zero = 0, ll_bytes = 0, stream_end = 0, enc_ll = 0, dec_ws = 0, dec_zero = 0;
-  if (do_enc) { size_t zo; fe_bytes = carve_fe(nullptr, nmax, nullptr, prm, boost, host_in_any, &zo, &fe_zero); enc_ll = carve_enc_ll(nullptr, nmax, nullptr, cen, boost, &stream_end); }
-  if (do_dec) dec_ws = carve_dec(nullptr, ncap_max, tcap_max, ccap_max, nullptr, &dec_zero, lines);
+  if (do_enc) { size_t zo; fe_bytes = carve_fe(nullptr, nmax, nullptr, prm, boost, host_in_any, &zo, &fe_zero); enc_ll = carve_enc_ll(nullptr, nmax, nullptr, cen, boost, &stream_end, detail); }
+  if (do_dec) dec_ws = carve_dec(nullptr, ncap_max, tcap_max, ccap_max, nullptr, &dec_zero, lines, dpts_max, boost);
   const size_t ws_off = rt ? stream_end : 0;                          // round trip: the decoder's workspace lies over the encoder's dead buffers
   const size_t in_stage_off = std::max(enc_ll, ws_off + dec_ws);
   const size_t out_stage_off = in_stage_off + in_stage_max;
   ll_bytes = out_stage_off + out_stage_max;
   {
     const int want_ll = std::max(1, std::min(2 * ngroups, (c->inflight_max + G - 1) / G));
-    const int want_fe = std::max(1, std::min(2 * ngroups, std::max(4, c->fe_frames / G)));
+    const int want_fe = std::max(1, std::min(2 * ngroups, std::max(2, c->fe_frames / G)));
     int rc;
     if (do_enc && (rc = ensure_ring(c, c->fe, fe_bytes, G, want_fe, "front-end")) != CCV2_OK) return rc;
     if ((rc = ensure_ring(c, c->ll, ll_bytes, G, want_ll, "long-lived")) != CCV2_OK) return rc;
@@ -714,8 +786,8 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
   if (do_enc) fe.seq += ngroups;
   ll.seq += ngroups;
   CU(x.stage.ensure(stage_total + 256));
-  grow_events(x.ev_h2d, ngroups); grow_events(x.ev_side, 2 * (size_t)ngroups); grow_events(x.ev_done, ngroups); grow_events(x.ev_fin, ngroups); grow_events(x.ev_enc, ngroups);
-  if ((int)x.ev_h2d.size() < ngroups || (int)x.ev_side.size() < 2 * ngroups || (int)x.ev_done.size() < ngroups || (int)x.ev_fin.size() < ngroups || (int)x.ev_enc.size() < ngroups) { c->err = "cudaEventCreate failed"; return CCV2_ERR_CUDA; }
+  grow_events(x.ev_h2d, ngroups); grow_events(x.ev_side, 2 * (size_t)ngroups); grow_events(x.ev_done, ngroups); grow_events(x.ev_fin, ngroups); grow_events(x.ev_enc, ngroups); grow_events(x.ev_hop, 4 * (size_t)ngroups);
+  if ((int)x.ev_h2d.size() < ngroups || (int)x.ev_side.size() < 2 * ngroups || (int)x.ev_done.size() < ngroups || (int)x.ev_fin.size() < ngroups || (int)x.ev_enc.size() < ngroups || (int)x.ev_hop.size() < 4 * ngroups) { c->err = "cudaEventCreate failed"; return CCV2_ERR_CUDA; }
 
   // ------------------------------------------------------------------ frame records
   EncFrame *hf = nullptr, *df = nullptr; DecFrame *hd = nullptr, *dd = nullptr;
@@ -724,7 +796,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
   size_t frames_bytes = 0;
   if (do_enc) {
     frames_bytes = (sizeof(EncFrame) * nframes + 255) & ~size_t(255);
-    CU(x.enc_frames.ensure(frames_bytes + (size_t)nframes * 3 * 256 * 4));
+    CU(x.enc_frames.ensure(frames_bytes + (size_t)nframes * 5 * 256 * 4));
     CU(x.h_frames.ensure(sizeof(EncFrame) * nframes));
     hf = (EncFrame *)x.h_frames.p; df = (EncFrame *)x.enc_frames.p;
     memset(hf, 0, sizeof(EncFrame) * nframes);
@@ -739,13 +811,13 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
       uint8_t *fb = fe.frame_base(x.fe_set[g], j);
       carve_fe(fb, nmax, &f, prm, boost, x.in_kind[i] != PK_DEVICE, nullptr, nullptr);     // host input: f.pts = the set's staging area
       f.zero_ptr = fb; f.zero_bytes = fe_zero;
-      carve_enc_ll(ll.frame_base(x.ll_set[g], j), nmax, &f, cen, boost, nullptr);
-      f.hist = (uint32_t *)((uint8_t *)x.enc_frames.p + frames_bytes) + (size_t)i * 3 * 256;
+      carve_enc_ll(ll.frame_base(x.ll_set[g], j), nmax, &f, cen, boost, nullptr, detail);
+      f.hist = (uint32_t *)((uint8_t *)x.enc_frames.p + frames_bytes) + (size_t)i * 5 * 256;
       if (color && (prm.color_coding_type == 0 || prm.color_coding_type == 3)) f.avg = f.cpay;   // raw averages are the colour payload
       switch (x.out_kind[i]) {
         case PK_DEVICE: f.out_ptr = (uint8_t *)out[i]; f.out_cap = out_cap[i]; break;
         case PK_PINNED: { void *dp = nullptr; CU(cudaHostGetDevicePointer(&dp, out[i], 0)); f.out_ptr = (uint8_t *)dp; f.out_cap = out_cap[i]; break; }
-        case PK_PAGEABLE: f.out_ptr = (uint8_t *)x.stage.p + x.stage_off_stream[i]; f.out_cap = std::min(out_cap[i], stream_cap_for(npts[i], cen, boost)); break;
+        case PK_PAGEABLE: f.out_ptr = (uint8_t *)x.stage.p + x.stage_off_stream[i]; f.out_cap = std::min(out_cap[i], stream_cap_for(npts[i], cen, boost, detail)); break;
         default: f.out_ptr = nullptr; f.out_cap = 0; break;
       }
     }
@@ -754,8 +826,9 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
     P.do_color = color; P.color_type = prm.color_coding_type; P.do_centroid = cen;
     P.color_reduction = (prm.color_coding_type == 0) ? std::max(0, 8 - (int)prm.color_bit_resolution) : 0;   // jp_color_coder_ is never configured
     P.prefix_len = 16384;
+    P.detail = detail; P.point_res_f = (float)prm.point_resolution;
     H.octree_res = prm.octree_resolution; H.point_res = (double)(float)prm.point_resolution;
-    H.do_voxel_grid = 1; H.with_color = color; H.color_bits = prm.color_bit_resolution; H.do_centroid = cen;
+    H.do_voxel_grid = detail ? 0 : 1; H.with_color = color; H.color_bits = prm.color_bit_resolution; H.do_centroid = cen;
     H.connectivity = prm.code_connectivity != 0; H.scalable = prm.create_scalable_stream != 0; H.icp_offset = prm.do_icp_color_offset != 0; H._p = 0;
     H.color_type = prm.color_coding_type; H.macroblock = prm.macroblock_size;
     c->last_enc_params = P;
@@ -781,7 +854,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
         default: f.out_pts = (uint8_t *)pts_out[i]; break;
       }
       f.out_cap = pts_cap[i];
-      carve_dec(lb + ws_off, ncap_max, tcap_max, ccap_max, &f, nullptr, lines);
+      carve_dec(lb + ws_off, ncap_max, tcap_max, ccap_max, &f, nullptr, lines, dpts_max, boost);
       f.zero_ptr = lb + ws_off; f.zero_bytes = dec_zero;
     }
   }
@@ -801,7 +874,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
   CUQ(cudaEventRecord(x.ev_start, ms));
   if (do_enc) {
     CUQ(cudaMemcpyAsync(df, hf, sizeof(EncFrame) * nframes, cudaMemcpyHostToDevice, ms));
-    CUQ(cudaMemsetAsync((uint8_t *)x.enc_frames.p + frames_bytes, 0, (size_t)nframes * 3 * 256 * 4, ms));
+    CUQ(cudaMemsetAsync((uint8_t *)x.enc_frames.p + frames_bytes, 0, (size_t)nframes * 5 * 256 * 4, ms));
   }
   if (do_dec) CUQ(cudaMemcpyAsync(dd, hd, sizeof(DecFrame) * nframes, cudaMemcpyHostToDevice, ms));
   // serial CTAs reserve enough shared memory (1 KB per CTA is the system's) that only serial_cap of them fit on an SM
@@ -815,13 +888,24 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
   CUQ(cudaEventRecord(x.ev_setup, ms));
   bool host_io = host_in_any;
   for (int i = 0; i < nframes && !host_io; i++) host_io = (x.out_kind[i] != PK_NONE && x.out_kind[i] != PK_DEVICE) || (do_dec && x.pts_kind[i] != PK_DEVICE);
-  const bool use_lps_dec = c->lps_dec < 0 ? (rt && !host_io) : c->lps_dec != 0;
+  // the lane-per-stream decoder wins whenever many frames are in flight on the device (2416 against 1902 Mpoints/s round trip,
+  // 4329 against 3239 decode-only); with host buffers the copies pace the pipeline and the CTA-per-frame decoder's shorter
+  // latency is worth more (1174 against 1103 end to end)
+  const bool use_lps_dec = c->lps_dec < 0 ? !host_io : c->lps_dec != 0;
   uint64_t launches = 0;
   uint32_t *counter = c->d_frame_counter;
   bool copy_waits_setup = false;
   for (int g = 0; g < ngroups; g++) {
     const int sl = x.ll_set[g], sf = x.fe_set[g];
-    cudaStream_t st = c->streams[c->stage_seq++ % NS];
+    cudaStream_t const sp = c->streams[sl % NS], ss = c->profiling ? sp : c->ser_streams[sl % NS];   // parallel kernels / serial range-coder kernels (same stream unless the SMs are partitioned)
+    cudaStream_t st = sp;
+    int hops = 0;
+    auto hop = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t {     // hand the group over to the other partition's stream
+      if (from == to) return cudaSuccess;
+      cudaEvent_t ev = x.ev_hop[4 * g + (hops++ & 3)];
+      cudaError_t e2 = cudaEventRecord(ev, from);
+      return e2 != cudaSuccess ? e2 : cudaStreamWaitEvent(to, ev, 0);
+    };
     const int f0 = g * G, gf = std::min(G, nframes - f0);
     const unsigned steered_grid = (unsigned)((gf + c->n_sm - 1) / c->n_sm * c->n_sm);
     CUQ(cudaStreamWaitEvent(st, x.ev_setup, 0));
@@ -873,25 +957,25 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
         LAUNCH("lines_offsets_kernel", lines_offsets_kernel<<<gf, 1024, 0, st>>>(dg));
         LAUNCH("lines_copy_kernel", lines_copy_kernel<<<dim3(lines_max, gf), 256, 0, st>>>(dg));
       }
+      if (detail) {
+        LAUNCH("detail_scan_kernel", detail_scan_kernel<<<dim3((unsigned)((gn + 1023) / 1024), gf), 256, 0, st>>>(dg));
+        LAUNCH("detail_emit_kernel", detail_emit_kernel<<<dim3(gx256, gf), 256, 0, st>>>(dg, P));
+      }
       // the front-end set goes to the next group: everything from here on lives in the long-lived set
       CUQ(cudaEventRecord(fe.ev_free[sf], st)); fe.used[sf] = 1;
-      const size_t hmax = std::max(tree_cap_for(gn, boost), cpay_cap_for(gn, boost));
+      const size_t hmax = std::max(std::max(tree_cap_for(gn, boost), cpay_cap_for(gn, boost)), detail ? diff_cap_for(gn) : 0);
       mark(g, "leaves", st);
-      LAUNCH("hist_kernel", hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), 3, gf), 256, 0, st>>>(dg));
-      if (c->lps_enc) LAUNCH("rc_encode_lps_kernel", rc_encode_lps_kernel<<<dim3((unsigned)((gf + 31) / 32), 3), 32, c->lps_smem_enc, st>>>(dg, gf, cen, color));
-      else LAUNCH("rc_encode_kernel", rc_encode_kernel<<<gf, 96, serial_smem_enc, st>>>(dg, cen, color));
+      LAUNCH("hist_kernel", hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), detail ? 5 : 3, gf), 256, 0, st>>>(dg));
+      CUQ(hop(sp, ss)); st = ss;
+      if (detail) LAUNCH("rc_encode_int_kernel", rc_encode_int_kernel<<<gf, 32, 0, st>>>(dg));
+      if (c->lps_enc) LAUNCH("rc_encode_lps_kernel", rc_encode_lps_kernel<<<dim3((unsigned)((gf + 31) / 32), detail ? 5 : 3), 32, c->lps_smem_enc, st>>>(dg, gf, cen, color, detail));
+      else LAUNCH("rc_encode_kernel", rc_encode_kernel<<<gf, detail ? 160 : 96, serial_smem_enc, st>>>(dg, cen, color, detail));
+      CUQ(hop(ss, sp)); st = sp;
       LAUNCH("assemble_kernel", assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H));
       if (out) LAUNCH("export_kernel", export_kernel<<<dim3(2, gf), 256, 0, st>>>(dg));
       mark(g, "encoded", st);
     }
     if (do_dec) {
-      // the decode stage of a round trip moves to the next work stream: its 0.2-0.4 s must not hold up the encode stage of
-      // the group that comes next on this one
-      if (rt && NS > 1) {
-        cudaStream_t sd = c->streams[c->stage_seq++ % NS];
-        CUQ(cudaEventRecord(x.ev_enc[g], st)); CUQ(cudaStreamWaitEvent(sd, x.ev_enc[g], 0));
-        st = sd;
-      }
       DecFrame *dg = dd + f0;
       size_t pmax = 1;
       for (int i = 0; i < gf; i++) {
@@ -905,9 +989,10 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
       if (rt) LAUNCH("link_kernel", link_kernel<<<(gf + 63) / 64, 64, 0, st>>>(df + f0, dg, gf));
       // Two entropy stages.  dec_entropy_kernel (a CTA per frame) has the shorter latency; the lane-per-stream decoder
       // (8 frames to a warp) executes a third of the instructions and wins when the SMs' issue slots are the limit.
+      CUQ(hop(sp, ss)); st = ss;
       if (use_lps_dec) {
         // tree layers on the group's stream, speculated colour layers on a side stream at the same time
-        cudaStream_t s2 = c->profiling ? st : c->side_streams[c->stage_seq % SIDE_STREAMS];
+        cudaStream_t s2 = c->profiling ? st : c->side_streams[sl % SIDE_STREAMS];
         const unsigned lps_ctas = (unsigned)((gf + LPS_DEC_FRAMES - 1) / LPS_DEC_FRAMES);
         LAUNCH("dec_head_kernel", dec_head_kernel<<<gf, 32, 0, st>>>(dg));
         if (s2 != st) { CUQ(cudaEventRecord(x.ev_side[2 * g], st)); CUQ(cudaStreamWaitEvent(s2, x.ev_side[2 * g], 0)); }
@@ -922,6 +1007,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
       } else
       LAUNCH("dec_entropy_kernel", dec_entropy_kernel<<<gf, 96, serial_smem_dec, st>>>(dg, c->use_ring));
       mark(g, "entropy", st);
+      CUQ(hop(ss, sp)); st = sp;
       LAUNCH("jpeg_destuff_kernel", jpeg_destuff_kernel<<<gf, 1024, 0, st>>>(dg));
       LAUNCH("dec_serial_kernel", dec_serial_kernel<<<steered_grid, 64, 0, st>>>(dg, f0, gf));
       if (lines) {
@@ -934,6 +1020,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
       LAUNCH("jpeg_idct_kernel", jpeg_idct_kernel<<<dim3((unsigned)((nblocks + 31) / 32), gf), 256, 0, st>>>(dg, c->d_tables));
       LAUNCH("dec_leaves_kernel", dec_leaves_kernel<<<dim3((unsigned)((pmax + 255) / 256), gf), 256, 0, st>>>(dg));        // frames walked by the pipelined walkers
       LAUNCH("dec_points_kernel", dec_points_kernel<<<dim3((unsigned)((pmax + NODE_THREADS - 1) / NODE_THREADS), gf), NODE_THREADS, 0, st>>>(dg));
+      LAUNCH("detail_points_kernel", detail_points_kernel<<<dim3((unsigned)((pmax + 255) / 256), gf), 256, 0, st>>>(dg));   // detail-mode frames only
       mark(g, "decoded", st);
     }
     CUQ(cudaEventRecord(x.ev_done[g], st));
@@ -957,8 +1044,9 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
     ll.used[sl] = 1;
     CUQ(cudaGetLastError());
   }
-  for (int g = 0; g < ngroups; g++) CUQ(cudaStreamWaitEvent(ms, x.ev_fin[g], 0));
-  CUQ(cudaEventRecord(x.ev_end, ms));
+  // the call's end is gathered on its own stream: on the control stream it would hold back the set-up of the next call
+  for (int g = 0; g < ngroups; g++) CUQ(cudaStreamWaitEvent(x.end_stream, x.ev_fin[g], 0));
+  CUQ(cudaEventRecord(x.ev_end, x.end_stream));
 #undef CUQ
   x.launches = launches;
   return CCV2_OK;
@@ -1026,9 +1114,10 @@ static int finish_call(ccv2_codec *c, CallCtx &x) {
         }
         continue;
       }
-      x.npts_out[k] = f.V;
-      if (x.pts_kind[k] == PK_PAGEABLE && f.V) {
-        e = cudaMemcpy(x.pts_out[k], (uint8_t *)x.stage.p + x.stage_off_pts[k], 32ull * f.V, cudaMemcpyDeviceToHost);
+      const uint32_t nout = f.detail ? f.npoints_out : f.V;
+      x.npts_out[k] = nout;
+      if (x.pts_kind[k] == PK_PAGEABLE && nout) {
+        e = cudaMemcpy(x.pts_out[k], (uint8_t *)x.stage.p + x.stage_off_pts[k], 32ull * nout, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { c->err = std::string("cudaMemcpy (points): ") + cudaGetErrorString(e); return store(CCV2_ERR_CUDA); }
       }
     }
@@ -1161,8 +1250,8 @@ int ccv2_timer_start(ccv2_codec *c) {
 int ccv2_timer_stop(ccv2_codec *c, float *ms) {
   if (!c || !ms) return CCV2_ERR_ARG;
   CU(cudaSetDevice(c->device));
-  const int rc = finish_all(c);
-  CU(cudaEventRecord(c->ev_t1, c->main_stream));             // behind the last call's end on the control stream
+  const int rc = finish_all(c);                              // host-synchronous: everything submitted has completed
+  CU(cudaEventRecord(c->ev_t1, c->main_stream));
   CU(cudaEventSynchronize(c->ev_t1));
   CU(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
   return rc;
@@ -1174,7 +1263,7 @@ int ccv2_get_output_cloud(ccv2_codec *c, int frame, void *points_out, size_t cap
   if (c->last_mode != 0 || !c->enc_host_valid[frame]) { c->err = "the output cloud is only available right after ccv2_encode_batch (and while the frame's workspace has not been handed on)"; return CCV2_ERR_UNSUPPORTED; }
   CU(cudaSetDevice(c->device));
   const EncFrame &f = c->enc_host[frame];
-  if (f.error) { *npoints = 0; return CCV2_OK; }
+  if (f.error || c->last_enc_params.detail) { *npoints = 0; return CCV2_OK; }   // detail mode: the reference's callback leaves output_ empty (impl.hpp:1525-1541)
   *npoints = f.V;
   if (f.V == 0) return CCV2_OK;
   if (f.V > cap_points || !points_out) return CCV2_ERR_CAPACITY;
@@ -1186,6 +1275,69 @@ int ccv2_get_output_cloud(ccv2_codec *c, int frame, void *points_out, size_t cap
   if (!dev) CU(cudaMemcpyAsync(points_out, dst, 32ull * f.V, cudaMemcpyDeviceToHost, c->fin_stream));
   CU(cudaStreamSynchronize(c->fin_stream));
   return CCV2_OK;
+}
+
+// ---- tile mode (tile_kernels.cuh) -----------------------------------------------------------------------------------
+// Stable partition of one frame into 2^tile_bits spatial tiles.  pts_out (device or host, n records) receives the points
+// grouped by tile, original order kept inside a tile; tile_offsets[t] .. tile_offsets[t + 1] is tile t.
+int ccv2_split_tiles(ccv2_codec *c, const void *pts, size_t n, int tile_bits, void *pts_out, size_t *tile_offsets) {
+  if (!c || !tile_offsets || (tile_bits != 3 && tile_bits != 6) || n >= (1u << 28) || (n && (!pts || !pts_out))) return CCV2_ERR_ARG;
+  CU(cudaSetDevice(c->device));
+  finish_all(c);
+  const int k = tile_bits / 3; const uint32_t nt = 1u << tile_bits;
+  for (uint32_t t = 0; t <= nt; t++) tile_offsets[t] = 0;
+  if (n == 0) return CCV2_OK;
+  const uint32_t nblocks = (uint32_t)((n + TILE_BLOCK - 1) / TILE_BLOCK);
+  const bool din = is_device_ptr(pts), dout = is_device_ptr(pts_out);
+  const size_t stage_in = din ? 0 : (32 * n + 255) & ~size_t(255), stage_out = dout ? 0 : (32 * n + 255) & ~size_t(255);
+  const size_t cnt_bytes = ((size_t)nt * nblocks * 4 + 255) & ~size_t(255);
+  CU(c->tile_aux.ensure(stage_in + stage_out + cnt_bytes + (nt + 1) * 8 + 256));
+  uint8_t *w = (uint8_t *)c->tile_aux.p;
+  const uint8_t *src = din ? (const uint8_t *)pts : w;
+  uint8_t *dst = dout ? (uint8_t *)pts_out : w + stage_in;
+  uint32_t *counts = (uint32_t *)(w + stage_in + stage_out);
+  uint64_t *offs = (uint64_t *)(w + stage_in + stage_out + cnt_bytes);
+  cudaStream_t st = c->fin_stream;
+  if (!din) CU(cudaMemcpyAsync(w, pts, 32 * n, cudaMemcpyHostToDevice, st));
+  tile_count_kernel<<<nblocks, TILE_BLOCK, 0, st>>>(src, (uint32_t)n, k, counts, nblocks);
+  tile_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, nt, offs);
+  tile_scatter_kernel<<<nblocks, TILE_BLOCK, 0, st>>>(src, (uint32_t)n, k, counts, nblocks, dst);
+  CU(cudaGetLastError());
+  uint64_t h_offs[TILE_MAX + 1];
+  CU(cudaMemcpyAsync(h_offs, offs, (nt + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (!dout) CU(cudaMemcpyAsync(pts_out, dst, 32 * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (uint32_t t = 0; t <= nt; t++) tile_offsets[t] = (size_t)h_offs[t];
+  return CCV2_OK;
+}
+
+// One frame -> one reference-format stream per non-empty tile.  Encodes tiles first_tile, first_tile + tile_step, ...
+// (a rank of a node takes first_tile = rank, tile_step = world size; 0 and 1 for everything).  out / out_cap / out_len are
+// indexed by TILE (2^tile_bits entries; tiles this call does not own are left untouched, empty tiles report 0 bytes);
+// tile_npts (may be NULL) receives the number of points of every tile.  Frame ids continue the codec's counter in tile order.
+int ccv2_encode_tiles(ccv2_codec *c, const void *pts, size_t n, int tile_bits, int first_tile, int tile_step,
+                      void *const *out, const size_t *out_cap, size_t *out_len, size_t *tile_npts) {
+  if (!c || !out || !out_cap || !out_len || (tile_bits != 3 && tile_bits != 6) || first_tile < 0 || tile_step < 1) return CCV2_ERR_ARG;
+  const int nt = 1 << tile_bits;
+  CU(cudaSetDevice(c->device));
+  finish_all(c);
+  CU(c->tile_pts.ensure(32 * n + 256));
+  size_t offs[TILE_MAX + 1];
+  int rc = ccv2_split_tiles(c, pts, n, tile_bits, c->tile_pts.p, offs);
+  if (rc != CCV2_OK) return rc;
+  std::vector<const void *> tp; std::vector<size_t> tn, tcap, tlen; std::vector<void *> to; std::vector<int> owner;
+  for (int t = 0; t < nt; t++) {
+    if (tile_npts) tile_npts[t] = offs[t + 1] - offs[t];
+    if (t < first_tile || (t - first_tile) % tile_step) continue;
+    out_len[t] = 0;
+    if (offs[t + 1] == offs[t]) continue;                                     // empty tile: no frame (the reference writes nothing for an empty cloud)
+    tp.push_back((const uint8_t *)c->tile_pts.p + 32 * offs[t]); tn.push_back(offs[t + 1] - offs[t]); to.push_back(out[t]); tcap.push_back(out_cap[t]); owner.push_back(t);
+  }
+  tlen.assign(tp.size(), 0);
+  if (tp.empty()) return CCV2_OK;
+  rc = ccv2_encode_batch(c, (int)tp.size(), tp.data(), tn.data(), to.data(), tcap.data(), tlen.data());
+  for (size_t i = 0; i < owner.size(); i++) out_len[owner[i]] = tlen[i];
+  return rc;
 }
 
 // computeQualityMetric (quality_metrics_impl.hpp:82-239): exact nearest neighbours both ways, see quality_kernels.cuh

@@ -23,7 +23,7 @@ enum : uint32_t {
   FERR_CALLER_CAP = 1u << 7,  // encoder: the caller's stream buffer is too small
 };
 
-enum : int { TK_SORT0 = 0, TK_LEAF = 8, TK_HUFF = 9, TK_STUFF = 10, TK_NODES = 11, TK_EXPAND = 12, TK_COUNT = 16 };
+enum : int { TK_SORT0 = 0, TK_LEAF = 8, TK_HUFF = 9, TK_STUFF = 10, TK_NODES = 11, TK_EXPAND = 12, TK_DETAIL = 13, TK_COUNT = 16 };
 
 struct __align__(16) JpegTables {   // per codec, device resident
   uint16_t q[2][64];           // quant tables, natural order (lum, chroma)
@@ -38,6 +38,8 @@ struct EncParams {             // by value to kernels
   int res_pow2;
   int do_color, color_type, color_reduction, do_centroid;
   int prefix_len;              // points handled exactly by the single-CTA bbox kernel
+  int detail;                  // doVoxelGridDownDownSampling = false: per-point residuals and colour differences (impl.hpp:1525-1541)
+  float point_res_f;           // [PCL] PointCoding::pointCompressionResolution_ (setPrecision(float))
 };
 
 // One entry per change of the bounding box while the cloud is added in input order ([PCL] adoptBoundingBoxToPoint):
@@ -68,8 +70,10 @@ struct EncFrame {
   uint32_t frame_id_fixed, _padf;   // != 0: a retried frame keeps the id it was given the first time (frame_setup_kernel)
   uint8_t *out_ptr; uint64_t out_cap;   // where the finished stream goes (caller's device buffer, the device alias of a pinned host buffer, or a staging area); may be null
   uint64_t out_len; uint64_t coded[3];
-  uint32_t rc_len[3];          // coded bytes per layer incl. table (tree, centroid, colour)
-  uint32_t _pad1;
+  uint32_t rc_len[5];          // coded bytes per layer incl. table (tree, centroid, colour, point differences, colour differences)
+  uint32_t rc_int_len;         // coded bytes of the int-coded point counts (detail mode)
+  uint32_t npd, ncd;           // detail mode: bytes of point differences (3 per point) / colour differences (3 per point of a multi-point voxel)
+  uint32_t itsize, _pad1;      // detail mode: frequency table size of the int coder (after the final increment)
   // group-slot workspace
   uint64_t *keys[2]; uint32_t *vals[2];
   uint32_t *ghist;             // [8][256]
@@ -87,9 +91,15 @@ struct EncFrame {
   uint8_t *tree; uint32_t tree_cap; uint32_t _pad5;
   uint8_t *cen;                // centroid residual bytes
   uint8_t *cpay; uint32_t cpay_cap; uint32_t _pad6;   // colour payload (jpeg file or raw averages)
-  uint32_t *hist;              // [3][256]
+  uint32_t *hist;              // [5][256]
   uint8_t *stream; uint64_t stream_cap;
-  uint8_t *rc_tmp[2]; uint32_t rc_tmp_cap[2];         // range-coded centroid / colour layers before assembly
+  uint8_t *rc_tmp[4]; uint32_t rc_tmp_cap[4];         // range-coded centroid / colour / point-difference / colour-difference layers before assembly
+  // detail mode (impl.hpp:1525-1541, 1728-1757)
+  uint32_t *counts;            // points per voxel (point_count_data_vector_)
+  uint32_t *cd_off;            // per voxel: index of its first colour-difference triple (front-end ring)
+  uint8_t *pdiff, *cdiff;      // [PCL] PointCoding / ColorCoding differential vectors
+  uint64_t *itab; uint32_t itab_cap, _pad7;           // cumulative frequency table of the int coder
+  uint8_t *rc_int; uint32_t rc_int_cap, _pad9;        // int-coded counts before assembly
 };
 
 struct DecFrame {
@@ -126,6 +136,14 @@ struct DecFrame {
   uint32_t n_lines, lines_cap;                   // LINES colour mode: per-line offset/length/width, quant tables, row planes
   uint32_t *line_off, *line_len, *line_w; uint16_t *line_qt; uint8_t *line_planes;
   uint64_t *scan_status; uint32_t scan_tiles_max, _pad7;
+  // detail mode (entropyDecoding impl.hpp:1802-1832, deserializeTreeCallback :1592-1613)
+  uint32_t detail, ncounts; uint64_t npdiff, ncdiff;
+  float point_res_f; uint32_t _pad11;            // [PCL] readFrameHeader: point_coder_.setPrecision(float(point_resolution))
+  uint32_t *counts; uint32_t counts_cap, _pad9;
+  uint8_t *pdiff, *cdiff; uint64_t pdiff_cap;
+  uint64_t *itab; uint32_t itab_cap, _pad10;
+  uint64_t *dleaf_key;                           // Morton code of every voxel in stream order (detail_points_kernel expands them)
+  uint32_t npoints_out, _pad12;                  // detail mode: points written (V stays the voxel count)
 };
 
 // ---------------------------------------------------------------- small device helpers

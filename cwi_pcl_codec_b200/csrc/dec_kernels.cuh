@@ -17,6 +17,7 @@ __device__ inline void jpeg_huff_decode(DecFrame &f, HuffDec *hd);
 __device__ inline void warp_destuff(DecFrame &f);
 
 __device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *lut, uint32_t *stack);
+__device__ inline bool decode_detail_layers(DecFrame &f, const uint8_t *in, uint64_t len, uint64_t &pos, uint32_t *freq_s, uint32_t &err);
 
 // ---- stage 1: header + entropy decoding of the layers (impl.hpp:231-261, 1766-1835), one block per frame (steered):
 // warp 0 parses the header and range-decodes tree -> [centroid] -> colour (serially dependent: no stored lengths);
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(96) dec_entropy_kernel(DecFrame *frames, int u
       const uint64_t point_count = ld_u64_unaligned(h + 7);
       const double res = ld_f64_unaligned(h + 15);
       const uint8_t color_bits = h[23];
+      const double point_res = ld_f64_unaligned(h + 24);
       double bmin[3], bmax[3];
       for (int a = 0; a < 3; a++) { bmin[a] = ld_f64_unaligned(h + 32 + 8 * a); bmax[a] = ld_f64_unaligned(h + 56 + 8 * a); }
       do_centroid = h[80];
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(96) dec_entropy_kernel(DecFrame *frames, int u
       if (lane == 0) {
         f.frame_id = frame_id; f.data_with_color = data_with_color; f.point_count = point_count; f.res = res; f.color_bits = color_bits;
         for (int a = 0; a < 3; a++) { f.bmin[a] = bmin[a]; f.bmax[a] = bmax[a]; }
-        f.do_centroid = do_centroid; f.cct = cct; f.depth = depth;
+        f.do_centroid = do_centroid; f.cct = cct; f.depth = depth; f.point_res_f = (float)point_res;
       }
     }
     if (lane == 0) { rg.B = (uint32_t)B; rg.depth = depth; rg.go = (use_ring && !err && B > 0 && depth >= 1 && depth <= 17) ? 1u : 0u;
@@ -180,8 +182,9 @@ __global__ void __launch_bounds__(96) dec_entropy_kernel(DecFrame *frames, int u
       }
     }
   }
-  // trailing bytes would switch the reference into detail mode (impl.hpp:1802-1806): outside the implemented scope
-  if (ok && pos != len) { ok = false; err |= FERR_UNSUPPORTED; }
+  // trailing bytes switch the reference into detail mode (impl.hpp:1802-1806): the enhancement vectors follow
+  __syncwarp();
+  if (ok && pos != len) { ok = decode_detail_layers(f, in, len, pos, freq, err); if (ok && pos != len) ok = false; }
   if (lane == 0) {
     if (!ok) { atomicOr(&f.error, err ? err : FERR_BAD_STREAM); f.B = 0; f.V = 0; }
     else {
@@ -659,16 +662,18 @@ __global__ void __launch_bounds__(NODE_THREADS) dec_points_kernel(DecFrame *fram
   }
   __syncthreads();
   const uint64_t base = s_excl;
-  if (g == nb - 1) { uint64_t V = base + excl_local + cnt; f.V = (uint32_t)V; if (V != f.point_count || V > f.out_cap) atomicOr(&f.error, FERR_BAD_STREAM); }
+  const uint32_t detail = f.detail;
+  if (g == nb - 1) { uint64_t V = base + excl_local + cnt; f.V = (uint32_t)V; if (detail ? (V != f.ncounts || V > f.counts_cap) : (V != f.point_count || V > f.out_cap)) atomicOr(&f.error, FERR_BAD_STREAM); }
   const double res = f.res;
   const uint32_t do_centroid = f.do_centroid;
   const uint64_t out_cap = f.out_cap;
   for (uint32_t j = threadIdx.x; j < (uint32_t)tot; j += NODE_THREADS) {     // consecutive threads write consecutive 32-byte records
     const uint64_t i64 = base + j;
-    if (i64 >= out_cap) break;
+    if (i64 >= (detail ? (uint64_t)f.counts_cap : out_cap)) break;
     const uint32_t i = (uint32_t)i64;
     const uint32_t e = s_leaf[j];
     const uint64_t key = (s_prefix[e >> 3] << 3) | (e & 7u);
+    if (detail) { if (i < f.counts_cap) f.dleaf_key[i] = key; continue; }      // detail mode: detail_points_kernel expands the voxels
     const uint32_t k3[3] = { compact3(key >> 2), compact3(key >> 1), compact3(key) };
     float xyz[3];
 #pragma unroll
@@ -725,16 +730,18 @@ __global__ void __launch_bounds__(256) dec_leaves_kernel(DecFrame *frames) {
   }
   __syncthreads();
   const uint64_t base = s_excl;
-  if (g == n2 - 1) { uint64_t V = base + excl_local + cnt; f.V = (uint32_t)V; if (V != f.point_count || V > f.out_cap) atomicOr(&f.error, FERR_BAD_STREAM); }
+  const uint32_t detail = f.detail;
+  if (g == n2 - 1) { uint64_t V = base + excl_local + cnt; f.V = (uint32_t)V; if (detail ? (V != f.ncounts || V > f.counts_cap) : (V != f.point_count || V > f.out_cap)) atomicOr(&f.error, FERR_BAD_STREAM); }
   const double res = f.res;
   const uint32_t do_centroid = f.do_centroid;
   const uint64_t out_cap = f.out_cap;
   for (uint32_t j = threadIdx.x; j < (uint32_t)tot; j += 256) {
     const uint64_t i64 = base + j;
-    if (i64 >= out_cap) break;
+    if (i64 >= (detail ? (uint64_t)f.counts_cap : out_cap)) break;
     const uint32_t i = (uint32_t)i64;
     const uint32_t e = s_leaf[j];
     const uint64_t key = (((s_prefix[e >> 6] << 3) | ((e >> 3) & 7u)) << 3) | (e & 7u);
+    if (detail) { if (i < f.counts_cap) f.dleaf_key[i] = key; continue; }      // detail mode: detail_points_kernel expands the voxels
     const uint32_t k3[3] = { compact3(key >> 2), compact3(key >> 1), compact3(key) };
     float xyz[3];
 #pragma unroll

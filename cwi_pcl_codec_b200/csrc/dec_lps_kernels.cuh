@@ -103,6 +103,7 @@ __device__ inline void dec_parse_header(DecFrame &f) {
     for (int a = 0; a < 3; a++) { bmin[a] = ld_f64_unaligned(h + 32 + 8 * a); bmax[a] = ld_f64_unaligned(h + 56 + 8 * a); f.bmin[a] = bmin[a]; f.bmax[a] = bmax[a]; }
     f.do_centroid = h[80];
     f.cct = ld_u32_unaligned(h + 83);
+    f.point_res_f = (float)ld_f64_unaligned(h + 24);
     f.point_count = point_count; f.res = res;
     pos += 92;
     // [PCL] readFrameHeader -> defineBoundingBox -> getKeyBitSize
@@ -335,8 +336,9 @@ __global__ void __launch_bounds__(32) dec_finish_kernel(DecFrame *frames) {
       }
     }
   }
-  // trailing bytes would switch the reference into detail mode (impl.hpp:1802-1806): outside the implemented scope
-  if (ok && pos != len) { ok = false; err |= FERR_UNSUPPORTED; }
+  // trailing bytes switch the reference into detail mode (impl.hpp:1802-1806): the enhancement vectors follow
+  __syncwarp();
+  if (ok && pos != len) { ok = decode_detail_layers(f, in, len, pos, freq, err); if (ok && pos != len) ok = false; }
   if (lane == 0) {
     if (!ok) { atomicOr(&f.error, err ? err : FERR_BAD_STREAM); f.B = 0; f.V = 0; }
     else {

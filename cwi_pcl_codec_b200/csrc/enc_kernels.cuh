@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(256) leaf_emit_kernel(EncFrame *frames, EncPar
     uint8_t *o = f.avg + 3ull * j;
     o[0] = (uint8_t)c0; o[1] = (uint8_t)c1; o[2] = (uint8_t)c2;
   }
-  if (P.do_centroid) {
+  if (P.do_centroid && !P.detail) {                      // detail mode codes per-point residuals instead (detail_emit_kernel)
     float ax = 0.f, ay = 0.f, az = 0.f;                  // pcl::compute3DCentroid: float accumulation in index order
     for (uint32_t k = s0; k < s1; k++) {
       float4 q = __ldg((const float4 *)(f.pts + 32ull * vals[k]));
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(256) leaf_emit_kernel(EncFrame *frames, EncPar
     }
   }
   if (j == V - 1) {
-    if (P.do_centroid) f.ncen = 3 * V;
+    if (P.do_centroid) f.ncen = P.detail ? 0 : 3 * V;   // detail mode: the (empty) centroid vector is still written (impl.hpp:1701-1707)
     if (P.do_color && P.color_type != 1 && P.color_type != 2) f.ncolor = 3 * V;   // raw averages are the payload
   }
 }

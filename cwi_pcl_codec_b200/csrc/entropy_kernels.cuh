@@ -19,7 +19,9 @@
 __device__ __forceinline__ void enc_layer(const EncFrame &f, int which, const uint8_t *&src, uint32_t &n) {
   if (which == 0) { src = f.tree; n = f.B; }
   else if (which == 1) { src = f.cen; n = f.ncen; }
-  else { src = f.cpay; n = f.ncolor; }
+  else if (which == 2) { src = f.cpay; n = f.ncolor; }
+  else if (which == 3) { src = f.pdiff; n = f.npd; }       // detail mode: point differences
+  else { src = f.cdiff; n = f.ncd; }                       // detail mode: colour differences
 }
 __global__ void __launch_bounds__(256) hist_kernel(EncFrame *frames) {
   EncFrame &f = frames[blockIdx.z];
@@ -63,19 +65,19 @@ __device__ __forceinline__ uint32_t rc_equal_bits(uint32_t x) {
 }
 
 // ---- range encoder: one block per frame (steered over the SMs), one warp per layer (tree, centroid, colour)
-__global__ void __launch_bounds__(96) rc_encode_kernel(EncFrame *frames, int do_centroid, int do_color) {
+__global__ void __launch_bounds__(160) rc_encode_kernel(EncFrame *frames, int do_centroid, int do_color, int detail) {
   EncFrame &f = frames[blockIdx.x];
   if (threadIdx.x == 0) f.serial_sm = sm_id();
   if (f.V == 0) return;
   const int which = threadIdx.x >> 5;
-  if ((which == 1 && !do_centroid) || (which == 2 && !do_color)) return;
+  if ((which == 1 && !do_centroid) || (which == 2 && !do_color) || (which == 3 && !detail) || (which == 4 && !(detail && do_color))) return;
   const uint8_t *src; uint32_t n;
   enc_layer(f, which, src, n);
   uint8_t *dst; uint64_t cap;
   if (which == 0) { dst = f.stream + FRAME_HDR_BYTES + 8; cap = f.stream_cap > FRAME_HDR_BYTES + 8 ? f.stream_cap - FRAME_HDR_BYTES - 8 : 0; }
   else { dst = f.rc_tmp[which - 1]; cap = f.rc_tmp_cap[which - 1]; }
-  __shared__ uint32_t freq_all[3][257];
-  __shared__ uint32_t packed_all[3][256];
+  __shared__ uint32_t freq_all[5][257];
+  __shared__ uint32_t packed_all[5][256];
   uint32_t *freq = freq_all[which], *packed = packed_all[which];
   const uint32_t lane = lane_id();
   if (lane == 0) rc_build_table(f.hist + which * 256, freq);
@@ -174,9 +176,9 @@ __global__ void __launch_bounds__(96) rc_encode_kernel(EncFrame *frames, int do_
 // The arithmetic per symbol is the one above (closed-form renormalisation, branch-free word flush); only the rare
 // underflow loop diverges.  grid (ceil(frames / 32), 3 layers), one warp per CTA.
 #define LPS_SYMS 16
-__global__ void __launch_bounds__(32) rc_encode_lps_kernel(EncFrame *frames, int nframes, int do_centroid, int do_color) {
+__global__ void __launch_bounds__(32) rc_encode_lps_kernel(EncFrame *frames, int nframes, int do_centroid, int do_color, int detail) {
   const int which = blockIdx.y;
-  if ((which == 1 && !do_centroid) || (which == 2 && !do_color)) return;
+  if ((which == 1 && !do_centroid) || (which == 2 && !do_color) || (which == 3 && !detail) || (which == 4 && !(detail && do_color))) return;
   __shared__ uint32_t tab[257 * 32];                       // [symbol][lane]: cumulative table, then (cum << 16 | width)
   const uint32_t lane = lane_id();
   const int fi = blockIdx.x * 32 + lane;
@@ -289,7 +291,11 @@ __global__ void __launch_bounds__(256) assemble_kernel(EncFrame *frames, HeaderP
   const uint64_t l0 = f.rc_len[0], l1 = H.do_centroid ? f.rc_len[1] : 0, l2 = H.with_color ? f.rc_len[2] : 0;
   const uint64_t off_cen = FRAME_HDR_BYTES + 8 + l0;
   const uint64_t off_col = off_cen + (H.do_centroid ? 4 + l1 : 0);
-  const uint64_t total = off_col + (H.with_color ? 8 + l2 : 0);
+  const uint64_t off_cnt = off_col + (H.with_color ? 8 + l2 : 0);               // detail mode (impl.hpp:1728-1757): counts, point differences, colour differences
+  const uint64_t li = H.do_voxel_grid ? 0 : f.rc_int_len, l3 = H.do_voxel_grid ? 0 : f.rc_len[3], l4 = (!H.do_voxel_grid && H.with_color) ? f.rc_len[4] : 0;
+  const uint64_t off_pd = off_cnt + (H.do_voxel_grid ? 0 : 8 + li);
+  const uint64_t off_cd = off_pd + (H.do_voxel_grid ? 0 : 8 + l3);
+  const uint64_t total = off_cd + ((!H.do_voxel_grid && H.with_color) ? 8 + l4 : 0);
   if (total > f.stream_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) { atomicOr(&f.error, FERR_STREAM_CAP); f.out_len = 0; } return; }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const char id2[] = "<PCL-OCT-CODECV2-COMPRESSED>", id1[] = "<PCL-OCT-COMPRESSED>";
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(EncFrame *frames, HeaderP
     auto put = [&](uint64_t off, const void *p, int nb) { const uint8_t *q = (const uint8_t *)p; for (int k = 0; k < nb; k++) s[off + k] = q[k]; };
     uint32_t fid = f.frame_id; put(48, &fid, 4);
     s[52] = 1; s[53] = H.do_voxel_grid; s[54] = H.with_color;
-    uint64_t pc = f.V; put(55, &pc, 8);
+    uint64_t pc = H.do_voxel_grid ? f.V : f.n_finite; put(55, &pc, 8);   // [PCL] writeFrameHeader: leaf_count_ or object_count_
     put(63, &H.octree_res, 8); s[71] = H.color_bits; put(72, &H.point_res, 8);
     put(80, f.bmin, 24); put(104, f.bmax, 24);
     s[128] = H.do_centroid; s[129] = H.connectivity; s[130] = H.scalable;
@@ -306,12 +312,22 @@ __global__ void __launch_bounds__(256) assemble_kernel(EncFrame *frames, HeaderP
     uint64_t B = f.B; put(140, &B, 8);
     if (H.do_centroid) { uint32_t c = f.ncen; put(off_cen, &c, 4); }
     if (H.with_color) { uint64_t c = f.ncolor; put(off_col, &c, 8); }
+    if (!H.do_voxel_grid) {
+      uint64_t c = f.V; put(off_cnt, &c, 8);
+      c = f.npd; put(off_pd, &c, 8);
+      if (H.with_color) { c = f.ncd; put(off_cd, &c, 8); }
+    }
     f.out_len = total;
     f.coded[0] = l0; f.coded[1] = l1; f.coded[2] = l2;
   }
   const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (uint64_t)gridDim.x * blockDim.x;
   if (H.do_centroid) for (uint64_t k = gtid; k < l1; k += gsz) s[off_cen + 4 + k] = f.rc_tmp[0][k];
   if (H.with_color) for (uint64_t k = gtid; k < l2; k += gsz) s[off_col + 8 + k] = f.rc_tmp[1][k];
+  if (!H.do_voxel_grid) {
+    for (uint64_t k = gtid; k < li; k += gsz) s[off_cnt + 8 + k] = f.rc_int[k];
+    for (uint64_t k = gtid; k < l3; k += gsz) s[off_pd + 8 + k] = f.rc_tmp[2][k];
+    for (uint64_t k = gtid; k < l4; k += gsz) s[off_cd + 8 + k] = f.rc_tmp[3][k];
+  }
 }
 
 // ---- stream export: the assembled frame leaves the codec's slot for the caller's buffer (device memory, or pinned

@@ -42,7 +42,7 @@ typedef enum ccv2_status {
   CCV2_OK = 0,
   CCV2_ERR_ARG = -1,          /* bad argument */
   CCV2_ERR_CUDA = -2,         /* CUDA runtime error / no device (see ccv2_last_error) */
-  CCV2_ERR_UNSUPPORTED = -3,  /* configuration outside the implemented scope (detail mode, profiles != MANUAL) */
+  CCV2_ERR_UNSUPPORTED = -3,  /* outside the implemented scope: profiles != MANUAL; decoding a detail-mode frame with a JPEG colour type (undefined in the reference) */
   CCV2_ERR_CAPACITY = -4,     /* caller's output buffer too small */
   CCV2_ERR_WORKSPACE = -5,    /* internal workspace bound exceeded (tree bytes / stream arena) */
   CCV2_ERR_STREAM = -6,       /* malformed compressed stream */
@@ -56,7 +56,8 @@ typedef struct ccv2_params {
   int32_t show_statistics;         /* showStatistics_arg (accepted, ignored: PCL_INFO printing is not reproduced) */
   double point_resolution;         /* pointResolution_arg   (eval.hpp:381: 2^-(octree_bits+enh_bits)) */
   double octree_resolution;        /* octreeResolution_arg  (eval.hpp:383: 2^-octree_bits) */
-  int32_t do_voxel_grid_downsampling; /* doVoxelGridDownDownSampling_arg (eval.hpp:385 passes true; only true is implemented) */
+  int32_t do_voxel_grid_downsampling; /* doVoxelGridDownDownSampling_arg (eval.hpp:385 passes true); false = detail mode, the class default: per-point
+                                         residuals at point_resolution and colour differences (impl.hpp:1525-1541, 1728-1757) */
   uint32_t i_frame_rate;           /* iFrameRate_arg (eval.hpp:386 passes 0: every frame is an I frame) */
   int32_t do_color_encoding;       /* doColorEncoding_arg */
   uint8_t color_bit_resolution;    /* colorBitResolution_arg */
@@ -169,6 +170,19 @@ const char *ccv2_status_string(int status);
  * device memory for cap_points records; *npoints receives the voxel count (also when cap_points is too small:
  * CCV2_ERR_CAPACITY). */
 int ccv2_get_output_cloud(ccv2_codec *c, int frame, void *points_out, size_t cap_points, size_t *npoints);
+
+/* Tile mode (BASELINE configs[3]; no counterpart in the reference, which has no parallelism: CMakeLists.txt:85-87).  One
+ * large frame is cut into 2^tile_bits (8 or 64) spatial tiles of the unit cube evaluate_compression normalises clouds
+ * into (impl.hpp:1915-1945): tile = Morton index, x most significant, of floor(p * 2^(tile_bits/3)) per axis, clamped.
+ * Every tile keeps its points in their original relative order and is encoded as an ordinary frame, so each tile stream
+ * is what encodePointCloud (codec.h:174-175) writes for that subset and any reference decoder reads it; the union of the
+ * decoded tiles is the decoded frame.  The tiles' serial entropy stages run side by side: that is what shortens the
+ * latency of a single frame, on one GPU or over the ranks of a node (first_tile = rank, tile_step = world size).
+ * ccv2_split_tiles: stable partition only (pts_out: n records, host or device; tile_offsets: 2^tile_bits + 1 entries).
+ * ccv2_encode_tiles: partition + encode; out / out_cap / out_len (and tile_npts, may be NULL) are indexed by tile. */
+int ccv2_split_tiles(ccv2_codec *c, const void *pts, size_t n, int tile_bits, void *pts_out, size_t *tile_offsets);
+int ccv2_encode_tiles(ccv2_codec *c, const void *pts, size_t n, int tile_bits, int first_tile, int tile_step,
+                      void *const *out, const size_t *out_cap, size_t *out_len, size_t *tile_npts);
 
 /* Replaces: computeQualityMetric(cloud_a, cloud_b, QualityMetric&) of evaluate_compression
  * (apps/evaluate_compression/include/pcl/apps/evaluate_compression/impl/quality_metrics_impl.hpp:82-239; struct

@@ -57,7 +57,7 @@ def test_no_cpu_fallback_without_a_device(K):
 def test_unsupported_configurations_are_rejected_before_touching_cuda(K):
     lib = K.load_library()
     h = C.c_void_p()
-    for kw, want in [(dict(profile=3), -3), (dict(do_voxel_grid_downsampling=0), -3), (dict(color_coding_type=7), -1), (dict(octree_resolution=0.0), -1)]:
+    for kw, want in [(dict(profile=3), -3), (dict(color_coding_type=7), -1), (dict(octree_resolution=0.0), -1), (dict(color_bit_resolution=9), -1)]:
         assert lib.ccv2_create(C.byref(K.default_params(**kw)), 0, C.byref(h)) == want
         assert lib.ccv2_last_error(None)
 

@@ -163,7 +163,7 @@ def test_baseline_config_0_end_to_end(exe, oracle, tmp_path):
     cl = raw_cloud(10000, 0)
     write_ply(d / "frame_0000.ply", cl, True)
     out = tmp_path / "out"
-    r = subprocess.run([exe, "-b", "8", "-t", "1", "-j", "85", "-q", "-o", str(out), "--intra_frame_quality_csv", str(tmp_path / "q.csv"), "--predictive_quality_csv", "", str(d)],
+    r = subprocess.run([exe, "-b", "8", "-t", "1", "-j", "85", "-q", "1", "-o", str(out), "--intra_frame_quality_csv", str(tmp_path / "q.csv"), "--predictive_quality_csv", "", str(d)],
                        capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 0, r.stderr + r.stdout
     (norm,), mn_bb, mx_bb = normalize_group([np.stack([cl["x"], cl["y"], cl["z"]], 1)], 0.2)
