@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "Mpoints/s encode+decode @ depth-11 intra; bitstream bit-exact vs ref"
+INFLIGHT_CALLS = int(os.environ.get("BENCH_INFLIGHT_CALLS", "3"))     # steps submitted ahead (ccv2_submit_*): the library holds up to three calls in flight
 
 
 def shard_frames(n_frames_per_rank, rank, world):
@@ -231,7 +232,7 @@ def main():
             avail = psutil.virtual_memory().available
         except Exception:
             avail = 64 << 30
-        per_frame = NP * 32 * 3 + 2 * cap
+        per_frame = NP * 32 * (1 + INFLIGHT_CALLS) + INFLIGHT_CALLS * cap
         F_e2e = int(max(8, min(F, (0.6 * avail / world) // per_frame)))
     h_in = K.PinnedBuffer(F_e2e * NP * 32) if F_e2e else None
 
@@ -276,7 +277,7 @@ def main():
         launches, pend, res = 0, [], None
         for _ in range(k):
             pend.append(submit())
-            if len(pend) == 2:
+            if len(pend) == INFLIGHT_CALLS:
                 res = pend.pop(0).wait(); launches += codec.last_launch_count
         while pend:
             res = pend.pop(0).wait(); launches += codec.last_launch_count
@@ -348,13 +349,13 @@ def main():
         torch.cuda.empty_cache()
         ceiling = pcie_ceiling(torch, dist, world, dev)
         # one pinned allocation per role, sliced per frame; two sets of result buffers (consecutive steps are in flight together)
-        h_str = [K.PinnedBuffer(FE * cap) for _ in range(2)]; h_out = [K.PinnedBuffer(FE * NP * 32) for _ in range(2)]
+        h_str = [K.PinnedBuffer(FE * cap) for _ in range(INFLIGHT_CALLS)]; h_out = [K.PinnedBuffer(FE * NP * 32) for _ in range(INFLIGHT_CALLS)]
         hi = [h_in.ptr + i * NP * 32 for i in range(FE)]
         hs = [[b.ptr + i * cap for i in range(FE)] for b in h_str]; ho = [[b.ptr + i * NP * 32 for i in range(FE)] for b in h_out]
         flip = [0]
 
         def submit_host():
-            k = flip[0]; flip[0] ^= 1
+            k = flip[0]; flip[0] = (k + 1) % INFLIGHT_CALLS
             return codec.submit_roundtrip_raw(hi, [NP] * FE, hs[k], [cap] * FE, ho[k], [NP] * FE)
         run_steps(2, submit_host)
         barrier()
@@ -367,7 +368,7 @@ def main():
         e2e = {"value": world * FE * NP * args.steps / t_e2e / 1e6, "unit": "Mpoints/s", "frames_per_step_per_gpu": FE,
                "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
                "d2h_note": "decoded clouds come down as one capacity-sized transfer per frame (32 B x %d records, of which %.0f are voxels); streams by zero-copy stores at their exact size" % (NP, float(np.mean(n2))),
-               "api": "ccv2_submit_roundtrip / ccv2_wait, two calls in flight",
+               "api": "ccv2_submit_roundtrip / ccv2_wait, %d calls in flight" % INFLIGHT_CALLS,
                "timing": "wall clock around K pipelined C-ABI calls, pinned host buffers in and out, max over ranks; the stream stays on the device between encoder and decoder (its 1.2 MB/frame re-upload is not part of the step)",
                "pcie_ceiling_gbs": ceiling, "achieved_h2d_gbs": gbs[0], "achieved_d2h_gbs": gbs[1],
                "frac_of_pcie": max(gbs[0] / ceiling["h2d_gbs"], gbs[1] / ceiling["d2h_gbs"])}
@@ -391,7 +392,7 @@ def main():
                 "vs_baseline": None, "dtype": "u8/u32/f64 (integer codec, FP64 keys)", "data": "synthetic",
                 "config": dict(workload_config(args, F), distinct_clouds_per_gpu=U), "bit_exact_vs_oracle": bit_exact, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "value_api": "ccv2_submit_roundtrip x K (two calls in flight), ccv2_wait" if args.value_api == "roundtrip" else "ccv2_encode_batch + ccv2_decode_batch",
+                "value_api": "ccv2_submit_roundtrip x K (%d calls in flight), ccv2_wait" % INFLIGHT_CALLS if args.value_api == "roundtrip" else "ccv2_encode_batch + ccv2_decode_batch",
                 "encode_ms_per_step": split_final["enc"] / split_steps, "decode_ms_per_step": split_final["dec"] / split_steps,
                 "encode_only_mpoints_s": F * NP * split_steps / max(split_final["enc"], 1e-9) / 1e3, "decode_only_mpoints_s": F * NP * split_steps / max(split_final["dec"], 1e-9) / 1e3,
                 "single_frame_latency_ms": lat, "stream_bytes_per_frame": S, "voxels_per_frame": V}
@@ -430,7 +431,7 @@ def run_decode_mode(args, torch, dist, K, rank, world, local, dev):
         pend, res, launches = [], None, 0
         for _ in range(k):
             pend.append(codec.submit_decode_raw(sp, sl, op_, [NP] * F))
-            if len(pend) == 2:
+            if len(pend) == INFLIGHT_CALLS:
                 res = pend.pop(0).wait(); launches += codec.last_launch_count
         while pend:
             res = pend.pop(0).wait(); launches += codec.last_launch_count
@@ -476,7 +477,7 @@ def run_decode_mode(args, torch, dist, K, rank, world, local, dev):
                 "single_frame_latency_ms": lat, "stream_bytes_per_frame": S, "voxels_per_frame": V,
                 "roofline": {"bound": "hbm", "achieved": alg * F / (t_dev / args.steps) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg * F / (t_dev / args.steps) / 1e9 / peak,
                              "traffic": None, "note": "step level: algorithmic decode bytes (S + 32 V) x frames per step / step time"},
-                "api": "ccv2_submit_decode x K (two calls in flight), ccv2_wait"}
+                "api": "ccv2_submit_decode x K (%d calls in flight), ccv2_wait" % INFLIGHT_CALLS}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

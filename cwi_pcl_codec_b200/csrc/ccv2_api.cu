@@ -88,7 +88,7 @@ constexpr int MAX_STREAMS = 20;         // work streams: long-lived set s always
 constexpr int SIDE_STREAMS = 6;          // group + side + copy + control streams stay within 32 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, see ccv2.h)
 constexpr int MAX_GROUP = 128;           // frames per group.  The serial range-coder kernels are latency bound (0.1-0.4 s per launch whatever the frame count),
                                          // so throughput = frames per launch x launches in flight: large groups, one stream each (measured: 32-frame groups 650, 64 1040-1270 Mpoints/s)
-constexpr int N_CALLS = 3;               // call contexts: two user calls in flight + one for the retry of a frame that overflowed its workspace
+constexpr int N_CALLS = 4;               // call contexts: three user calls in flight + one for the retry of a frame that overflowed its workspace
 
 struct DoneRc { int ticket, rc; };
 enum PtrKind : char { PK_NONE = 0, PK_DEVICE = 1, PK_PINNED = 2, PK_PAGEABLE = 3 };
@@ -130,8 +130,8 @@ struct ccv2_codec {
   int trace = 0;                          // CCV2_TRACE=1: print per-group timeline (ms since call start) to stderr
   int use_ring = 1;                       // pipeline the DFS walk behind the range decoder (CCV2_NO_RING=1 disables: debugging)
   int n_streams = 0, group = 0;           // CCV2_STREAMS / CCV2_GROUP overrides (0 = automatic)
-  int inflight_max = 2048;                // frames the long-lived ring may hold (CCV2_INFLIGHT); memory permitting
-  int fe_frames = 256;                    // frames the front-end ring holds (CCV2_FE_FRAMES); at least two sets
+  int inflight_max = 3072;                // frames the long-lived ring may hold (CCV2_INFLIGHT); memory permitting
+  int fe_frames = 0;                      // frames the front-end ring holds (CCV2_FE_FRAMES; 0 = 256, or 512 when host inputs are staged in it); at least two sets
   cudaStream_t main_stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr, fin_stream = nullptr;
   cudaStream_t streams[MAX_STREAMS] = {};
   cudaStream_t ser_streams[MAX_STREAMS] = {};     // green contexts on: the same slots on the serial partition's SMs; off: aliases of streams[]
@@ -294,8 +294,11 @@ size_t rc_cap_for(size_t raw_cap) { return ((raw_cap + raw_cap / 8 + 4096) + 255
 size_t itab_cap_for(size_t n, bool boost) { return boost ? 4 * (n + 2) : std::min<size_t>(4 * (n + 2), 65536); }
 size_t rc_int_cap_for(size_t n, bool boost) { return ((9 + 8 * itab_cap_for(n, boost) + 8 * n + 64) + 255) & ~size_t(255); }
 size_t diff_cap_for(size_t n) { return ((3 * n + 64) + 255) & ~size_t(255); }
+// The stream: with `boost` the sum of every layer's worst case; by default half of that for the tree and colour layers
+// (occupancy bytes code to ~0.6 of their size, a stream that does not fit is flagged and retried like the other bounds).
 size_t stream_cap_for(size_t n, bool cen, bool boost, bool detail = false) {
-  return FRAME_HDR_BYTES + 8 + rc_cap_for(tree_cap_for(n, boost)) + (cen ? 4 + rc_cap_for(cen_cap_for(n)) : 0) + 8 + rc_cap_for(cpay_cap_for(n, boost)) +
+  const size_t tc = rc_cap_for(tree_cap_for(n, boost)) + rc_cap_for(cpay_cap_for(n, boost));
+  return FRAME_HDR_BYTES + 8 + (boost || n < 65536 ? tc : tc / 2 + 65536) + (cen ? 4 + rc_cap_for(cen_cap_for(n)) : 0) + 8 +
          (detail ? 8 + rc_int_cap_for(n, boost) + 2 * (8 + rc_cap_for(diff_cap_for(n))) : 0);
 }
 
@@ -367,7 +370,7 @@ size_t carve_enc_ll(uint8_t *base, size_t n, EncFrame *f, bool cen, bool boost, 
   return cv.end();
 }
 // decoder workspace of one frame: ncap = voxels it may hold, tcap / ccap = tree / colour payload bytes
-size_t carve_dec(uint8_t *base, size_t ncap, size_t tcap, size_t ccap, DecFrame *f, size_t *zero_bytes, bool lines, size_t dpts /* detail mode: points the frame may hold, 0 = no detail buffers */, bool boost) {
+size_t carve_dec(uint8_t *base, size_t ncap, size_t tcap, size_t ccap, DecFrame *f, size_t *zero_bytes, bool lines, size_t dpts /* detail mode: points the frame may hold, 0 = no detail buffers */, bool boost, bool cen) {
   Carver cv(base);
   const size_t lines_cap = lines ? ncap / LINE_PX + 2 : 0;
   const size_t img_h = ncap / 256 + 2, mcu_h = (img_h + 15) / 16, nblocks = lines ? (lines_cap * LINE_MCU_STRIDE + LINE_MCU_STRIDE) * 6 : mcu_h * 16 * 6;
@@ -376,7 +379,7 @@ size_t carve_dec(uint8_t *base, size_t ncap, size_t tcap, size_t ccap, DecFrame 
   int16_t *coef = cv.take<int16_t>(nblocks * 64 + 64);
   const size_t z1 = cv.end();
   uint8_t *tree = cv.take<uint8_t>(tcap + 64);
-  uint8_t *cen = cv.take<uint8_t>(cen_cap_for(ncap));
+  uint8_t *cenb = cv.take<uint8_t>(cen ? cen_cap_for(ncap) : 256);
   uint8_t *col = cv.take<uint8_t>(ccap + 64);
   // The pipelined walker records level depth-2 branches (l2_*), the fallback walkers bottom-level branches (node_*): a
   // frame uses one or the other, so they share their memory.
@@ -403,7 +406,7 @@ size_t carve_dec(uint8_t *base, size_t ncap, size_t tcap, size_t ccap, DecFrame 
     f->counts = counts; f->counts_cap = dpts ? (uint32_t)ncap : 0; f->dleaf_key = dleaf_key; f->pdiff = pdiff; f->cdiff = cdiff; f->pdiff_cap = dpts ? 3 * dpts : 0;
     f->itab = itab; f->itab_cap = dpts ? (uint32_t)itab_cap_for(dpts, boost) : 0;
     f->scan_status = scan_status; f->scan_tiles_max = scan_tiles; f->coef = coef; f->coef_cap_blocks = (uint32_t)nblocks;
-    f->tree = tree; f->tree_cap = (uint32_t)std::min(tcap, (size_t)0xFFFFFF00u); f->cen = cen; f->cen_cap = (uint32_t)cen_cap_for(ncap) - 64;
+    f->tree = tree; f->tree_cap = (uint32_t)std::min(tcap, (size_t)0xFFFFFF00u); f->cen = cenb; f->cen_cap = cen ? (uint32_t)cen_cap_for(ncap) - 64 : 192;
     f->col = col; f->col_cap = (uint32_t)std::min(ccap, (size_t)0xFFFFFF00u);
     f->node_prefix = node_prefix; f->node_byte = node_byte; f->node_cap = (uint32_t)ncap;
     f->l2_prefix = l2_prefix; f->l2_mask = l2_mask; f->l2_off = l2_off;
@@ -709,7 +712,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
   const ccv2_params &prm = c->prm;
   const bool cen = prm.do_voxel_grid_centroid != 0, color = prm.do_color_encoding != 0, lines = prm.color_coding_type == 2;
   const bool detail = prm.do_voxel_grid_downsampling == 0;           // the encoder's mode; a decoder learns it from the stream
-  CallCtx &x = boost ? c->calls[N_CALLS - 1] : c->calls[c->user_calls++ & 1];
+  CallCtx &x = boost ? c->calls[N_CALLS - 1] : c->calls[c->user_calls++ % (N_CALLS - 1)];
   if (x.busy) finish_call(c, x);
   const int ticket = c->next_ticket++;
   if (ticket_out) *ticket_out = ticket;
@@ -723,6 +726,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
   x.stage_off_stream.assign(nframes + 1, 0); x.stage_off_pts.assign(nframes + 1, 0);
   size_t nmax = 1, ncap_max = 1, tcap_max = 0, ccap_max = 0, in_stage_max = 0, out_stage_max = 0, stage_total = 0, dpts_max = 0;
   bool host_in_any = false;
+  bool dec_cen = rt ? (cen && !detail) : false;            // does any frame carry a centroid layer?  (round trip: the encoder's setting; decode: the header, or assume so)
   std::vector<size_t> dcount(nframes, 0);                  // records a pinned destination receives by one copy-engine transfer
   for (int i = 0; i < nframes; i++) {
     if (do_enc) {
@@ -752,8 +756,9 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
           tcap = (size_t)std::min<uint64_t>(pi.B, 22ull * ncap + 1024) + 1024;          // B <= depth * V: a larger size word is a malformed stream
           ccap = cpay_cap_for(ncap, boost) + (boost ? 2 * in_len[i] : 0);
           dcount[i] = ncap;
-          if (!pi.voxel_grid) dpts_max = std::max(dpts_max, ncap);               // detail-mode stream: room for the enhancement vectors
-        } else { ncap = std::max<size_t>(ncap, 1); tcap = tree_cap_for(ncap, boost); ccap = cpay_cap_for(ncap, boost) + (boost ? 2 * in_len[i] : 0); dcount[i] = pts_cap[i]; if (boost) dpts_max = std::max(dpts_max, ncap); }   // header not read here: detail buffers only on the retry
+          if (!pi.voxel_grid) dpts_max = std::max(dpts_max, ncap);
+          if (pi.centroid) dec_cen = true;               // detail-mode stream: room for the enhancement vectors
+        } else { ncap = std::max<size_t>(ncap, 1); tcap = tree_cap_for(ncap, boost); ccap = cpay_cap_for(ncap, boost) + (boost ? 2 * in_len[i] : 0); dcount[i] = pts_cap[i]; dec_cen = true; if (boost) dpts_max = std::max(dpts_max, ncap); }   // header not read here: detail buffers only on the retry
       }
       ncap_max = std::max(ncap_max, ncap); tcap_max = std::max(tcap_max, tcap); ccap_max = std::max(ccap_max, ccap);
       if (x.pts_kind[i] == PK_PINNED) out_stage_max = std::max(out_stage_max, (32 * dcount[i] + 255) & ~size_t(255));
@@ -767,14 +772,17 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
 
   size_t fe_bytes = 0, fe_zero = 0, ll_bytes = 0, stream_end = 0, enc_ll = 0, dec_ws = 0, dec_zero = 0;
   if (do_enc) { size_t zo; fe_bytes = carve_fe(nullptr, nmax, nullptr, prm, boost, host_in_any, &zo, &fe_zero); enc_ll = carve_enc_ll(nullptr, nmax, nullptr, cen, boost, &stream_end, detail); }
-  if (do_dec) dec_ws = carve_dec(nullptr, ncap_max, tcap_max, ccap_max, nullptr, &dec_zero, lines, dpts_max, boost);
+  if (do_dec) dec_ws = carve_dec(nullptr, ncap_max, tcap_max, ccap_max, nullptr, &dec_zero, lines, dpts_max, boost, dec_cen);
   const size_t ws_off = rt ? stream_end : 0;                          // round trip: the decoder's workspace lies over the encoder's dead buffers
   const size_t in_stage_off = std::max(enc_ll, ws_off + dec_ws);
   const size_t out_stage_off = in_stage_off + in_stage_max;
   ll_bytes = out_stage_off + out_stage_max;
   {
-    const int want_ll = std::max(1, std::min(2 * ngroups, (c->inflight_max + G - 1) / G));
-    const int want_fe = std::max(1, std::min(2 * ngroups, std::max(2, c->fe_frames / G)));
+    const int want_ll = std::max(1, std::min((N_CALLS - 1) * ngroups, (c->inflight_max + G - 1) / G));
+    // host inputs are uploaded into the front-end set: with only two sets the copy engine waits whenever a front-end runs long
+    // under load (measured: 140 ms instead of 20, the next upload 90 ms late), so staged inputs get four
+    const int fe_frames = c->fe_frames ? c->fe_frames : (host_in_any ? 512 : 256);
+    const int want_fe = std::max(1, std::min((N_CALLS - 1) * ngroups, std::max(2, fe_frames / G)));
     int rc;
     if (do_enc && (rc = ensure_ring(c, c->fe, fe_bytes, G, want_fe, "front-end")) != CCV2_OK) return rc;
     if ((rc = ensure_ring(c, c->ll, ll_bytes, G, want_ll, "long-lived")) != CCV2_OK) return rc;
@@ -854,7 +862,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
         default: f.out_pts = (uint8_t *)pts_out[i]; break;
       }
       f.out_cap = pts_cap[i];
-      carve_dec(lb + ws_off, ncap_max, tcap_max, ccap_max, &f, nullptr, lines, dpts_max, boost);
+      carve_dec(lb + ws_off, ncap_max, tcap_max, ccap_max, &f, nullptr, lines, dpts_max, boost, dec_cen);
       f.zero_ptr = lb + ws_off; f.zero_bytes = dec_zero;
     }
   }

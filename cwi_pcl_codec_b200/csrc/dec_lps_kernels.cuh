@@ -22,7 +22,9 @@
 #pragma once
 #include "dec_kernels.cuh"
 
+#ifndef LPS_DEC_FRAMES
 #define LPS_DEC_FRAMES 8
+#endif
 #define LPS_LUT_SHIFT 4
 #define LPS_LUT_ENTRIES (65536 >> LPS_LUT_SHIFT)
 #define LPS_Q_SLACK 3                                      // the float quotient estimate is within [-3, +0] of ... see LPS_DEC_LOOKUP

@@ -110,7 +110,7 @@ int ccv2_roundtrip_batch(ccv2_codec *c, int nframes, const void *const *pts, con
                          void *const *pts_out, const size_t *pts_cap, size_t *npts_out);
 
 /* Asynchronous forms of the three calls above: enqueue the whole batch and return a ticket; ccv2_wait(ticket) blocks until
- * the results are in the caller's buffers and returns the call's status.  Two calls may be in flight on one handle (a third
+ * the results are in the caller's buffers and returns the call's status.  Three calls may be in flight on one handle (a fourth
  * submit collects the oldest first): they share the codec's workspace rings, so the uploads and parallel kernels of the
  * next call overlap the serial entropy stages of the previous one -- a continuous pipeline over consecutive batches,
  * which the synchronous calls cannot give (each pays the pipeline's fill and drain).  All arrays passed to a submit call
