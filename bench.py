@@ -498,8 +498,12 @@ def run_tiles_mode(args, torch, dist, K, rank, world, local, dev):
     d_in = torch.from_numpy(fr.view(np.uint8).reshape(-1)).to(dev)
     cap = 2 * NP + (1 << 20)
     mine = T.owned_tiles(tb, rank, world)
-    d_str = {t: torch.empty(cap // max(1, nt // 8) + (1 << 20), dtype=torch.uint8, device=dev) for t in mine}
-    d_out = {t: torch.empty(NP * 32 // max(1, nt // 4) + (1 << 20), dtype=torch.uint8, device=dev) for t in mine}
+    probe = K.Codec(K.default_params(octree_bits=bits), device=local)
+    _, tile_off = probe.split_tiles(fr, tb)                        # points per tile: sizes of this rank's stream and cloud buffers
+    probe.close()
+    tn = [tile_off[t + 1] - tile_off[t] for t in range(nt)]
+    d_str = {t: torch.empty(4 * tn[t] + (1 << 18), dtype=torch.uint8, device=dev) for t in mine}
+    d_out = {t: torch.empty(32 * max(tn[t], 1), dtype=torch.uint8, device=dev) for t in mine}
     results = {}
 
     def barrier():

@@ -85,7 +85,7 @@ struct Carver {
 
 constexpr int MAX_STREAMS = 20;         // work streams: long-lived set s always runs on stream s mod 20 -- a group waits for the previous user of its set anyway,
                                          // so with at most 20 sets no group ever queues behind a stream that is busy with an unrelated one
-constexpr int SIDE_STREAMS = 6;          // group + side + copy + control streams stay within 32 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, see ccv2.h)
+constexpr int SIDE_STREAMS = 20;         // one per work stream: a group's colour layer must not queue behind another group's (100 ms each)          // group + side + copy + control streams stay within 32 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, see ccv2.h)
 constexpr int MAX_GROUP = 128;           // frames per group.  The serial range-coder kernels are latency bound (0.1-0.4 s per launch whatever the frame count),
                                          // so throughput = frames per launch x launches in flight: large groups, one stream each (measured: 32-frame groups 650, 64 1040-1270 Mpoints/s)
 constexpr int N_CALLS = 4;               // call contexts: three user calls in flight + one for the retry of a frame that overflowed its workspace
@@ -130,6 +130,8 @@ struct ccv2_codec {
   int trace = 0;                          // CCV2_TRACE=1: print per-group timeline (ms since call start) to stderr
   int use_ring = 1;                       // pipeline the DFS walk behind the range decoder (CCV2_NO_RING=1 disables: debugging)
   int n_streams = 0, group = 0;           // CCV2_STREAMS / CCV2_GROUP overrides (0 = automatic)
+  int n_side = SIDE_STREAMS;              // side streams in use (CCV2_SIDE)
+  int enc_reserve = 1;                    // lane-per-stream encoder CTAs reserve half an SM's shared memory (one CTA per SM); CCV2_ENC_RESERVE=0 turns it off
   int inflight_max = 3072;                // frames the long-lived ring may hold (CCV2_INFLIGHT); memory permitting
   int fe_frames = 0;                      // frames the front-end ring holds (CCV2_FE_FRAMES; 0 = 256, or 512 when host inputs are staged in it); at least two sets
   cudaStream_t main_stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr, fin_stream = nullptr;
@@ -523,6 +525,8 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   if (const char *s = getenv("CCV2_NO_RING")) c->use_ring = atoi(s) ? 0 : 1;
   if (const char *s = getenv("CCV2_STREAMS")) c->n_streams = std::max(0, std::min(MAX_STREAMS, atoi(s)));
   if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(256, atoi(s)));
+  if (const char *s = getenv("CCV2_ENC_RESERVE")) c->enc_reserve = atoi(s) != 0;
+  if (const char *s = getenv("CCV2_SIDE")) c->n_side = std::max(1, std::min(SIDE_STREAMS, atoi(s)));
   if (const char *s = getenv("CCV2_INFLIGHT")) c->inflight_max = std::max(1, atoi(s));
   if (const char *s = getenv("CCV2_FE_FRAMES")) c->fe_frames = std::max(1, atoi(s));
   auto fail = [&](cudaError_t ee, const char *what) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ee); ccv2_destroy(c); return CCV2_ERR_CUDA; };
@@ -976,7 +980,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
       LAUNCH("hist_kernel", hist_kernel<<<dim3((unsigned)((hmax + 16383) / 16384), detail ? 5 : 3, gf), 256, 0, st>>>(dg));
       CUQ(hop(sp, ss)); st = ss;
       if (detail) LAUNCH("rc_encode_int_kernel", rc_encode_int_kernel<<<gf, 32, 0, st>>>(dg));
-      if (c->lps_enc) LAUNCH("rc_encode_lps_kernel", rc_encode_lps_kernel<<<dim3((unsigned)((gf + 31) / 32), detail ? 5 : 3), 32, c->lps_smem_enc, st>>>(dg, gf, cen, color, detail));
+      if (c->lps_enc) LAUNCH("rc_encode_lps_kernel", rc_encode_lps_kernel<<<dim3((unsigned)((gf + 31) / 32), detail ? 5 : 3), 32, c->enc_reserve ? c->lps_smem_enc : 0, st>>>(dg, gf, cen, color, detail));
       else LAUNCH("rc_encode_kernel", rc_encode_kernel<<<gf, detail ? 160 : 96, serial_smem_enc, st>>>(dg, cen, color, detail));
       CUQ(hop(ss, sp)); st = sp;
       LAUNCH("assemble_kernel", assemble_kernel<<<dim3(64, gf), 256, 0, st>>>(dg, H));
@@ -1000,7 +1004,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
       CUQ(hop(sp, ss)); st = ss;
       if (use_lps_dec) {
         // tree layers on the group's stream, speculated colour layers on a side stream at the same time
-        cudaStream_t s2 = c->profiling ? st : c->side_streams[sl % SIDE_STREAMS];
+        cudaStream_t s2 = c->profiling ? st : c->side_streams[sl % c->n_side];
         const unsigned lps_ctas = (unsigned)((gf + LPS_DEC_FRAMES - 1) / LPS_DEC_FRAMES);
         LAUNCH("dec_head_kernel", dec_head_kernel<<<gf, 32, 0, st>>>(dg));
         if (s2 != st) { CUQ(cudaEventRecord(x.ev_side[2 * g], st)); CUQ(cudaStreamWaitEvent(s2, x.ev_side[2 * g], 0)); }

@@ -161,6 +161,26 @@ __device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t a) { uint32_t v; a
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_volatile_u32(uint32_t a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 
+// ---- TMA 1-D bulk copies (cp.async.bulk, sm_90+): a contiguous global span lands in shared memory as ONE asynchronous
+// transfer issued by one thread and signalled through an mbarrier, instead of one load instruction per thread and element.
+// src, dst and bytes must be multiples of 16.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+  uint32_t done = 0;
+  const uint32_t a = smem_addr(bar);
+  while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(a), "r"(phase) : "memory");
+}
+
 // spread the low 21 bits of v so that bit i lands at bit 3i
 __device__ __forceinline__ uint64_t spread3(uint32_t v) {
   uint64_t x = v & 0x1FFFFFull;

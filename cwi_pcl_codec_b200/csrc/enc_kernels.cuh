@@ -244,23 +244,37 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pass_kernel(EncFrame *frame
   uint64_t *skey = (uint64_t *)sort_dyn;
   uint32_t *sval = (uint32_t *)(sort_dyn + SORT_TILE * 8);
   __shared__ uint32_t s_tile;
+  __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t whist[SORT_THREADS / 32][256];
   __shared__ uint32_t tile_off[256], dbase[256];
   __shared__ uint64_t s_scan[33];
-  if (threadIdx.x == 0) s_tile = atomicAdd(&f.ticket[TK_SORT0 + pass], 1u);
+  const uint64_t *skeys = f.keys[pass & 1]; const uint32_t *svals = f.vals[pass & 1];
+  if (threadIdx.x == 0) {
+    // The tile -- 4096 keys (32 KB) and 4096 indices (16 KB), both contiguous -- comes in as two TMA bulk copies issued
+    // by this one thread as soon as the ticket is known; everybody else meets the data at the mbarrier.  Byte counts are
+    // rounded up to 16 (the buffers carry 8 elements of slack).
+    const uint32_t t = atomicAdd(&f.ticket[TK_SORT0 + pass], 1u);
+    s_tile = t;
+    const uint32_t cnt = min((uint32_t)SORT_TILE, n - t * SORT_TILE);
+    const uint32_t kb = ((cnt * 8u) + 15u) & ~15u, vb = ((cnt * 4u) + 15u) & ~15u;
+    mbar_init(&s_bar, 1);
+    mbar_expect_tx(&s_bar, kb + vb);
+    bulk_g2s(skey, skeys + (size_t)t * SORT_TILE, kb, &s_bar);
+    bulk_g2s(sval, svals + (size_t)t * SORT_TILE, vb, &s_bar);
+  }
   for (uint32_t k = threadIdx.x; k < (SORT_THREADS / 32) * 256; k += blockDim.x) (&whist[0][0])[k] = 0;
   // global digit base: exclusive scan of the pass histogram (256 threads, one digit each)
   uint64_t tot;
   uint32_t gbase = (uint32_t)block_excl_scan_u64(f.ghist[pass * 256 + threadIdx.x], &tot, s_scan);
   const uint32_t tile = s_tile;
   const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
-  const uint64_t *skeys = f.keys[pass & 1]; const uint32_t *svals = f.vals[pass & 1];
   uint64_t *dkeys = f.keys[(pass + 1) & 1]; uint32_t *dvals = f.vals[(pass + 1) & 1];
   const uint32_t shift = 8 * pass;
   const uint32_t wbase = tile * SORT_TILE + w * (32 * SORT_ITEMS);
   uint64_t key[SORT_ITEMS]; uint32_t val[SORT_ITEMS]; uint16_t rank[SORT_ITEMS];
+  mbar_wait(&s_bar, 0);
 #pragma unroll
-  for (int k = 0; k < SORT_ITEMS; k++) { uint32_t i = wbase + k * 32 + lane; key[k] = i < n ? skeys[i] : ~0ull; val[k] = i < n ? svals[i] : 0u; }
+  for (int k = 0; k < SORT_ITEMS; k++) { const uint32_t li = w * (32 * SORT_ITEMS) + k * 32 + lane; const bool in = wbase + k * 32 + lane < n; key[k] = in ? skey[li] : ~0ull; val[k] = in ? sval[li] : 0u; }
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; k++) {
     uint32_t i = wbase + k * 32 + lane;
