@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "Mpoints/s encode+decode @ depth-11 intra; bitstream bit-exact vs ref"
-INFLIGHT_CALLS = int(os.environ.get("BENCH_INFLIGHT_CALLS", "3"))     # steps submitted ahead (ccv2_submit_*): the library holds up to three calls in flight
+INFLIGHT_CALLS = int(os.environ.get("BENCH_INFLIGHT_CALLS", "3"))     # steps submitted ahead (ccv2_submit_*): the third queues behind the first on the 16 work streams, so a set is taken again the moment it is free
 
 
 def shard_frames(n_frames_per_rank, rank, world):

@@ -83,9 +83,10 @@ struct Carver {
   size_t end() const { return (off + 255) & ~size_t(255); }
 };
 
-constexpr int MAX_STREAMS = 20;         // work streams: long-lived set s always runs on stream s mod 20 -- a group waits for the previous user of its set anyway,
-                                         // so with at most 20 sets no group ever queues behind a stream that is busy with an unrelated one
-constexpr int SIDE_STREAMS = 20;         // one per work stream: a group's colour layer must not queue behind another group's (100 ms each)          // group + side + copy + control streams stay within 32 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, see ccv2.h)
+constexpr int MAX_STREAMS = 16;         // work streams: long-lived set s always runs on stream s mod 16 -- a group waits for the previous user of its set anyway,
+                                         // so with at most 16 sets no group ever queues behind a stream that is busy with an unrelated one
+constexpr int SIDE_STREAMS = 8;          // 16 work + 8 side + copy, D2H, control, collect, end = 29 streams <= the 32 hardware queues: with more, streams alias
+                                         // onto queues and a group's front-end kernels sit behind another group's 0.4 s serial kernel (measured: 48 streams 2270, 34 streams 2340 Mpoints/s)          // group + side + copy + control streams stay within 32 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, see ccv2.h)
 constexpr int MAX_GROUP = 128;           // frames per group.  The serial range-coder kernels are latency bound (0.1-0.4 s per launch whatever the frame count),
                                          // so throughput = frames per launch x launches in flight: large groups, one stream each (measured: 32-frame groups 650, 64 1040-1270 Mpoints/s)
 constexpr int N_CALLS = 4;               // call contexts: three user calls in flight + one for the retry of a frame that overflowed its workspace
@@ -107,7 +108,6 @@ struct CallCtx {
   DevBuf enc_frames, dec_frames, stage;                     // frame records (+ histograms); per-call staging for pageable destinations
   HostBuf h_frames, h_dframes;
   cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_setup = nullptr;
-  cudaStream_t end_stream = nullptr;                        // gathers the call's group events; the control stream must stay free for the next call's set-up
   std::vector<cudaEvent_t> ev_h2d, ev_side, ev_done, ev_fin, ev_enc, ev_hop;
   // per-frame bookkeeping of the call (the caller's arrays must stay alive until the call is collected)
   std::vector<char> in_kind, out_kind, pts_kind;            // PtrKind of pts[i] / in[i], out[i], pts_out[i]
@@ -132,9 +132,10 @@ struct ccv2_codec {
   int n_streams = 0, group = 0;           // CCV2_STREAMS / CCV2_GROUP overrides (0 = automatic)
   int n_side = SIDE_STREAMS;              // side streams in use (CCV2_SIDE)
   int enc_reserve = 1;                    // lane-per-stream encoder CTAs reserve half an SM's shared memory (one CTA per SM); CCV2_ENC_RESERVE=0 turns it off
-  int inflight_max = 3072;                // frames the long-lived ring may hold (CCV2_INFLIGHT); memory permitting
+  int inflight_max = 2048;                // frames the long-lived ring may hold (CCV2_INFLIGHT); memory permitting
   int fe_frames = 0;                      // frames the front-end ring holds (CCV2_FE_FRAMES; 0 = 256, or 512 when host inputs are staged in it); at least two sets
   cudaStream_t main_stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr, fin_stream = nullptr;
+  cudaStream_t end_stream = nullptr;      // gathers every call's group events (calls complete in order); on the control stream that wait would hold back the next call's set-up
   cudaStream_t streams[MAX_STREAMS] = {};
   cudaStream_t ser_streams[MAX_STREAMS] = {};     // green contexts on: the same slots on the serial partition's SMs; off: aliases of streams[]
   int green_sms = 0;                      // SMs set aside for the latency-bound range-coder kernels (CCV2_GREEN; 0 = no partition)
@@ -144,7 +145,7 @@ struct ccv2_codec {
   cudaStream_t side_streams[SIDE_STREAMS] = {};   // colour layer of a group, concurrent with its tree layer (lane-per-stream decoder)
   int lps_dec = -1;                       // lane-per-stream range decoder: -1 auto (round trips only), 0 off, 1 on (CCV2_LPS_DEC)
   cudaEvent_t ev_id_chain = nullptr; bool id_chain_used = false;     // frame ids are sequential: a group's setup waits for the previous group's
-  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;                      // ccv2_timer_*
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr; bool timer_on = false; // ccv2_timer_* (CCV2_TRACE prints times since the timer's start when it runs)
   JpegTables *d_tables = nullptr;
   uint32_t *d_frame_counter = nullptr;
   size_t lps_smem_enc = 0;                // dynamic shared memory that keeps the lane-per-stream coder CTAs one to an SM
@@ -460,7 +461,7 @@ bool peek_header(const uint8_t *b, size_t len, PeekInfo &o) {
 
 // ================================================================================================ handle life cycle
 static void drain(ccv2_codec *c) {                           // waits for everything the codec has enqueued
-  for (auto &x : c->calls) if (x.end_stream) cudaStreamSynchronize(x.end_stream);
+  cudaStreamSynchronize(c->end_stream);
   cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->d2h_stream);
   for (int i = 0; i < MAX_STREAMS; i++) { cudaStreamSynchronize(c->streams[i]); if (c->ser_streams[i] != c->streams[i]) cudaStreamSynchronize(c->ser_streams[i]); }
   for (int i = 0; i < SIDE_STREAMS; i++) cudaStreamSynchronize(c->side_streams[i]);
@@ -532,7 +533,7 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   auto fail = [&](cudaError_t ee, const char *what) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ee); ccv2_destroy(c); return CCV2_ERR_CUDA; };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
   if ((e = cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return fail(e, "cudaDeviceGetAttribute");
-  for (cudaStream_t *s : { &c->main_stream, &c->copy_stream, &c->d2h_stream, &c->fin_stream })
+  for (cudaStream_t *s : { &c->main_stream, &c->copy_stream, &c->d2h_stream, &c->fin_stream, &c->end_stream })
     if ((e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
   // SM partition (CUDA green contexts): the serial range-coder kernels are latency bound -- one warp per 8-32 frames, a few
   // hundred warps in all -- and lose up to half their speed when bandwidth-bound front-end kernels of other groups share
@@ -571,7 +572,6 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
     if (i < SIDE_STREAMS && (e = cudaStreamCreateWithFlags(&c->side_streams[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
   }
   for (auto &x : c->calls) {
-    if ((e = cudaStreamCreateWithFlags(&x.end_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaEventCreate(&x.ev_start)) != cudaSuccess) return fail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&x.ev_end)) != cudaSuccess) return fail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&x.ev_setup, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
@@ -618,7 +618,6 @@ void ccv2_destroy(ccv2_codec *c) {
   for (auto &x : c->calls) {
     for (auto *v : { &x.ev_h2d, &x.ev_side, &x.ev_done, &x.ev_fin, &x.ev_enc, &x.ev_hop, &x.ev_trace }) for (auto ev : *v) cudaEventDestroy(ev);
     for (cudaEvent_t ev : { x.ev_start, x.ev_end, x.ev_setup }) if (ev) cudaEventDestroy(ev);
-    if (x.end_stream) cudaStreamDestroy(x.end_stream);
     x.enc_frames.release(); x.dec_frames.release(); x.stage.release(); x.h_frames.release(); x.h_dframes.release();
   }
   for (Ring *r : { &c->fe, &c->ll }) { for (auto ev : r->ev_free) cudaEventDestroy(ev); r->buf.release(); }
@@ -626,7 +625,7 @@ void ccv2_destroy(ccv2_codec *c) {
   for (cudaEvent_t ev : { c->ev_id_chain, c->ev_t0, c->ev_t1 }) if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < MAX_STREAMS; i++) { if (c->ser_streams[i] && c->ser_streams[i] != c->streams[i]) cudaStreamDestroy(c->ser_streams[i]); if (c->streams[i]) cudaStreamDestroy(c->streams[i]); }
   for (int i = 0; i < SIDE_STREAMS; i++) if (c->side_streams[i]) cudaStreamDestroy(c->side_streams[i]);
-  for (cudaStream_t s : { c->main_stream, c->copy_stream, c->d2h_stream, c->fin_stream }) if (s) cudaStreamDestroy(s);
+  for (cudaStream_t s : { c->main_stream, c->copy_stream, c->d2h_stream, c->fin_stream, c->end_stream }) if (s) cudaStreamDestroy(s);
   if (c->green_ser && c->drv_green_destroy) c->drv_green_destroy(c->green_ser);
   if (c->green_par && c->drv_green_destroy) c->drv_green_destroy(c->green_par);
   if (c->d_tables) cudaFree(c->d_tables);
@@ -903,7 +902,8 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
   // the lane-per-stream decoder wins whenever many frames are in flight on the device (2416 against 1902 Mpoints/s round trip,
   // 4329 against 3239 decode-only); with host buffers the copies pace the pipeline and the CTA-per-frame decoder's shorter
   // latency is worth more (1174 against 1103 end to end)
-  const bool use_lps_dec = c->lps_dec < 0 ? !host_io : c->lps_dec != 0;
+  // ... and a call of a few frames is a latency matter: the CTA-per-frame decoder (179 ms for a 1M-point frame against 240)
+  const bool use_lps_dec = c->lps_dec < 0 ? (!host_io && nframes >= 256) : c->lps_dec != 0;
   uint64_t launches = 0;
   uint32_t *counter = c->d_frame_counter;
   bool copy_waits_setup = false;
@@ -1056,9 +1056,9 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
     ll.used[sl] = 1;
     CUQ(cudaGetLastError());
   }
-  // the call's end is gathered on its own stream: on the control stream it would hold back the set-up of the next call
-  for (int g = 0; g < ngroups; g++) CUQ(cudaStreamWaitEvent(x.end_stream, x.ev_fin[g], 0));
-  CUQ(cudaEventRecord(x.ev_end, x.end_stream));
+  // the call's end is gathered on the end stream: on the control stream it would hold back the set-up of the next call
+  for (int g = 0; g < ngroups; g++) CUQ(cudaStreamWaitEvent(c->end_stream, x.ev_fin[g], 0));
+  CUQ(cudaEventRecord(x.ev_end, c->end_stream));
 #undef CUQ
   x.launches = launches;
   return CCV2_OK;
@@ -1139,7 +1139,7 @@ static int finish_call(ccv2_codec *c, CallCtx &x) {
     for (int g = 0; g < x.ngroups; g++) {
       fprintf(stderr, "  group %2d:", g);
       for (size_t k = 0; k < x.trace_marks.size(); k++) if (x.trace_marks[k].group == g) {
-        float t = -1; cudaEventElapsedTime(&t, x.ev_start, x.ev_trace[k]);
+        float t = -1; if (cudaEventElapsedTime(&t, c->timer_on ? c->ev_t0 : x.ev_start, x.ev_trace[k]) != cudaSuccess) { cudaGetLastError(); cudaEventElapsedTime(&t, x.ev_start, x.ev_trace[k]); }
         fprintf(stderr, " %s %.1f |", x.trace_marks[k].label, t);
       }
       fprintf(stderr, "\n");
@@ -1257,6 +1257,7 @@ int ccv2_timer_start(ccv2_codec *c) {
   CU(cudaSetDevice(c->device));
   finish_all(c); drain(c);
   CU(cudaEventRecord(c->ev_t0, c->main_stream));
+  c->timer_on = true;
   return CCV2_OK;
 }
 int ccv2_timer_stop(ccv2_codec *c, float *ms) {
@@ -1266,6 +1267,7 @@ int ccv2_timer_stop(ccv2_codec *c, float *ms) {
   CU(cudaEventRecord(c->ev_t1, c->main_stream));
   CU(cudaEventSynchronize(c->ev_t1));
   CU(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+  c->timer_on = false;
   return rc;
 }
 
