@@ -131,6 +131,7 @@ struct ccv2_codec {
   int use_ring = 1;                       // pipeline the DFS walk behind the range decoder (CCV2_NO_RING=1 disables: debugging)
   int n_streams = 0, group = 0;           // CCV2_STREAMS / CCV2_GROUP overrides (0 = automatic)
   int n_side = SIDE_STREAMS;              // side streams in use (CCV2_SIDE)
+  int allow_packed = 1;                   // packed sort elements (CCV2_PACKED=0: always (code, index) pairs)
   int enc_reserve = 1;                    // lane-per-stream encoder CTAs reserve half an SM's shared memory (one CTA per SM); CCV2_ENC_RESERVE=0 turns it off
   int inflight_max = 2048;                // frames the long-lived ring may hold (CCV2_INFLIGHT); memory permitting
   int fe_frames = 0;                      // frames the front-end ring holds (CCV2_FE_FRAMES; 0 = 256, or 512 when host inputs are staged in it); at least two sets
@@ -526,6 +527,7 @@ int ccv2_create(const ccv2_params *p, int device, ccv2_codec **out) {
   if (const char *s = getenv("CCV2_NO_RING")) c->use_ring = atoi(s) ? 0 : 1;
   if (const char *s = getenv("CCV2_STREAMS")) c->n_streams = std::max(0, std::min(MAX_STREAMS, atoi(s)));
   if (const char *s = getenv("CCV2_GROUP")) c->group = std::max(0, std::min(256, atoi(s)));
+  if (const char *s = getenv("CCV2_PACKED")) c->allow_packed = atoi(s) != 0;
   if (const char *s = getenv("CCV2_ENC_RESERVE")) c->enc_reserve = atoi(s) != 0;
   if (const char *s = getenv("CCV2_SIDE")) c->n_side = std::max(1, std::min(SIDE_STREAMS, atoi(s)));
   if (const char *s = getenv("CCV2_INFLIGHT")) c->inflight_max = std::max(1, atoi(s));
@@ -781,7 +783,9 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
   const size_t out_stage_off = in_stage_off + in_stage_max;
   ll_bytes = out_stage_off + out_stage_max;
   {
-    const int want_ll = std::max(1, std::min((N_CALLS - 1) * ngroups, (c->inflight_max + G - 1) / G));
+    // at most one long-lived set per work stream: sets that share a stream queue behind each other although they are unrelated
+    // (measured end to end with 19 sets on 16 streams: a group's kernels 220 ms late, the copy engine idle meanwhile)
+    const int want_ll = std::max(1, std::min(std::min((N_CALLS - 1) * ngroups, NS), (c->inflight_max + G - 1) / G));
     // host inputs are uploaded into the front-end set: with only two sets the copy engine waits whenever a front-end runs long
     // under load (measured: 140 ms instead of 20, the next upload 90 ms late), so staged inputs get four
     const int fe_frames = c->fe_frames ? c->fe_frames : (host_in_any ? 512 : 256);
@@ -838,6 +842,7 @@ static int submit_call(ccv2_codec *c, int mode, int nframes,
     P.color_reduction = (prm.color_coding_type == 0) ? std::max(0, 8 - (int)prm.color_bit_resolution) : 0;   // jp_color_coder_ is never configured
     P.prefix_len = 16384;
     P.detail = detail; P.point_res_f = (float)prm.point_resolution;
+    P.allow_packed = (!cen && !detail && c->allow_packed) ? 1 : 0;
     H.octree_res = prm.octree_resolution; H.point_res = (double)(float)prm.point_resolution;
     H.do_voxel_grid = detail ? 0 : 1; H.with_color = color; H.color_bits = prm.color_bit_resolution; H.do_centroid = cen;
     H.connectivity = prm.code_connectivity != 0; H.scalable = prm.create_scalable_stream != 0; H.icp_offset = prm.do_icp_color_offset != 0; H._p = 0;
@@ -1406,7 +1411,8 @@ int ccv2_debug_fetch(ccv2_codec *c, int frame, int what, void *host_buf, size_t 
     case 1: src = f.tree; n = f.B; break;
     case 2: src = f.avg; n = (size_t)f.V * 3; break;
     case 3: src = f.cpay; n = f.ncolor; break;
-    case 4: src = f.vals[f.npasses & 1]; n = (size_t)f.n_finite * 4; break;
+    case 4: if (f.packed) { c->err = "this frame was sorted as packed (code, colour) words: there are no point indices (CCV2_PACKED=0 keeps them)"; return CCV2_ERR_UNSUPPORTED; }
+            src = f.vals[f.npasses & 1]; n = (size_t)f.n_finite * 4; break;
     case 5:
       memset(&info, 0, sizeof info);
       info.depth = f.depth; info.n_finite = f.n_finite; info.n_leaves = f.V; info.n_tree_bytes = f.B; info.n_color_bytes = f.ncolor; info.error = f.error;

@@ -38,6 +38,7 @@ struct EncParams {             // by value to kernels
   int res_pow2;
   int do_color, color_type, color_reduction, do_centroid;
   int prefix_len;              // points handled exactly by the single-CTA bbox kernel
+  int allow_packed;            // voxel-grid mode without centroids: a frame of depth <= 13 sorts ONE 64-bit word per point (40-bit code << 24 | b,g,r)
   int detail;                  // doVoxelGridDownDownSampling = false: per-point residuals and colour differences (impl.hpp:1525-1541)
   float point_res_f;           // [PCL] PointCoding::pointCompressionResolution_ (setPrecision(float))
 };
@@ -57,7 +58,7 @@ struct EncFrame {
   // bbox / keys
   double bmin[3], bmax[3];
   uint32_t depth, defined, n_finite, violator, rekey, npasses;
-  uint32_t n_events, _pade; BoxEvent ev[CCV2_MAX_EVENTS];
+  uint32_t n_events, packed; BoxEvent ev[CCV2_MAX_EVENTS];   // packed: sort elements are (code << 24 | bgr), no index array (see keygen_kernel)
   // leaves
   uint32_t V, B;
   // jpeg geometry / sizes

@@ -140,6 +140,11 @@ __global__ void __launch_bounds__(256) keygen_kernel(EncFrame *frames, EncParams
   // the sequential walk covered [0, prefix) in the first launch and everything in the slow path; only points beyond it
   // have to be checked against the box (a point inside the walked range fits the box of its own time by construction)
   const uint32_t walked = rekey_only ? n : min(n, (uint32_t)P.prefix_len);
+  // Packed sort element: the colour sum of a voxel does not depend on the order of its points, so without centroids (and
+  // outside detail mode) nothing needs the point index after the sort.  A Morton code of depth <= 13 has 39 bits (+1 for
+  // the non-finite sentinel): code << 24 | b,g,r is ONE 64-bit word per point -- 16 instead of 24 bytes per point and pass
+  // through the sort, and leaf_emit reads its colours sequentially instead of gathering them from the cloud.
+  const bool packed = P.allow_packed && depth <= 13;
   bool fin = false, viol = false;
   uint64_t key = 1ull << (3 * depth);                    // sorts after every valid code
   if (i < n) {
@@ -170,9 +175,10 @@ __global__ void __launch_bounds__(256) keygen_kernel(EncFrame *frames, EncParams
       }
       key = morton_xyz(k[0], k[1], k[2]);
     }
-    f.keys[0][i] = key;
-    f.vals[0][i] = i;
+    if (packed) f.keys[0][i] = (key << 24) | (__ldg((const uint32_t *)(f.pts + 32ull * i + 16)) & 0xFFFFFFu);   // same 32-byte sector as x,y,z
+    else { f.keys[0][i] = key; f.vals[0][i] = i; }
   }
+  if (i == 0) f.packed = packed;
   // n_finite starts at n (set by the host / the slow bbox path) and only non-finite points touch it: no atomics at
   // all for the usual all-finite cloud (one same-address atomic per warp cost ~20 us per 1M-point frame)
   const uint32_t bad = __popc(__ballot_sync(FULL_MASK, i < n && !fin));
@@ -219,10 +225,11 @@ __global__ void __launch_bounds__(256) sort_hist_kernel(EncFrame *frames) {
   for (uint32_t k = threadIdx.x; k < 8 * 256; k += blockDim.x) (&sh[0][0])[k] = 0;
   __syncthreads();
   const uint64_t *keys = f.keys[0];
+  const uint32_t kshift = f.packed ? 24 : 0;
   for (uint32_t k = 0; k < SORT_ITEMS; k++) {
     uint32_t i = base + k * SORT_THREADS + threadIdx.x;
     if (i < n) {
-      uint64_t key = keys[i];
+      uint64_t key = keys[i] >> kshift;
       for (uint32_t p = 0; p < np; p++) atomicAdd(&sh[p][(key >> (8 * p)) & 255], 1u);
     }
   }
@@ -249,6 +256,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pass_kernel(EncFrame *frame
   __shared__ uint32_t tile_off[256], dbase[256];
   __shared__ uint64_t s_scan[33];
   const uint64_t *skeys = f.keys[pass & 1]; const uint32_t *svals = f.vals[pass & 1];
+  const bool packed = f.packed != 0;
   if (threadIdx.x == 0) {
     // The tile -- 4096 keys (32 KB) and 4096 indices (16 KB), both contiguous -- comes in as two TMA bulk copies issued
     // by this one thread as soon as the ticket is known; everybody else meets the data at the mbarrier.  Byte counts are
@@ -258,9 +266,9 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pass_kernel(EncFrame *frame
     const uint32_t cnt = min((uint32_t)SORT_TILE, n - t * SORT_TILE);
     const uint32_t kb = ((cnt * 8u) + 15u) & ~15u, vb = ((cnt * 4u) + 15u) & ~15u;
     mbar_init(&s_bar, 1);
-    mbar_expect_tx(&s_bar, kb + vb);
+    mbar_expect_tx(&s_bar, kb + (packed ? 0u : vb));
     bulk_g2s(skey, skeys + (size_t)t * SORT_TILE, kb, &s_bar);
-    bulk_g2s(sval, svals + (size_t)t * SORT_TILE, vb, &s_bar);
+    if (!packed) bulk_g2s(sval, svals + (size_t)t * SORT_TILE, vb, &s_bar);
   }
   for (uint32_t k = threadIdx.x; k < (SORT_THREADS / 32) * 256; k += blockDim.x) (&whist[0][0])[k] = 0;
   // global digit base: exclusive scan of the pass histogram (256 threads, one digit each)
@@ -269,12 +277,12 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pass_kernel(EncFrame *frame
   const uint32_t tile = s_tile;
   const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
   uint64_t *dkeys = f.keys[(pass + 1) & 1]; uint32_t *dvals = f.vals[(pass + 1) & 1];
-  const uint32_t shift = 8 * pass;
+  const uint32_t shift = 8 * pass + (packed ? 24 : 0);
   const uint32_t wbase = tile * SORT_TILE + w * (32 * SORT_ITEMS);
   uint64_t key[SORT_ITEMS]; uint32_t val[SORT_ITEMS]; uint16_t rank[SORT_ITEMS];
   mbar_wait(&s_bar, 0);
 #pragma unroll
-  for (int k = 0; k < SORT_ITEMS; k++) { const uint32_t li = w * (32 * SORT_ITEMS) + k * 32 + lane; const bool in = wbase + k * 32 + lane < n; key[k] = in ? skey[li] : ~0ull; val[k] = in ? sval[li] : 0u; }
+  for (int k = 0; k < SORT_ITEMS; k++) { const uint32_t li = w * (32 * SORT_ITEMS) + k * 32 + lane; const bool in = wbase + k * 32 + lane < n; key[k] = in ? skey[li] : ~0ull; val[k] = (in && !packed) ? sval[li] : 0u; }
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; k++) {
     uint32_t i = wbase + k * 32 + lane;
@@ -320,7 +328,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pass_kernel(EncFrame *frame
     if (i < n) {
       uint32_t d = (uint32_t)((key[k] >> shift) & 255);
       uint32_t lp = dbase[d] + whist[w][d] + rank[k];
-      skey[lp] = key[k]; sval[lp] = val[k];
+      skey[lp] = key[k]; if (!packed) sval[lp] = val[k];
     }
   }
   __syncthreads();
@@ -329,7 +337,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pass_kernel(EncFrame *frame
     const uint64_t kk = skey[idx];
     const uint32_t d = (uint32_t)((kk >> shift) & 255);
     const uint32_t pos = tile_off[d] + (idx - dbase[d]);
-    dkeys[pos] = kk; dvals[pos] = sval[idx];
+    dkeys[pos] = kk; if (!packed) dvals[pos] = sval[idx];
   }
 }
 
@@ -352,16 +360,17 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf_scan_kernel(EncFrame *frame
   __syncthreads();
   const uint32_t tile = s_tile, d = f.depth;
   const uint64_t *keys = f.keys[f.npasses & 1];
+  const uint32_t kshift = f.packed ? 24 : 0;               // packed elements carry the colour in their low 24 bits
   const uint32_t i0 = tile * LEAF_TILE + threadIdx.x * LEAF_ITEMS;
   uint64_t k[LEAF_ITEMS], prev = 0;
-  if (i0 > 0 && i0 < nf) prev = keys[i0 - 1];
+  if (i0 > 0 && i0 < nf) prev = keys[i0 - 1] >> kshift;
   uint64_t v[LEAF_ITEMS], sum = 0; uint8_t fn[LEAF_ITEMS];
 #pragma unroll
   for (int j = 0; j < LEAF_ITEMS; j++) {
     uint32_t i = i0 + j;
     v[j] = 0; fn[j] = 0;
     if (i < nf) {
-      k[j] = keys[i];
+      k[j] = keys[i] >> kshift;
       if (i == 0) { v[j] = (1ull << 36) | d; fn[j] = 0; }
       else if (k[j] != prev) {
         uint32_t msb = 63 - __clzll((long long)(k[j] ^ prev));
@@ -458,6 +467,10 @@ __global__ void __launch_bounds__(256) leaf_emit_kernel(EncFrame *frames, EncPar
   const uint32_t *vals = f.vals[f.npasses & 1];
   if (P.do_color) {
     uint32_t c0 = 0, c1 = 0, c2 = 0;
+    if (f.packed) {                                        // colours rode through the sort: sequential reads
+      const uint64_t *sk = f.keys[f.npasses & 1];
+      for (uint32_t k = s0; k < s1; k++) { const uint32_t c = (uint32_t)__ldg(&sk[k]); c0 += c & 0xFF; c1 += (c >> 8) & 0xFF; c2 += (c >> 16) & 0xFF; }
+    } else
     for (uint32_t k = s0; k < s1; k++) {
       uint32_t c = __ldg((const uint32_t *)(f.pts + 32ull * vals[k] + 16));
       c0 += c & 0xFF; c1 += (c >> 8) & 0xFF; c2 += (c >> 16) & 0xFF;

@@ -296,10 +296,12 @@ def test_reference_facade(K, oracle):
     assert cdc.getPerformanceMetrics()[0] > 0
 
 
-@pytest.mark.parametrize("env", [{"CCV2_LPS_DEC": "1"}, {"CCV2_LPS_ENC": "0", "CCV2_LPS_DEC": "0"}])
+@pytest.mark.parametrize("env", [{"CCV2_LPS_DEC": "1"}, {"CCV2_LPS_ENC": "0", "CCV2_LPS_DEC": "0"}, {"CCV2_PACKED": "0"}, {"CCV2_GROUP": "3", "CCV2_STREAMS": "2", "CCV2_INFLIGHT": "6"}])
 def test_both_entropy_stage_implementations_are_bit_exact(K, oracle, env, monkeypatch):
     """The lane-per-stream coders and the CTA-per-frame ones are interchangeable (the library picks by call type; the
-    knobs are read when a handle is created): same streams, same clouds, whichever is forced."""
+    knobs are read when a handle is created): same streams, same clouds, whichever is forced.  Likewise the packed
+    (code, colour) sort elements against (code, index) pairs, and a tiny ring (2 long-lived sets of 3 frames on 2 streams:
+    every set is handed on several times inside one call)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     clouds = [synth.gen_surface(40000, 70 + i) for i in range(11)] + [np.zeros(0, synth.POINT_DTYPE), synth.gen_uniform(3000, 90)]
@@ -367,10 +369,36 @@ def test_roundtrip_call_matches_separate_calls(K, oracle):
     c.close()
 
 
-def test_config4_shape_4m_points_depth12(K, oracle):
-    """BASELINE configs[3] shape on one GPU: dense 4M-point frame, octree_bits 12 (realised depth 15), JPEG Q95."""
+@pytest.mark.parametrize("quality", [60, 75, 95])
+def test_config4_shape_4m_points_depth12(K, oracle, quality):
+    """BASELINE configs[3] shape on one GPU: dense 4M-point frame, octree_bits 12, points of the JPEG quality sweep 60..95."""
     pts = synth.gen_surface(4000000, 0)
-    check_batch(K, oracle, [pts], K.default_params(octree_bits=12, jpeg_quality=95))
+    check_batch(K, oracle, [pts], K.default_params(octree_bits=12, jpeg_quality=quality))
+
+
+def test_lines_mode_stream_as_the_reference_writes_it_for_a_small_cloud(K, oracle):
+    """color_coding_type 2 with fewer than 2048 voxels: the reference leaves the line 2048 pixels wide and reads past its
+    buffer (cjpeg.h:255-274), so ITS stream carries one 2048 x 1 image whose first V pixels are the voxel colours; oracle
+    and CUDA encoder write a V x 1 image instead (documented divergence).  A decoder must still read the reference's
+    form: build it (same tree layer, colour layer = one 2048-wide line with arbitrary pixels after the first V)."""
+    cl = synth.gen_surface(1500, 22)
+    op = oracle.default_params(octree_bits=10, color_coding_type=2, jpeg_quality=85)
+    ref, info, dbg = oracle.encode(cl, op, frame_id=1, debug=True)
+    V = info.n_leaves
+    assert V < 2048
+    rng = np.random.default_rng(3)
+    line = np.concatenate([dbg["avg_colors"].reshape(-1, 3), rng.integers(0, 256, (2048 - V, 3), dtype=np.uint8)])[None, :, :]
+    jpg = oracle.jpeg_encode(line, 85).tobytes()
+    payload = (1).to_bytes(4, "little") + len(jpg).to_bytes(4, "little") + jpg
+    s = ref[:148 + info.coded[0]] + len(payload).to_bytes(8, "little") + oracle.range_encode(np.frombuffer(payload, np.uint8)).tobytes()
+    rd, _ = oracle.decode(s)
+    assert rd.shape[0] == V
+    c = K.Codec(K.default_params(octree_bits=10, color_coding_type=2))
+    d = c.decode_batch([s])[0]
+    assert np.array_equal(d, rd)
+    # and the V x 1 form both encoders write
+    assert np.array_equal(c.decode_batch([ref])[0], oracle.decode(ref)[0])
+    c.close()
 
 
 def test_many_frames_in_one_call_all_groups_and_streams(K, oracle):
