@@ -68,3 +68,45 @@ def gen_uniform(n, seed=0):
     xyz = (1.0 / 7.0 + rng.random((n, 3)) * (5.0 / 7.0)).astype(np.float32)
     rgb = rng.integers(0, 256, size=(n, 3), dtype=np.uint8)
     return pack_points(xyz, rgb)
+
+
+def gen_gof(n, seed=0, frames=30):
+    """GOF(seed, F): a group of frames of the G-surf body under a slow rigid motion (BASELINE configs[2]):
+    frame f is the frame-0 surface rotated by f * 0.4 degrees about the vertical axis through the body and shifted by
+    f * 0.002 along x (a quarter of a 16-voxel macroblock per frame at 11 bits), with 1 % of its points re-sampled and every
+    point's colour noise re-drawn (seed + f), in a fresh shuffled order.  All frames share ONE normalisation (the reference
+    normalises a group with a common box, impl.hpp:1871-1986), so the motion survives it."""
+    rng0 = np.random.default_rng(seed)
+    a, b, c = _ELLIPSOIDS[:, 3], _ELLIPSOIDS[:, 4], _ELLIPSOIDS[:, 5]
+    wts = a * b + a * c + b * c
+    counts = rng0.multinomial(n, wts / wts.sum())
+    parts = []
+    for e, m in zip(_ELLIPSOIDS, counts):
+        d = rng0.normal(size=(m, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        parts.append(e[:3] + d * e[3:])
+    body = np.concatenate(parts)
+    x, y, z = body[:, 0], body[:, 1], body[:, 2]
+    base_col = np.stack([128 + 100 * np.sin(12 * x + 3 * z), 128 + 90 * np.cos(9 * y + 5 * z), 128 + 110 * np.sin(7 * z)], axis=1)
+    clouds = []
+    for f in range(frames):
+        rng = np.random.default_rng(seed + 1000003 * (f + 1))
+        th = np.deg2rad(0.4 * f)
+        R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+        pts = body.copy()
+        col = base_col.copy()
+        k = max(1, n // 100)
+        sel = rng.choice(n, k, replace=False)
+        src = rng.choice(n, k)
+        pts[sel] = body[src] + rng.normal(scale=1e-3, size=(k, 3))
+        col[sel] = base_col[src]
+        pts = (pts - [0.5, 0.5, 0.5]) @ R.T + [0.5, 0.5, 0.5] + [0.002 * f, 0, 0]
+        colf = np.clip(np.rint(col) + rng.integers(-4, 5, size=(n, 3)), 0, 255).astype(np.uint8)
+        perm = rng.permutation(n)
+        clouds.append((pts[perm].astype(np.float32), colf[perm]))
+    mn = np.min([c[0].min(axis=0) for c in clouds], axis=0)
+    mx = np.max([c[0].max(axis=0) for c in clouds], axis=0)
+    ext = (mx - mn).astype(np.float32)
+    mn = (mn - np.float32(0.2) * ext).astype(np.float32)
+    rngv = ((mx + np.float32(0.2) * ext).astype(np.float32) - mn).astype(np.float32)
+    return [pack_points(((xyz - mn) / rngv).astype(np.float32), col) for xyz, col in clouds]

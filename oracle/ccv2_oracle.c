@@ -610,8 +610,11 @@ static void get_key_bit_size_first(obox *b) {          /* getKeyBitSize() with l
   double side = (double)(1u << b->depth) * b->res;
   for (int a = 0; a < 3; a++) { double over = (side - (b->max[a] - b->min[a])) / 2.0; if (over > EPSF) { b->min[a] -= over; b->max[a] += over; } }
 }
-int orc_bbox_keys(const void *pts, size_t n, double res, double bb_min[3], double bb_max[3], uint32_t *depth, uint32_t *keys, uint8_t *finite) {
+/* init != NULL: the tree starts with a box the caller defined ([PCL] defineBoundingBox -> getKeyBitSize, as simplifyPCloud and
+ * generate_macroblock_tree do, impl.hpp:336,427); points outside still grow it. */
+static int bbox_keys_impl(const void *pts, size_t n, double res, const obox *init, double bb_min[3], double bb_max[3], uint32_t *depth, uint32_t *keys, uint8_t *finite) {
   obox b; memset(&b, 0, sizeof b); b.res = res;
+  if (init) { b = *init; b.res = res; }
   const uint8_t *base = (const uint8_t *)pts;
   size_t n_seen = 0;
   for (size_t i = 0; i < n; i++) {
@@ -647,6 +650,9 @@ int orc_bbox_keys(const void *pts, size_t n, double res, double bb_min[3], doubl
   for (int a = 0; a < 3; a++) { bb_min[a] = b.min[a]; bb_max[a] = b.max[a]; }
   *depth = b.depth;
   return n_seen ? 0 : 1;
+}
+int orc_bbox_keys(const void *pts, size_t n, double res, double bb_min[3], double bb_max[3], uint32_t *depth, uint32_t *keys, uint8_t *finite) {
+  return bbox_keys_impl(pts, n, res, NULL, bb_min, bb_max, depth, keys, finite);
 }
 
 static inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z, uint32_t depth) {
@@ -1176,3 +1182,5 @@ int orc_quality_metrics(const void *cloud_a, size_t na, const void *cloud_b, siz
   for (int k = 0; k < 3; k++) out->psnr_yuv[k] = 10 * log10(1.0 / (mse[k] / (double)na));
   return 0;
 }
+
+#include "ccv2_oracle_inter.c"

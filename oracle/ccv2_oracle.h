@@ -115,6 +115,27 @@ typedef struct orc_quality {
 } orc_quality;
 int orc_quality_metrics(const void *cloud_a, size_t na, const void *cloud_b, size_t nb, orc_quality *out);
 
+
+/* ---- inter-frame (predictive) path: oracle/ccv2_oracle_inter.c -- PARITY UNPINNED (see that file's header) ---- */
+typedef struct orc_delta_info {
+  uint64_t macro_blocks, shared_blocks, converged_blocks;   /* macro_block_count, shared_macroblock_count, convergence_count (impl.hpp:803-805) */
+  uint64_t n_intra_points, n_p_points;                      /* points coded intra; points of the (simplified) P cloud */
+  float shared_percentage, convergence_percentage;          /* getMacroBlockPercentage / getMacroBlockConvergencePercentage (impl.hpp:1105-1106) */
+} orc_delta_info;
+/* simplifyPCloud (impl.hpp:318-400): one point per occupied voxel of the unit-box octree, DFS order */
+int orc_simplify(const orc_params *p, const void *pts, size_t n, void **out, size_t *nout);
+/* encodePointCloudDeltaFrame (impl.hpp:787-1112).  out_cloud may be NULL (write_out_cloud = false, as eval.hpp:506 passes). */
+int orc_encode_delta(const orc_params *p, const void *icloud, size_t ni, const void *pcloud, size_t np, int icp_on_original,
+                     uint8_t **i_out, size_t *i_len, uint8_t **p_out, size_t *p_len, void **out_cloud, size_t *n_out_cloud, orc_delta_info *info);
+/* decodePointCloudDeltaFrame (impl.hpp:1120-1235) */
+int orc_decode_delta(const orc_params *p, const void *icloud, size_t ni, const uint8_t *i_in, size_t i_len, const uint8_t *p_in, size_t p_len,
+                     void **out, size_t *nout, uint64_t *decoded_blocks);
+/* RigidTransformCoding::compressRigidTransform / deCompressRigidTransform (rigid_transform_coding_impl.hpp:63-203); m: row-major 4x4 */
+int orc_compress_rigid_transform(const float *m, int16_t *out /* 10 */, int *nwords /* 6 or 10 */);
+int orc_decompress_rigid_transform(const int16_t *in, int nwords, float *m);
+/* pcl::IterativeClosestPoint as do_icp_prediction drives it (impl.hpp:544-560); packed xyz floats; F: row-major 4x4 */
+int orc_icp(const float *src, size_t ns, const float *tgt, size_t nt, int max_iter, double tf_eps, double fit_eps, float *F, int *converged, double *fitness);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,12 @@ class OrcDebug(C.Structure):
                 ("centroid_bytes", C.POINTER(C.c_uint8)), ("output_cloud", C.POINTER(C.c_uint8))]
 
 
+class OrcDeltaInfo(C.Structure):
+    _fields_ = [("macro_blocks", C.c_uint64), ("shared_blocks", C.c_uint64), ("converged_blocks", C.c_uint64),
+                ("n_intra_points", C.c_uint64), ("n_p_points", C.c_uint64),
+                ("shared_percentage", C.c_float), ("convergence_percentage", C.c_float)]
+
+
 class OrcQuality(C.Structure):
     _fields_ = [("in_point_count", C.c_uint64), ("out_point_count", C.c_uint64), ("symm_rms", C.c_float), ("symm_hausdorff", C.c_float),
                 ("left_hausdorff", C.c_float), ("right_hausdorff", C.c_float), ("left_rms", C.c_float), ("right_rms", C.c_float),
@@ -74,6 +80,15 @@ def lib():
                                     C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
         L.orc_dfs_recursive.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(u8p), szp]
         L.orc_quality_metrics.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(OrcQuality)]
+        L.orc_simplify.argtypes = [C.POINTER(OrcParams), C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), szp]
+        L.orc_encode_delta.argtypes = [C.POINTER(OrcParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int,
+                                       C.POINTER(u8p), szp, C.POINTER(u8p), szp, C.POINTER(C.c_void_p), szp, C.POINTER(OrcDeltaInfo)]
+        L.orc_decode_delta.argtypes = [C.POINTER(OrcParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                       C.POINTER(C.c_void_p), szp, C.POINTER(C.c_uint64)]
+        L.orc_compress_rigid_transform.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.orc_decompress_rigid_transform.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_icp.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_void_p,
+                              C.POINTER(C.c_int), C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -235,3 +250,79 @@ def quality_metrics(cloud_a, cloud_b):
     q = OrcQuality()
     lib().orc_quality_metrics(a.ctypes.data, a.nbytes // 32, b.ctypes.data, b.nbytes // 32, C.byref(q))
     return q
+
+
+# ---------------------------------------------------------------- inter-frame (predictive) path
+def _take_points(ptr, n):
+    if not n:
+        return np.zeros((0, 32), np.uint8)
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * 32,)).copy()
+    lib().orc_free(ptr)
+    return arr.reshape(-1, 32)
+
+
+def simplify(points, params):
+    """simplifyPCloud (impl.hpp:318-400): (V, 32) uint8 records."""
+    a = np.ascontiguousarray(points)
+    out, n = C.c_void_p(), C.c_size_t()
+    rc = lib().orc_simplify(C.byref(params), a.ctypes.data, a.nbytes // 32, C.byref(out), C.byref(n))
+    if rc:
+        raise RuntimeError("orc_simplify rc=%d" % rc)
+    return _take_points(out, n.value)
+
+
+def encode_delta(icloud, pcloud, params, icp_on_original=False, want_out_cloud=False):
+    """encodePointCloudDeltaFrame (impl.hpp:787-1112) -> (i_stream, p_stream, info[, predicted cloud])."""
+    L = lib()
+    ic, pc = np.ascontiguousarray(icloud), np.ascontiguousarray(pcloud)
+    io, po = C.POINTER(C.c_uint8)(), C.POINTER(C.c_uint8)()
+    il, pl = C.c_size_t(), C.c_size_t()
+    oc, on = C.c_void_p(), C.c_size_t()
+    info = OrcDeltaInfo()
+    rc = L.orc_encode_delta(C.byref(params), ic.ctypes.data, ic.nbytes // 32, pc.ctypes.data, pc.nbytes // 32, int(icp_on_original),
+                            C.byref(io), C.byref(il), C.byref(po), C.byref(pl),
+                            C.byref(oc) if want_out_cloud else None, C.byref(on) if want_out_cloud else None, C.byref(info))
+    if rc:
+        raise RuntimeError("orc_encode_delta rc=%d" % rc)
+    i_s, p_s = _take(io, il.value).tobytes(), _take(po, pl.value).tobytes()
+    L.orc_free(io); L.orc_free(po)
+    if want_out_cloud:
+        return i_s, p_s, info, _take_points(oc, on.value)
+    return i_s, p_s, info
+
+
+def decode_delta(icloud, i_stream, p_stream, params):
+    """decodePointCloudDeltaFrame (impl.hpp:1120-1235) -> ((n, 32) uint8 records, decoded macroblocks)."""
+    ic = np.ascontiguousarray(icloud)
+    a, b = np.frombuffer(i_stream, np.uint8), np.frombuffer(p_stream, np.uint8)
+    out, n, nb = C.c_void_p(), C.c_size_t(), C.c_uint64()
+    rc = lib().orc_decode_delta(C.byref(params), ic.ctypes.data, ic.nbytes // 32, a.ctypes.data if a.size else None, a.size,
+                                b.ctypes.data if b.size else None, b.size, C.byref(out), C.byref(n), C.byref(nb))
+    if rc:
+        raise RuntimeError("orc_decode_delta rc=%d" % rc)
+    return _take_points(out, n.value), nb.value
+
+
+def compress_rigid_transform(m):
+    """4x4 float32 (row-major) -> int16 words (6: quaternion mode, 10: two-row mode)."""
+    a = np.ascontiguousarray(m, np.float32)
+    out = np.zeros(10, np.int16)
+    n = C.c_int()
+    lib().orc_compress_rigid_transform(a.ctypes.data, out.ctypes.data, C.byref(n))
+    return out[:n.value].copy()
+
+
+def decompress_rigid_transform(words):
+    w = np.ascontiguousarray(words, np.int16)
+    m = np.zeros((4, 4), np.float32)
+    lib().orc_decompress_rigid_transform(w.ctypes.data, w.size, m.ctypes.data)
+    return m
+
+
+def icp(src_xyz, tgt_xyz, max_iter=50, tf_eps=float(np.float32(1e-8)), fit_eps=float(np.float32(3) * np.float32(1e-8))):
+    """-> (4x4 float32, converged, fitness, iterations)."""
+    s, t = np.ascontiguousarray(src_xyz, np.float32), np.ascontiguousarray(tgt_xyz, np.float32)
+    F = np.zeros((4, 4), np.float32)
+    conv, fit = C.c_int(), C.c_double()
+    it = lib().orc_icp(s.ctypes.data, s.shape[0], t.ctypes.data, t.shape[0], max_iter, tf_eps, fit_eps, F.ctypes.data, C.byref(conv), C.byref(fit))
+    return F, bool(conv.value), fit.value, it
