@@ -46,6 +46,14 @@ class Quality(C.Structure):
                 ("psnr_db", C.c_double), ("psnr_yuv", C.c_double * 3)]
 
 
+class DeltaInfo(C.Structure):
+    """ccv2_delta_info: the prediction statistics of one delta frame (impl.hpp:803-805, 1105-1106)."""
+    _fields_ = [("macro_blocks", C.c_uint64), ("shared_blocks", C.c_uint64), ("converged_blocks", C.c_uint64),
+                ("n_intra_points", C.c_uint64), ("n_p_points", C.c_uint64),
+                ("shared_percentage", C.c_float), ("convergence_percentage", C.c_float),
+                ("predict_ms", C.c_float), ("intra_ms", C.c_float)]
+
+
 _lib = None
 
 
@@ -98,6 +106,13 @@ def load_library():
     L.ccv2_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, szp]
     L.ccv2_get_output_cloud.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, szp]
     L.ccv2_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.ccv2_encode_delta.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, szp,
+                                    C.c_void_p, C.c_size_t, szp, C.c_void_p, C.c_size_t, szp, C.POINTER(DeltaInfo)]
+    L.ccv2_decode_delta.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                    C.c_void_p, C.c_size_t, szp, C.POINTER(C.c_uint64)]
+    L.ccv2_simplify.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, szp]
+    L.ccv2_max_p_stream_size.argtypes = [C.c_size_t]
+    L.ccv2_max_p_stream_size.restype = C.c_size_t
     L.ccv2_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int)]
     _lib = L
     return L
@@ -108,7 +123,8 @@ EXPORTED_SYMBOLS = ["ccv2_default_params", "ccv2_create", "ccv2_destroy", "ccv2_
                     "ccv2_set_frame_id", "ccv2_get_frame_id", "ccv2_last_launch_count", "ccv2_last_device_ms",
                     "ccv2_last_error", "ccv2_status_string", "ccv2_host_alloc", "ccv2_host_free", "ccv2_debug_fetch", "ccv2_get_output_cloud",
                     "ccv2_set_profiling", "ccv2_get_profile", "ccv2_submit_encode", "ccv2_submit_decode", "ccv2_submit_roundtrip",
-                    "ccv2_wait", "ccv2_timer_start", "ccv2_timer_stop", "ccv2_quality_metrics", "ccv2_split_tiles", "ccv2_encode_tiles"]
+                    "ccv2_wait", "ccv2_timer_start", "ccv2_timer_stop", "ccv2_quality_metrics", "ccv2_split_tiles", "ccv2_encode_tiles",
+                    "ccv2_encode_delta", "ccv2_decode_delta", "ccv2_simplify", "ccv2_max_p_stream_size"]
 
 
 def _status_string(s):
@@ -329,6 +345,58 @@ class Codec:
         self._check(self._L.ccv2_quality_metrics(self._h, a.ctypes.data if a.size else None, a.nbytes // 32, b.ctypes.data if b.size else None, b.nbytes // 32, C.byref(q)))
         return q
 
+    # ---- inter-frame (predictive) coding: encodePointCloudDeltaFrame / decodePointCloudDeltaFrame (impl.hpp:787-1235)
+    def encode_delta_raw(self, i_ptr, ni, p_ptr, np_, i_out, i_cap, p_out, p_cap, icp_on_original=False, out_ptr=None, out_cap=0):
+        """Pointers may be host or device addresses.  Returns (i_len, p_len, n_out, DeltaInfo)."""
+        il, pl, no = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        info = DeltaInfo()
+        self._check(self._L.ccv2_encode_delta(self._h, i_ptr, ni, p_ptr, np_, int(icp_on_original), i_out, i_cap, C.byref(il),
+                                              p_out, p_cap, C.byref(pl), out_ptr, out_cap, C.byref(no), C.byref(info)))
+        return il.value, pl.value, no.value, info
+
+    def encode_delta(self, icloud, pcloud, icp_on_original=False, want_out_cloud=False):
+        """-> (i_stream, p_stream, DeltaInfo[, predicted frame])."""
+        ic, pc = np.ascontiguousarray(icloud), np.ascontiguousarray(pcloud)
+        ni, npn = ic.nbytes // 32, pc.nbytes // 32
+        icap = min(self._L.ccv2_max_compressed_size(npn), 6 * npn + (1 << 16))
+        pcap = self._L.ccv2_max_p_stream_size(npn)
+        ib, pb = np.empty(icap, np.uint8), np.empty(pcap, np.uint8)
+        ob = np.zeros((ni + npn + 1, 32), np.uint8) if want_out_cloud else None
+        il, pl, no, info = self.encode_delta_raw(ic.ctypes.data if ni else None, ni, pc.ctypes.data if npn else None, npn, ib.ctypes.data, icap,
+                                                 pb.ctypes.data, pcap, icp_on_original, ob.ctypes.data if want_out_cloud else None, ni + npn + 1 if want_out_cloud else 0)
+        if want_out_cloud:
+            return ib[:il].tobytes(), pb[:pl].tobytes(), info, ob[:no]
+        return ib[:il].tobytes(), pb[:pl].tobytes(), info
+
+    def decode_delta_raw(self, i_ptr, ni, is_ptr, is_len, ps_ptr, ps_len, out_ptr, out_cap):
+        n, nb = C.c_size_t(), C.c_uint64()
+        self._check(self._L.ccv2_decode_delta(self._h, i_ptr, ni, is_ptr, is_len, ps_ptr, ps_len, out_ptr, out_cap, C.byref(n), C.byref(nb)))
+        return n.value, nb.value
+
+    def decode_delta(self, icloud, i_stream, p_stream, cap_points=None):
+        """-> ((n, 32) uint8 records, decoded macroblocks)."""
+        ic = np.ascontiguousarray(icloud)
+        ni = ic.nbytes // 32
+        a, b = np.frombuffer(i_stream, np.uint8), np.frombuffer(p_stream, np.uint8)
+        if cap_points is None:
+            cnt = C.c_uint64(0)
+            if a.size and self._L.ccv2_peek_point_count(a.ctypes.data, a.size, C.byref(cnt)):
+                cnt = C.c_uint64(0)
+            cap_points = ni * max(1, b.size // 19 // max(1, ni) + 1) + cnt.value + 1
+        out = np.zeros((cap_points, 32), np.uint8)
+        n, nb = self.decode_delta_raw(ic.ctypes.data if ni else None, ni, a.ctypes.data if a.size else None, a.size,
+                                      b.ctypes.data if b.size else None, b.size, out.ctypes.data, cap_points)
+        return out[:n], nb
+
+    def simplify(self, cloud):
+        """simplifyPCloud (impl.hpp:318-400) -> (V, 32) uint8 records."""
+        a = np.ascontiguousarray(cloud)
+        n = a.nbytes // 32
+        out = np.zeros((max(n, 1), 32), np.uint8)
+        v = C.c_size_t()
+        self._check(self._L.ccv2_simplify(self._h, a.ctypes.data if n else None, n, out.ctypes.data, out.shape[0], C.byref(v)))
+        return out[:v.value]
+
     def timer_start(self):
         self._check(self._L.ccv2_timer_start(self._h))
 
@@ -468,7 +536,38 @@ class OctreePointCloudCodecV2:
         p.num_threads = num_threads
         p.macroblock_size = 16            # codec.h:138
         p.do_icp_color_offset = 0         # codec.h:141
+        self._params, self._device = p, device
         self._codec = Codec(p, device)
+        self._mb = (0.0, 0.0)
+
+    def _reconfigure(self):               # the setters change state the C handle was created with
+        fid = self._codec.frame_id
+        self._codec.close()
+        self._codec = Codec(self._params, self._device)
+        self._codec.frame_id = fid
+
+    def setMacroblockSize(self, size):    # codec.h:149-152
+        self._params.macroblock_size = int(size); self._reconfigure()
+
+    def setDoICPColorOffset(self, doit):  # codec.h:164-167 (the bool overload)
+        self._params.do_icp_color_offset = int(bool(doit)); self._reconfigure()
+
+    def encodePointCloudDeltaFrame(self, icloud, pcloud, icp_on_original=False, write_out_cloud=False):
+        """codec.h:180-184: returns (i_coded_data, p_coded_data, out_cloud); out_cloud is empty unless write_out_cloud."""
+        r = self._codec.encode_delta(icloud, pcloud, icp_on_original, write_out_cloud)
+        info = r[2]
+        self._mb = (info.shared_percentage, info.convergence_percentage)
+        return r[0], r[1], (r[3] if write_out_cloud else np.zeros((0, 32), np.uint8))
+
+    def decodePointCloudDeltaFrame(self, icloud, i_coded_data, p_coded_data):
+        """codec.h:186-190: returns the decoded frame."""
+        return self._codec.decode_delta(icloud, i_coded_data, p_coded_data)[0]
+
+    def getMacroBlockPercentage(self):            # codec.h:200-204
+        return self._mb[0]
+
+    def getMacroBlockConvergencePercentage(self):  # codec.h:206-210
+        return self._mb[1]
 
     def encodePointCloud(self, cloud):
         return self._codec.encode_batch([cloud])[0]

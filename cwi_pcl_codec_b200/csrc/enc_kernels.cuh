@@ -72,6 +72,9 @@ __global__ void __launch_bounds__(1024) bbox_kernel(EncFrame *frames, EncParams 
     start = 0; end = min(f.n, (uint32_t)P.prefix_len); nev = 0;
     b.defined = 0; b.depth = 0;
     for (int a = 0; a < 3; a++) { b.mn[a] = 0; b.mx[a] = 0; }
+    // a box the host defined before the first point ([PCL] defineBoundingBox, as simplifyPCloud and the macroblock trees
+    // do, impl.hpp:336,427): the record carries it together with its entry 0 of the event log; points outside still grow it
+    if (f.defined) { b.defined = 1; b.depth = f.depth; nev = f.n_events; for (int a = 0; a < 3; a++) { b.mn[a] = f.bmin[a]; b.mx[a] = f.bmax[a]; } }
   } else {
     if (f.violator == NONE_U32 || (f.error & FERR_DEPTH)) return;
     start = f.violator; end = f.n; nev = f.n_events;
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf_scan_kernel(EncFrame *frame
       if (i == nf - 1) {
         uint32_t V = (uint32_t)(excl >> 36); uint64_t B = excl & 0xFFFFFFFFFull;
         f.V = V; f.leaf_start[V] = nf; f.leaf_off[V] = (uint32_t)B;
-        if (B > f.tree_cap) { f.error |= FERR_TREE_CAP; B = 0; f.V = 0; }
+        if (f.tree && B > f.tree_cap) { f.error |= FERR_TREE_CAP; B = 0; f.V = 0; }   // f.tree == nullptr: a grid without occupancy bytes (inter_kernels.cuh)
         f.B = (uint32_t)B;
         f.img_h = V / 256 + 1;                         // cjpeg.h:197-198
         f.mcu_h = (f.img_h + 15) / 16;
@@ -414,6 +417,7 @@ __global__ void __launch_bounds__(LEAF_THREADS) leaf_scan_kernel(EncFrame *frame
     }
   }
   // zero this tile's slice of the tree bytes (the occupancy kernel ORs into it)
+  if (!f.tree) return;
   uint64_t b0 = tile_excl & 0xFFFFFFFFFull, b1 = b0 + (tile_total & 0xFFFFFFFFFull);
   if (b1 > f.tree_cap) b1 = f.tree_cap;
   // word-granular zeroing with byte edges

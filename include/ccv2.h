@@ -197,6 +197,40 @@ typedef struct ccv2_quality {
 } ccv2_quality;
 int ccv2_quality_metrics(ccv2_codec *c, const void *cloud_a, size_t na, const void *cloud_b, size_t nb, ccv2_quality *out);
 
+/* ---- Inter-frame (predictive) coding: BASELINE configs[2], SURVEY 8 rows a14 / f-1 ---------------------------------------
+ * Replaces: encodePointCloudDeltaFrame / decodePointCloudDeltaFrame (codec.h:180-190, impl.hpp:787-1112, 1120-1235) with
+ * their helpers simplifyPCloud (impl.hpp:318-400), generate_macroblock_tree (:410-431), do_icp_prediction (:443-568) and
+ * the RigidTransformCoding / QuaternionCoding classes (rigid_transform_coding_impl.hpp:63-203,
+ * quaternion_coding_impl.hpp:55-222).  icloud = the frame predicted FROM (evaluate_compression passes the encoder's
+ * simplified cloud of the previous frame, eval.hpp:862 -> ccv2_get_output_cloud; the decoder passes its decoded previous
+ * frame), pcloud = the frame to code.  Both streams are the reference's: the P stream is the chunk list
+ * [u8 size][3 x i16 macroblock key][6 | 10 x i16 transform][3 x i8 colour offsets] (impl.hpp:877-883), the I stream an
+ * ordinary intra frame of the points no macroblock predicted, written by a fresh codec with the reference's ten explicit
+ * constructor arguments (impl.hpp:1089-1101: scalable stream on, JPEG quality 75 whatever this codec uses).
+ * The registration follows PCL 1.10's IterativeClosestPoint as the reference configures it (50 iterations, transformation
+ * epsilon 1e-8f, fitness epsilon 3e-8f, accepted when the fitness is below 2 x point_resolution) with the arithmetic
+ * oracle/ccv2_oracle_inter.c states; no build of the reference reproduces another build's ICP bits, so parity for this path
+ * is: bit-exact against the oracle, format + quality against the reference.
+ * All cloud and stream pointers may be host or device memory.  out_cloud (may be NULL) receives the predicted frame the
+ * reference writes when write_out_cloud is set.  Macroblock size and colour offsets come from ccv2_params. */
+typedef struct ccv2_delta_info {
+  uint64_t macro_blocks, shared_blocks, converged_blocks;   /* macro_block_count, shared_macroblock_count, convergence_count (impl.hpp:803-805) */
+  uint64_t n_intra_points, n_p_points;                      /* points coded intra; points of the (simplified) P cloud */
+  float shared_percentage, convergence_percentage;          /* getMacroBlockPercentage / getMacroBlockConvergencePercentage (codec.h:200-210) */
+  float predict_ms, intra_ms;                               /* device time of the prediction stage / of the intra coder's call */
+} ccv2_delta_info;
+int ccv2_encode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *pcloud, size_t np, int icp_on_original,
+                      void *i_out, size_t i_cap, size_t *i_len, void *p_out, size_t p_cap, size_t *p_len,
+                      void *out_cloud, size_t out_cap_points, size_t *n_out, ccv2_delta_info *info);
+/* pts_out: cap_points records; the predicted macroblocks come first (chunk order), then the intra-coded points.
+ * decoded_blocks (may be NULL): macroblocks that found their I block. */
+int ccv2_decode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *i_in, size_t i_len, const void *p_in, size_t p_len,
+                      void *pts_out, size_t cap_points, size_t *npts, uint64_t *decoded_blocks);
+/* simplifyPCloud alone (impl.hpp:318-400): one point per occupied voxel of the unit-box octree, DFS order. */
+int ccv2_simplify(ccv2_codec *c, const void *pts, size_t n, void *pts_out, size_t cap_points, size_t *npts);
+/* Upper bound of a P stream for a P cloud of np points. */
+size_t ccv2_max_p_stream_size(size_t np);
+
 /* Pinned host memory helpers (cudaMallocHost / cudaFreeHost) for callers that want full-speed PCIe copies. */
 void *ccv2_host_alloc(size_t bytes);
 void ccv2_host_free(void *p);
