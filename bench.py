@@ -215,9 +215,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--mode", default="roundtrip", choices=["roundtrip", "decode", "tiles"],
+    ap.add_argument("--mode", default="roundtrip", choices=["roundtrip", "decode", "tiles", "inter"],
                     help="roundtrip: the headline metric (encode+decode); decode: BASELINE configs[4], decode-only on oracle-produced streams resident in device memory; "
-                         "tiles: BASELINE configs[3], one dense 4M-point frame at octree_bits 12 cut into root-octant tiles (sharded over the ranks, streams gathered on rank 0)")
+                         "tiles: BASELINE configs[3], one dense 4M-point frame at octree_bits 12 cut into root-octant tiles (sharded over the ranks, streams gathered on rank 0); "
+                         "inter: BASELINE configs[2], a 30-frame group of 1M-point frames, every frame coded intra and as a P frame against its predecessor, frames sharded over the ranks, "
+                         "the predictor clouds sent to the neighbour rank over NCCL")
+    ap.add_argument("--gof-frames", type=int, default=30)
     ap.add_argument("--tile-bits", type=int, default=3, choices=[3, 6])
     ap.add_argument("--frames", type=int, default=int(os.environ.get("BENCH_FRAMES", "0")),
                     help="frames per step per GPU (0: as many as fit in device memory, at most 1024 -- the serial entropy stage is latency bound, so throughput grows with the frames in flight)")
@@ -248,6 +251,8 @@ def main():
         return run_decode_mode(args, torch, dist, K, rank, world, local, dev)
     if args.mode == "tiles":
         return run_tiles_mode(args, torch, dist, K, rank, world, local, dev)
+    if args.mode == "inter":
+        return run_inter_mode(args, torch, dist, K, rank, world, local, dev)
     NP = args.points
     F = args.frames
     cap = 4 * NP + (1 << 16)
@@ -604,6 +609,134 @@ def run_tiles_mode(args, torch, dist, K, rank, world, local, dev):
                 "stream_bytes_tiled": r["stream_bytes"], "stream_bytes_untiled": plain["stream_bytes"], "voxels": r["voxels"],
                 "jpeg_quality_sweep": {str(q): {"ms_per_frame": results[q]["ms_per_frame"], "stream_bytes": results[q]["stream_bytes"]} for q in sorted(results)},
                 "clocks": r["clocks"], "gpu_launches": int(r["launches"])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_inter_mode(args, torch, dist, K, rank, world, local, dev):
+    """BASELINE configs[2]: a group of frames (30 x 1M points, synth.gen_gof), do_delta_coding as evaluate_compression runs it
+    (eval.hpp:818-889): every frame is coded intra (encode + decode), and every frame but the first is ALSO coded as a P frame
+    against the encoder's simplified cloud of its predecessor (encode + decode).  Frame f lives on rank f mod world; the
+    predictor cloud of frame f travels to the owner of frame f + 1 over NCCL point to point (gof.exchange_predictors).
+    Strong scaling of ONE group: value = points of the group / time of the step."""
+    from cwi_pcl_codec_b200 import gof as G, synth
+    NP, NF, bits = args.points, args.gof_frames, args.bits
+    mine = G.owned_frames(NF, rank, world)
+    clouds = synth.gen_gof(NP, seed=0, frames=NF)
+    d_in = {f: torch.from_numpy(clouds[f].view(np.uint8).reshape(-1)).to(dev) for f in mine}
+    first = clouds[0] if rank == 0 else None
+    del clouds
+    cap = 4 * NP + (1 << 16)
+    codec = K.Codec(K.default_params(octree_bits=bits), device=local)
+    d_str = {f: torch.empty(cap, dtype=torch.uint8, device=dev) for f in mine}
+    d_dec = {f: torch.empty(NP * 32, dtype=torch.uint8, device=dev) for f in mine}
+    d_oc = {f: torch.empty(NP * 32, dtype=torch.uint8, device=dev) for f in mine}
+    d_is = {f: torch.empty(cap, dtype=torch.uint8, device=dev) for f in mine if f >= 1}
+    d_ps = {f: torch.empty(30 * NP // 16 + (1 << 20), dtype=torch.uint8, device=dev) for f in mine if f >= 1}
+    d_pdec = {f: torch.empty(2 * NP * 32, dtype=torch.uint8, device=dev) for f in mine if f >= 1}
+    lib = K.load_library()
+    import ctypes as C
+    stats = {}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        launches = 0
+        t = {}
+        t0 = time.perf_counter()
+        lens = codec.encode_batch_raw([d_in[f].data_ptr() for f in mine], [NP] * len(mine), [d_str[f].data_ptr() for f in mine], [cap] * len(mine)) if mine else []
+        launches += codec.last_launch_count if mine else 0
+        local_oc = {}
+        for k, f in enumerate(mine):                             # [PCL] getOutputCloud of every I frame, straight into device memory
+            n = C.c_size_t()
+            codec._check(lib.ccv2_get_output_cloud(codec._h, k, d_oc[f].data_ptr(), NP, C.byref(n)))
+            local_oc[f] = d_oc[f][:32 * n.value]
+            launches += 1
+        t["intra_encode"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        ns = codec.decode_batch_raw([d_str[f].data_ptr() for f in mine], lens, [d_dec[f].data_ptr() for f in mine], [NP] * len(mine)) if mine else []
+        launches += codec.last_launch_count if mine else 0
+        t["intra_decode"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        pred = G.exchange_predictors(local_oc, NF, dist if world > 1 else None, device=dev)
+        torch.cuda.synchronize()
+        t["exchange"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        tot = {"i": 0, "p": 0, "mb": 0, "shared": 0, "conv": 0, "intra_pts": 0, "ppts": 0, "dec_pts": 0, "predict_ms": 0.0, "intra_ms": 0.0, "xbytes": 0}
+        pf = [g for g in mine if g >= 1]
+        td = 0.0
+        if pf:                                                   # all P frames of this rank in one call each way: the intra parts run as one pipelined batch
+            ics = [pred[g] for g in pf]
+            nis = [ic.numel() // 32 for ic in ics]
+            tot["xbytes"] = sum(ic.numel() for g, ic in zip(pf, ics) if G.owner(g - 1, world) != rank)
+            ils, pls, infos = codec.encode_delta_batch_raw([ic.data_ptr() for ic in ics], nis, [d_in[g].data_ptr() for g in pf], [NP] * len(pf),
+                                                           [d_is[g].data_ptr() for g in pf], [d_is[g].numel() for g in pf], [d_ps[g].data_ptr() for g in pf], [d_ps[g].numel() for g in pf])
+            launches += codec.last_launch_count
+            t1 = time.perf_counter()
+            nds, nbs = codec.decode_delta_batch_raw([ic.data_ptr() for ic in ics], nis, [d_is[g].data_ptr() for g in pf], ils, [d_ps[g].data_ptr() for g in pf], pls,
+                                                    [d_pdec[g].data_ptr() for g in pf], [d_pdec[g].numel() // 32 for g in pf])
+            launches += codec.last_launch_count
+            td = time.perf_counter() - t1
+            for il, pl, info, n in zip(ils, pls, infos, nds):
+                tot["i"] += il; tot["p"] += pl; tot["mb"] += info.macro_blocks; tot["shared"] += info.shared_blocks; tot["conv"] += info.converged_blocks
+                tot["intra_pts"] += info.n_intra_points; tot["ppts"] += info.n_p_points; tot["dec_pts"] += n; tot["predict_ms"] += info.predict_ms; tot["intra_ms"] += info.intra_ms
+        t["delta_decode"] = td; t["delta_encode"] = time.perf_counter() - t0 - td
+        tot["intra_bytes"] = int(sum(lens)); tot["intra_voxels"] = int(sum(ns))
+        return launches, t, tot
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    launches = 0
+    for _ in range(args.steps):
+        l, tparts, tot = step(); launches += l
+    barrier()
+    wall = reduce_max(time.perf_counter() - t0, dist if world > 1 else None, dev)
+    clocks = sampler.stop()
+    keys = sorted(k for k in tot if k not in ("predict_ms", "intra_ms"))
+    agg = torch.tensor([float(tot[k]) for k in keys], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(agg)
+    tot_all = dict(zip(keys, [float(v) for v in agg]))
+    parts = torch.tensor([tparts[k] for k in sorted(tparts)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(parts, op=dist.ReduceOp.MAX)
+    # CPU side of the comparison (rank 0, one delta frame of the same group at reduced size would not be the same workload:
+    # the oracle codes frame 1 against frame 0 at FULL size once; ~10-30 s)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        cl = synth.gen_gof(NP, seed=0, frames=2)
+        op = O.default_params(octree_bits=bits)
+        t1 = time.perf_counter()
+        ref, _, dbg = O.encode(cl[0], op, debug=True)
+        rd, _ = O.decode(ref)
+        ri, rp, rinfo = O.encode_delta(dbg["output_cloud"], cl[1], op)
+        pdec, _ = O.decode_delta(dbg["output_cloud"], ri, rp, op)
+        dt = time.perf_counter() - t1
+        cpu = {"value": NP / dt / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "port",
+               "sample": "frames 0 and 1 of the same group: intra encode + decode of frame 0, P encode + decode of frame 1 against it, CPU oracle, 1 thread, %.1f s" % dt}
+    if rank == 0:
+        step_s = wall / args.steps
+        line = {"metric": "Mpoints/s of a group of frames with inter-frame prediction (BASELINE configs[2]): every frame intra encode+decode, every frame but the first also P encode+decode against its predecessor; P and I streams bit-exact vs the oracle",
+                "value": NF * NP / step_s / 1e6, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": step_s * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/u32/f32/f64 (integer codec, FP64 keys, FP32 ICP distances, FP64 alignment)", "data": "synthetic",
+                "config": {"workload": "BASELINE.json configs[2]: GOF(0, %d) of %d-point frames (synth.gen_gof: 0.4 deg/frame rotation, 0.002/frame shift, 1 %% re-sampled), octree_bits %d, macroblock_size 16, "
+                                       "icp_on_original 0; frame f on rank f mod %d, the simplified cloud of frame f sent to the owner of frame f+1 (NCCL point to point)" % (NF, NP, bits, world),
+                           "points_per_frame": NP, "frames": NF, "cache": "each frame (32 MB) and its simplified cloud (30 MB) exceed what stays in L2 between uses; frames of a step are distinct"},
+                "timing": "wall clock of the step (synchronous calls), max over ranks; device-resident inputs and outputs",
+                "phase_ms_max_over_ranks": dict(zip(sorted(tparts), [float(v) * 1e3 for v in parts])),
+                "prediction": {"macro_blocks": tot_all["mb"], "shared": tot_all["shared"], "predicted": tot_all["conv"], "points_coded_intra": tot_all["intra_pts"], "p_cloud_points": tot_all["ppts"],
+                               "p_stream_bytes": tot_all["p"], "i_stream_bytes": tot_all["i"], "intra_only_bytes_all_frames": tot_all["intra_bytes"], "decoded_points": tot_all["dec_pts"],
+                               "predictor_bytes_exchanged_per_step": tot_all["xbytes"],
+                               "device_ms_per_p_frame_rank0": {"prediction_stage": tot["predict_ms"] / max(1, len([g for g in mine if g >= 1])), "intra_coder": tot["intra_ms"] / max(1, len([g for g in mine if g >= 1]))}},
+                "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": int(launches)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -111,6 +111,8 @@ def load_library():
     L.ccv2_decode_delta.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                     C.c_void_p, C.c_size_t, szp, C.POINTER(C.c_uint64)]
     L.ccv2_simplify.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, szp]
+    L.ccv2_encode_delta_batch.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, C.c_int, vpp, szp, szp, vpp, szp, szp, C.POINTER(DeltaInfo)]
+    L.ccv2_decode_delta_batch.argtypes = [C.c_void_p, C.c_int, vpp, szp, vpp, szp, vpp, szp, vpp, szp, szp, C.POINTER(C.c_uint64)]
     L.ccv2_max_p_stream_size.argtypes = [C.c_size_t]
     L.ccv2_max_p_stream_size.restype = C.c_size_t
     L.ccv2_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int)]
@@ -124,7 +126,7 @@ EXPORTED_SYMBOLS = ["ccv2_default_params", "ccv2_create", "ccv2_destroy", "ccv2_
                     "ccv2_last_error", "ccv2_status_string", "ccv2_host_alloc", "ccv2_host_free", "ccv2_debug_fetch", "ccv2_get_output_cloud",
                     "ccv2_set_profiling", "ccv2_get_profile", "ccv2_submit_encode", "ccv2_submit_decode", "ccv2_submit_roundtrip",
                     "ccv2_wait", "ccv2_timer_start", "ccv2_timer_stop", "ccv2_quality_metrics", "ccv2_split_tiles", "ccv2_encode_tiles",
-                    "ccv2_encode_delta", "ccv2_decode_delta", "ccv2_simplify", "ccv2_max_p_stream_size"]
+                    "ccv2_encode_delta", "ccv2_decode_delta", "ccv2_simplify", "ccv2_max_p_stream_size", "ccv2_encode_delta_batch", "ccv2_decode_delta_batch"]
 
 
 def _status_string(s):
@@ -367,6 +369,23 @@ class Codec:
         if want_out_cloud:
             return ib[:il].tobytes(), pb[:pl].tobytes(), info, ob[:no]
         return ib[:il].tobytes(), pb[:pl].tobytes(), info
+
+    def encode_delta_batch_raw(self, i_ptrs, nis, p_ptrs, nps, i_outs, i_caps, p_outs, p_caps, icp_on_original=False):
+        """n delta frames in one call (the intra parts as one pipelined batch).  Returns (i_lens, p_lens, [DeltaInfo])."""
+        n = len(i_ptrs)
+        A = lambda v: (C.c_void_p * n)(*v)
+        Z = lambda v: (C.c_size_t * n)(*v)
+        il, pl, info = (C.c_size_t * n)(), (C.c_size_t * n)(), (DeltaInfo * n)()
+        self._check(self._L.ccv2_encode_delta_batch(self._h, n, A(i_ptrs), Z(nis), A(p_ptrs), Z(nps), int(icp_on_original), A(i_outs), Z(i_caps), il, A(p_outs), Z(p_caps), pl, info))
+        return list(il), list(pl), list(info)
+
+    def decode_delta_batch_raw(self, i_ptrs, nis, is_ptrs, is_lens, ps_ptrs, ps_lens, out_ptrs, out_caps):
+        n = len(i_ptrs)
+        A = lambda v: (C.c_void_p * n)(*v)
+        Z = lambda v: (C.c_size_t * n)(*v)
+        npts, nb = (C.c_size_t * n)(), (C.c_uint64 * n)()
+        self._check(self._L.ccv2_decode_delta_batch(self._h, n, A(i_ptrs), Z(nis), A(is_ptrs), Z(is_lens), A(ps_ptrs), Z(ps_lens), A(out_ptrs), Z(out_caps), npts, nb))
+        return list(npts), list(nb)
 
     def decode_delta_raw(self, i_ptr, ni, is_ptr, is_len, ps_ptr, ps_len, out_ptr, out_cap):
         n, nb = C.c_size_t(), C.c_uint64()

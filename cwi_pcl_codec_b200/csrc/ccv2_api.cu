@@ -163,7 +163,7 @@ struct ccv2_codec {
   EncParams last_enc_params;               // of the last encode (ccv2_get_output_cloud)
   DevBuf out_cloud;                        // staging for ccv2_get_output_cloud into host memory
   DevBuf tile_pts, tile_aux;               // tile mode: the partitioned frame, counters
-  DevBuf inter_ws;                         // inter-frame path: grids, macroblock results, staging (ccv2_inter.cuh)
+  DevBuf inter_ws, inter_batch;            // inter-frame path: grids, macroblock results, staging; the unpredicted points of a batch of delta frames (ccv2_inter.cuh)
   ccv2_codec *intra_child = nullptr;       // the fresh intra coder a delta frame's unpredicted points go through (impl.hpp:1089-1101)
   cudaEvent_t inter_ev0 = nullptr, inter_ev1 = nullptr;
   float mb_percentage = 0.f, mb_convergence = 0.f;   // getMacroBlockPercentage / getMacroBlockConvergencePercentage of the last delta frame
@@ -637,7 +637,7 @@ void ccv2_destroy(ccv2_codec *c) {
   if (c->green_par && c->drv_green_destroy) c->drv_green_destroy(c->green_par);
   if (c->d_tables) cudaFree(c->d_tables);
   if (c->d_frame_counter) cudaFree(c->d_frame_counter);
-  c->out_cloud.release(); c->tile_pts.release(); c->tile_aux.release(); c->inter_ws.release();
+  c->out_cloud.release(); c->tile_pts.release(); c->tile_aux.release(); c->inter_ws.release(); c->inter_batch.release();
   if (c->intra_child) ccv2_destroy(c->intra_child);
   for (cudaEvent_t ev : { c->inter_ev0, c->inter_ev1 }) if (ev) cudaEventDestroy(ev);
   delete c;

@@ -142,16 +142,13 @@ int ccv2_simplify(ccv2_codec *c, const void *pts, size_t n, void *pts_out, size_
   return CCV2_OK;
 }
 
-int ccv2_encode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *pcloud, size_t np, int icp_on_original,
-                      void *i_out, size_t i_cap, size_t *i_len, void *p_out, size_t p_cap, size_t *p_len,
-                      void *out_cloud, size_t out_cap_points, size_t *n_out, ccv2_delta_info *info) {
-  if (!c || !i_len || !p_len || (ni && !icloud) || (np && !pcloud) || ni >= (1u << 28) || np >= (1u << 28) || (out_cloud && !n_out)) return CCV2_ERR_ARG;
-  if (c->prm.macroblock_size < 1) { c->err = "macroblock_size must be >= 1"; return CCV2_ERR_ARG; }
-  CU(cudaSetDevice(c->device));
-  finish_all(c);
-  c->err.clear();
-  *i_len = 0; *p_len = 0; if (n_out) *n_out = 0;
-  if (info) memset(info, 0, sizeof *info);
+}  // extern "C"
+
+// The prediction stage of one delta frame: grids, matching, ICP, P stream (copied to the caller), predicted frame; the points
+// no macroblock predicted go to intra_dst (device memory, room for np records; nullptr: a buffer in the workspace, returned
+// through *intra_ptr).  One host wait at the end (the counts).
+static int delta_predict(ccv2_codec *c, const void *icloud, size_t ni, const void *pcloud, size_t np, int icp_on_original, uint8_t *intra_dst, const uint8_t **intra_ptr, size_t *n_intra,
+                         void *p_out, size_t p_cap, size_t *p_len, void *out_cloud, size_t out_cap_points, size_t *n_out, ccv2_delta_info *info, uint64_t &launches) {
   const ccv2_params &prm = c->prm;
   const bool cen = prm.do_voxel_grid_centroid != 0, orig = icp_on_original != 0, want_out = out_cloud != nullptr;
   const double res = prm.octree_resolution, mres = prm.octree_resolution * prm.macroblock_size;
@@ -170,7 +167,7 @@ int ccv2_encode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *
     L.res = cv.take<MbResult>(ncP + 1);
     L.cur = cv.take<float>(3 * ncI + 4); L.tgt = cv.take<float>(3 * ncP + 4); L.d2 = cv.take<float>(ncI + 4); L.nn = cv.take<uint32_t>(ncI + 4);
     L.p_off = cv.take<uint32_t>(ncP + 2); L.x_off = cv.take<uint32_t>(ncP + 2); L.o_off = cv.take<uint32_t>(ncP + 2);
-    L.pstr = cv.take<uint8_t>(ccv2_max_p_stream_size(ncP)); L.intra = cv.take<uint8_t>(32 * ncP);
+    L.pstr = cv.take<uint8_t>(ccv2_max_p_stream_size(ncP)); L.intra = intra_dst ? intra_dst : cv.take<uint8_t>(32 * ncP);
     L.outp = want_out ? cv.take<uint8_t>(32 * (ncI + ncP)) : nullptr;
     return cv.end();
   };
@@ -194,7 +191,6 @@ int ccv2_encode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *
   if ((rc = define_unit_box(h[1], mres)) != CCV2_OK || (rc = define_unit_box(h[2], mres)) != CCV2_OK) { c->err = "octree depth > 21"; return rc; }
   // ---- enqueue
   cudaStream_t st = c->fin_stream;
-  uint64_t launches = 0;
   if (!c->inter_ev0) { CU(cudaEventCreate(&c->inter_ev0)); CU(cudaEventCreate(&c->inter_ev1)); }
   CU(cudaEventRecord(c->inter_ev0, st));
   if (!di && ni) CU(cudaMemcpyAsync(L.dI, icloud, 32 * ni, cudaMemcpyHostToDevice, st));
@@ -249,29 +245,97 @@ int ccv2_encode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *
     if (nout > out_cap_points) { c->err = "predicted-frame buffer too small"; return CCV2_ERR_CAPACITY; }
     if (nout) CU(cudaMemcpy(out_cloud, L.outp, 32 * nout, is_device_ptr(out_cloud) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
   }
-  // ---- the rest goes through a fresh intra coder (frame id 1 every time; an empty cloud writes nothing, impl.hpp:206-212)
-  if (nx) {
-    ccv2_codec *ch = nullptr;
-    if ((rc = get_intra_child(c, &ch)) != CCV2_OK) return rc;
-    if ((rc = ccv2_set_frame_id(ch, 0)) != CCV2_OK) { c->err = ccv2_last_error(ch); return rc; }
-    const void *ip = L.intra; void *op = i_out; size_t nn1 = nx, cap1 = i_cap, len1 = 0;
-    if (!i_out) { c->err = "I stream buffer missing"; return CCV2_ERR_CAPACITY; }
-    rc = ccv2_encode_batch(ch, 1, &ip, &nn1, &op, &cap1, &len1);
-    if (rc != CCV2_OK) { c->err = std::string("intra coder of the delta frame: ") + ccv2_last_error(ch); return rc; }
-    *i_len = len1;
-    launches += ccv2_last_launch_count(ch);
-    if (info) info->intra_ms = ccv2_last_device_ms(ch);
-  }
-  c->launches = launches; c->device_ms = pms + (info ? info->intra_ms : 0.f);
+  *n_intra = nx; if (intra_ptr) *intra_ptr = L.intra;
   return CCV2_OK;
 }
 
-int ccv2_decode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *i_in, size_t i_len, const void *p_in, size_t p_len,
-                      void *pts_out, size_t cap_points, size_t *npts, uint64_t *decoded_blocks) {
-  if (!c || !npts || (ni && !icloud) || (i_len && !i_in) || (p_len && !p_in) || ni >= (1u << 28) || p_len >= (1ull << 32) || (cap_points && !pts_out)) return CCV2_ERR_ARG;
+// the unpredicted points of n delta frames through the child codec in ONE pipelined call; every frame is written by "a fresh
+// intra coder" (impl.hpp:1089-1101): frame id 1 each, an empty cloud writes nothing (impl.hpp:206-212)
+static int delta_intra_encode(ccv2_codec *c, int n, const void *const *pts, const size_t *npts, void *const *out, const size_t *cap, size_t *len, float *ms, uint64_t &launches) {
+  ccv2_codec *ch = nullptr;
+  int rc = get_intra_child(c, &ch);
+  if (rc != CCV2_OK) return rc;
+  int ticket = 0;
+  rc = submit_call(ch, 0, n, pts, npts, out, cap, len, nullptr, nullptr, nullptr, nullptr, nullptr, false, /*fixed frame id*/ 1, &ticket);
+  if (rc == CCV2_OK) rc = wait_ticket(ch, ticket);
+  if (rc != CCV2_OK) { c->err = std::string("intra coder of the delta frame: ") + ccv2_last_error(ch); return rc; }
+  launches += ccv2_last_launch_count(ch);
+  if (ms) *ms = ccv2_last_device_ms(ch);
+  return CCV2_OK;
+}
+
+extern "C" {
+
+int ccv2_encode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *pcloud, size_t np, int icp_on_original,
+                      void *i_out, size_t i_cap, size_t *i_len, void *p_out, size_t p_cap, size_t *p_len,
+                      void *out_cloud, size_t out_cap_points, size_t *n_out, ccv2_delta_info *info) {
+  if (!c || !i_len || !p_len || (ni && !icloud) || (np && !pcloud) || ni >= (1u << 28) || np >= (1u << 28) || (out_cloud && !n_out)) return CCV2_ERR_ARG;
+  if (c->prm.macroblock_size < 1) { c->err = "macroblock_size must be >= 1"; return CCV2_ERR_ARG; }
   CU(cudaSetDevice(c->device));
   finish_all(c);
   c->err.clear();
+  *i_len = 0; *p_len = 0; if (n_out) *n_out = 0;
+  ccv2_delta_info li; memset(&li, 0, sizeof li);
+  uint64_t launches = 0;
+  const uint8_t *ip = nullptr; size_t nx = 0;
+  int rc = delta_predict(c, icloud, ni, pcloud, np, icp_on_original, nullptr, &ip, &nx, p_out, p_cap, p_len, out_cloud, out_cap_points, n_out, &li, launches);
+  if (rc == CCV2_OK && nx) {
+    if (!i_out) { c->err = "I stream buffer missing"; rc = CCV2_ERR_CAPACITY; }
+    else { const void *p1 = ip; void *o1 = i_out; rc = delta_intra_encode(c, 1, &p1, &nx, &o1, &i_cap, i_len, &li.intra_ms, launches); }
+  }
+  if (info) *info = li;
+  c->launches = launches; c->device_ms = li.predict_ms + li.intra_ms;
+  return rc;
+}
+
+// n delta frames in one call: the prediction stages one after the other, then ALL the intra parts as one batch through the
+// child codec, whose serial range-coder stage is latency bound -- 29 frames take about as long as one.
+int ccv2_encode_delta_batch(ccv2_codec *c, int nframes, const void *const *icloud, const size_t *ni, const void *const *pcloud, const size_t *np, int icp_on_original,
+                            void *const *i_out, const size_t *i_cap, size_t *i_len, void *const *p_out, const size_t *p_cap, size_t *p_len, ccv2_delta_info *info) {
+  if (!c || nframes < 0 || (nframes && (!icloud || !ni || !pcloud || !np || !i_out || !i_cap || !i_len || !p_out || !p_cap || !p_len))) return CCV2_ERR_ARG;
+  if (c->prm.macroblock_size < 1) { c->err = "macroblock_size must be >= 1"; return CCV2_ERR_ARG; }
+  CU(cudaSetDevice(c->device));
+  finish_all(c);
+  c->err.clear();
+  size_t tot = 0; std::vector<size_t> off(nframes + 1, 0);
+  for (int k = 0; k < nframes; k++) {
+    if ((ni[k] && !icloud[k]) || (np[k] && !pcloud[k]) || ni[k] >= (1u << 28) || np[k] >= (1u << 28)) return CCV2_ERR_ARG;
+    off[k] = tot; tot += (32 * std::max<size_t>(np[k], 1) + 255) & ~size_t(255);
+    i_len[k] = 0; p_len[k] = 0;
+  }
+  CU(c->inter_batch.ensure(tot + 256));
+  uint64_t launches = 0;
+  std::vector<const void *> ip; std::vector<size_t> nx(nframes, 0), icap, ilen; std::vector<void *> io; std::vector<int> who;
+  float pms = 0;
+  for (int k = 0; k < nframes; k++) {
+    ccv2_delta_info li; memset(&li, 0, sizeof li);
+    const int rc = delta_predict(c, icloud[k], ni[k], pcloud[k], np[k], icp_on_original, (uint8_t *)c->inter_batch.p + off[k], nullptr, &nx[k], p_out[k], p_cap[k], &p_len[k], nullptr, 0, nullptr, &li, launches);
+    if (info) info[k] = li;
+    if (rc != CCV2_OK) return rc;
+    pms += li.predict_ms;
+    if (nx[k]) {
+      if (!i_out[k]) { c->err = "I stream buffer missing"; return CCV2_ERR_CAPACITY; }
+      ip.push_back((const uint8_t *)c->inter_batch.p + off[k]); io.push_back(i_out[k]); icap.push_back(i_cap[k]); who.push_back(k);
+    }
+  }
+  float ims = 0;
+  if (!who.empty()) {
+    std::vector<size_t> nn; for (int k : who) nn.push_back(nx[k]);
+    ilen.assign(who.size(), 0);
+    const int rc = delta_intra_encode(c, (int)who.size(), ip.data(), nn.data(), io.data(), icap.data(), ilen.data(), &ims, launches);
+    for (size_t q = 0; q < who.size(); q++) i_len[who[q]] = ilen[q];
+    if (rc != CCV2_OK) return rc;
+    if (info) for (int k : who) info[k].intra_ms = ims / (float)who.size();
+  }
+  c->launches = launches; c->device_ms = pms + ims;
+  return CCV2_OK;
+}
+
+}  // extern "C"
+
+// The prediction half of decodePointCloudDeltaFrame (impl.hpp:1120-1203): the I macroblock tree, the chunk walk, the
+// predicted points into pts_out (host or device).  One host wait (the counts).
+static int delta_apply(ccv2_codec *c, const void *icloud, size_t ni, const void *p_in, size_t p_len, void *pts_out, size_t cap_points, size_t *npts, uint64_t *decoded_blocks, uint64_t &launches) {
   *npts = 0; if (decoded_blocks) *decoded_blocks = 0;
   const ccv2_params &prm = c->prm;
   const double mres = prm.octree_resolution * prm.macroblock_size;
@@ -299,7 +363,6 @@ int ccv2_decode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *
   int rc;
   if ((rc = define_unit_box(h, mres)) != CCV2_OK) { c->err = "octree depth > 21"; return rc; }
   cudaStream_t st = c->fin_stream;
-  uint64_t launches = 0;
   if (!di && ni) CU(cudaMemcpyAsync(L.dI, icloud, 32 * ni, cudaMemcpyHostToDevice, st));
   if (!dps && p_len) CU(cudaMemcpyAsync(L.dps, p_in, p_len, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(L.rec, &h, sizeof h, cudaMemcpyHostToDevice, st));
@@ -338,16 +401,44 @@ int ccv2_decode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *
       CU(e);
     } else CU(cudaMemcpy(pts_out, L.stage, 32 * npred, cudaMemcpyDeviceToHost));
   }
-  size_t nin = 0;
-  if (i_len) {                                               // decodePointCloud of the rest, appended (impl.hpp:1226-1230)
+  return CCV2_OK;
+}
+
+extern "C" {
+
+int ccv2_decode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *i_in, size_t i_len, const void *p_in, size_t p_len,
+                      void *pts_out, size_t cap_points, size_t *npts, uint64_t *decoded_blocks) {
+  const void *ic1 = icloud, *ii1 = i_in, *pi1 = p_in; void *o1 = pts_out;
+  return ccv2_decode_delta_batch(c, 1, &ic1, &ni, &ii1, &i_len, &pi1, &p_len, &o1, &cap_points, npts, decoded_blocks);
+}
+
+// n delta frames: the predicted macroblocks of every frame first, then the intra-coded rest of ALL frames as one batch through
+// the child codec (decodePointCloud of the I streams, appended behind the predicted points, impl.hpp:1226-1230).
+int ccv2_decode_delta_batch(ccv2_codec *c, int nframes, const void *const *icloud, const size_t *ni, const void *const *i_in, const size_t *i_len,
+                            const void *const *p_in, const size_t *p_len, void *const *pts_out, const size_t *cap_points, size_t *npts, uint64_t *decoded_blocks) {
+  if (!c || nframes < 0 || (nframes && (!icloud || !ni || !i_in || !i_len || !p_in || !p_len || !pts_out || !cap_points || !npts))) return CCV2_ERR_ARG;
+  for (int k = 0; k < nframes; k++)
+    if ((ni[k] && !icloud[k]) || (i_len[k] && !i_in[k]) || (p_len[k] && !p_in[k]) || ni[k] >= (1u << 28) || p_len[k] >= (1ull << 32) || (cap_points[k] && !pts_out[k])) return CCV2_ERR_ARG;
+  CU(cudaSetDevice(c->device));
+  finish_all(c);
+  c->err.clear();
+  uint64_t launches = 0;
+  std::vector<const void *> ii; std::vector<size_t> il, cap, nin; std::vector<void *> oo; std::vector<int> who;
+  for (int k = 0; k < nframes; k++) {
+    const int rc = delta_apply(c, icloud[k], ni[k], p_in[k], p_len[k], pts_out[k], cap_points[k], &npts[k], decoded_blocks ? &decoded_blocks[k] : nullptr, launches);
+    if (rc != CCV2_OK) return rc;
+    if (i_len[k]) { ii.push_back(i_in[k]); il.push_back(i_len[k]); oo.push_back((uint8_t *)pts_out[k] + 32 * npts[k]); cap.push_back(cap_points[k] - npts[k]); who.push_back(k); }
+  }
+  if (!who.empty()) {
     ccv2_codec *ch = nullptr;
-    if ((rc = get_intra_child(c, &ch)) != CCV2_OK) return rc;
-    const void *ip = i_in; size_t il = i_len; void *op = (uint8_t *)pts_out + 32 * npred; size_t cap1 = cap_points - npred;
-    rc = ccv2_decode_batch(ch, 1, &ip, &il, &op, &cap1, &nin);
-    if (rc != CCV2_OK) { c->err = std::string("intra coder of the delta frame: ") + ccv2_last_error(ch); *npts = npred + nin; return rc; }
+    int rc = get_intra_child(c, &ch);
+    if (rc != CCV2_OK) return rc;
+    nin.assign(who.size(), 0);
+    rc = ccv2_decode_batch(ch, (int)who.size(), ii.data(), il.data(), oo.data(), cap.data(), nin.data());
+    for (size_t q = 0; q < who.size(); q++) npts[who[q]] += nin[q];
+    if (rc != CCV2_OK) { c->err = std::string("intra coder of the delta frame: ") + ccv2_last_error(ch); return rc; }
     launches += ccv2_last_launch_count(ch);
   }
-  *npts = npred + nin;
   c->launches = launches;
   return CCV2_OK;
 }

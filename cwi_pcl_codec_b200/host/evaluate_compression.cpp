@@ -7,8 +7,9 @@
 //     :795-897  evaluate_group(): outlier filter, bounding-box normalisation, per frame encode -> decode -> quality ->
 //               restore_scaling -> pointcloud_<n>.ply, CSV line
 //   .../impl/quality_metrics_impl.hpp:242-285  CSV header / line
-// Out of scope (ignored with a note, like the reference's own "not implemented" options): visualization, algorithm V1,
-// do_delta_coding / icp_on_original / do_icp_color_offset (inter-frame predictor), num_threads.
+//     :498-527, 854-889  do_delta_coding: frame i+1 coded against frame i (encoder's simplified cloud, or the input with
+//               icp_on_original), decoded against the decoded frame i, predictive_quality_csv, delta_decoded_pc_<n>.ply
+// Out of scope (ignored with a note, like the reference's own "not implemented" options): visualization, algorithm V1, num_threads.
 #include "pcl/cloud_codec_v2/point_cloud_codec_v2.h"
 #include "pcl/io/cloud_io_lite.h"
 
@@ -131,7 +132,6 @@ int main(int argc, char **argv) {
   const int debug_level = (int)o.i("debug_level");
   if (debug_level > 0) { std::cout << "debug_level=" << debug_level << "\n"; for (auto &kv : o.v) std::cout << "\t " << kv.first << "=" << kv.second << "\n"; }
   if (o.s("algorithm") != "V2") { std::cerr << "only algorithm V2 (cloud_codec_v2) is implemented here\n"; return 1; }
-  if (o.b("do_delta_coding")) std::cerr << "note: do_delta_coding (inter-frame predictor) is outside this build's scope; frames are coded intra\n";
   if (o.b("visualization")) std::cerr << "note: No visualization configured\n";
   if (o.input_directories.size() > 1) { std::cout << "Fusing multiple directories not implemented.\n"; return 1; }
   if (o.input_directories.empty()) { std::cout << "Need to specify a directory containing Point Cloud files (.pcd or .ply).\n"; return 1; }
@@ -210,6 +210,35 @@ int main(int argc, char **argv) {
         if (!o.s("output_directory").empty()) {
           mkdir(o.s("output_directory").c_str(), 0777);
           pcl::io_lite::save_ply_ascii(o.s("output_directory") + "/pointcloud_" + std::to_string(output_index++) + ".ply", *rescaled);
+        }
+        // iterative closest point predictive coding of the NEXT frame against this one (eval.hpp:854-889)
+        if (o.b("do_delta_coding") && bb_expand >= 0 && i + 1 < working.size()) {
+          Cloud::Ptr predicted(new Cloud());
+          std::cout << " delta coding frame nr " << i + 1 << std::endl;
+          std::stringstream p_pdat, p_idat;
+          FrameStats ps{};
+          const bool icp_on_original = o.b("icp_on_original");
+          Cloud::Ptr icl = icp_on_original ? pc : encoder->getOutputCloud();
+          auto d0 = std::chrono::steady_clock::now();
+          encoder->encodePointCloudDeltaFrame(icl, working[i + 1], predicted, p_idat, p_pdat, icp_on_original, false);   // eval.hpp:506
+          auto d1 = std::chrono::steady_clock::now();
+          ps.enc_ms = std::chrono::duration<double, std::milli>(d1 - d0).count();
+          const size_t ib = p_idat.str().size(), pb = p_pdat.str().size();
+          ps.bytes[0] = ib; ps.bytes[1] = pb; ps.bytes[2] = 0; ps.compressed_size = ib + pb;                         // eval.hpp:508-511
+          std::cout << " encoded a predictive frame: coded " << ib << " bytes intra and " << pb << " inter frame encoded " << std::endl;
+          auto d2 = std::chrono::steady_clock::now();
+          encoder->decodePointCloudDeltaFrame(out, predicted, p_idat, p_pdat);                                          // eval.hpp:525: predicted from the DECODED frame i
+          auto d3 = std::chrono::steady_clock::now();
+          ps.dec_ms = std::chrono::duration<double, std::milli>(d3 - d2).count();
+          if (!encoder->lastError().empty()) { std::cerr << "codec error: " << encoder->lastError() << "\n"; return false; }
+          std::cout << " shared macroblocks " << encoder->getMacroBlockPercentage() << ", of which predicted " << encoder->getMacroBlockConvergencePercentage() << std::endl;
+          if (o.b("do_quality_computation")) {
+            ccv2_quality q;
+            if (!decoder->computeQuality(*working[i + 1], *predicted, q)) { std::cerr << "quality computation failed\n"; return false; }
+            if (pcsv.is_open()) print_csv_line(pcsv, setting.str(), q, ps);
+          }
+          Codec::restore_scaling(predicted, bb);
+          if (!o.s("output_directory").empty()) pcl::io_lite::save_ply_ascii(o.s("output_directory") + "/delta_decoded_pc_" + std::to_string(output_index) + ".ply", *predicted);
         }
       }
       return true;

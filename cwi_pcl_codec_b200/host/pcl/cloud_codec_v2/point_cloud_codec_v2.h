@@ -105,6 +105,56 @@ public:
     return out;
   }
 
+  // codec.h:184-186, impl.hpp:787-1112: pcloud_arg coded against icloud_arg -- the P stream (macroblock chunks) and the I
+  // stream (an intra frame of what no macroblock predicted); out_cloud_arg receives the predicted frame when write_out_cloud.
+  // (generatePointCloudDeltaFrame, codec.h:180-182, is the older form of the same call that writes chunks without their
+  // size byte, which no decoder of the reference reads; it is not provided.)
+  void encodePointCloudDeltaFrame(const PointCloudConstPtr &icloud_arg, const PointCloudConstPtr &pcloud_arg, PointCloudPtr &out_cloud_arg,
+                                  std::ostream &i_coded_data, std::ostream &p_coded_data, bool icp_on_original = false, bool write_out_cloud = false) {
+    ensure();
+    const size_t ni = icloud_arg->points.size(), np = pcloud_arg->points.size();
+    buf_.resize(ccv2_max_compressed_size(np));
+    std::vector<unsigned char> pbuf(ccv2_max_p_stream_size(np));
+    std::vector<pcl::PointXYZRGB> oc(write_out_cloud ? ni + np + 1 : 0);
+    size_t il = 0, pl = 0, no = 0;
+    ccv2_delta_info info;
+    out_cloud_arg->height = 1; out_cloud_arg->width = 0;                     // impl.hpp:814-815
+    if (ccv2_encode_delta(h_, icloud_arg->points.data(), ni, pcloud_arg->points.data(), np, icp_on_original ? 1 : 0, buf_.data(), buf_.size(), &il,
+                          pbuf.data(), pbuf.size(), &pl, write_out_cloud ? (void *)oc.data() : nullptr, oc.size(), write_out_cloud ? &no : nullptr, &info) != CCV2_OK) {
+      last_error_ = ccv2_last_error(h_); return;
+    }
+    i_coded_data.write(reinterpret_cast<const char *>(buf_.data()), static_cast<std::streamsize>(il));
+    p_coded_data.write(reinterpret_cast<const char *>(pbuf.data()), static_cast<std::streamsize>(pl));
+    if (write_out_cloud) { oc.resize(no); out_cloud_arg->points.insert(out_cloud_arg->points.end(), oc.begin(), oc.end()); out_cloud_arg->width = (std::uint32_t)out_cloud_arg->points.size(); }
+    shared_macroblock_percentage_ = info.shared_percentage; shared_macroblock_convergence_percentage_ = info.convergence_percentage;
+    delta_info_ = info;
+  }
+  // codec.h:188-190, impl.hpp:1120-1235: predicted macroblocks first (chunk order), then the intra-coded rest, appended to out_cloud_arg
+  void decodePointCloudDeltaFrame(const PointCloudConstPtr &icloud_arg, PointCloudPtr &out_cloud_arg, std::istream &i_coded_data, std::istream &p_coded_data) {
+    ensure();
+    const std::string is((std::istreambuf_iterator<char>(i_coded_data)), std::istreambuf_iterator<char>());
+    const std::string ps((std::istreambuf_iterator<char>(p_coded_data)), std::istreambuf_iterator<char>());
+    uint64_t cnt = 0;
+    if (!is.empty() && ccv2_peek_point_count(is.data(), is.size(), &cnt) != CCV2_OK) cnt = 0;
+    const size_t ni = icloud_arg->points.size();
+    size_t cap = ni + cnt + 1, n = 0;
+    std::vector<pcl::PointXYZRGB> out;
+    for (int attempt = 0; attempt < 2; attempt++) {                          // a chunk list may name a block more than once: grow once
+      out.resize(cap);
+      const int rc = ccv2_decode_delta(h_, icloud_arg->points.data(), ni, is.data(), is.size(), ps.data(), ps.size(), out.data(), cap, &n, nullptr);
+      if (rc == CCV2_OK) break;
+      if (rc == CCV2_ERR_CAPACITY && attempt == 0) { cap = n + cnt + 1; continue; }
+      last_error_ = ccv2_last_error(h_); return;
+    }
+    out.resize(n);
+    out_cloud_arg->points.insert(out_cloud_arg->points.end(), out.begin(), out.end());
+    out_cloud_arg->width = (std::uint32_t)out_cloud_arg->points.size(); out_cloud_arg->height = 1;
+  }
+  // codec.h:200-210
+  float getMacroBlockPercentage() { return shared_macroblock_percentage_; }
+  float getMacroBlockConvergencePercentage() { return shared_macroblock_convergence_percentage_; }
+  const ccv2_delta_info &lastDeltaInfo() const { return delta_info_; }
+
   // codec.h:193-197
   uint64_t *getPerformanceMetrics() { return metrics_; }
 
@@ -208,6 +258,8 @@ private:
   uint64_t metrics_[3];
   std::vector<unsigned char> buf_;
   std::string last_error_;
+  float shared_macroblock_percentage_ = 0.f, shared_macroblock_convergence_percentage_ = 0.f;
+  ccv2_delta_info delta_info_{};
 };
 
 }}  // namespace pcl::io

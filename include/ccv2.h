@@ -226,6 +226,15 @@ int ccv2_encode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *
  * decoded_blocks (may be NULL): macroblocks that found their I block. */
 int ccv2_decode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *i_in, size_t i_len, const void *p_in, size_t p_len,
                       void *pts_out, size_t cap_points, size_t *npts, uint64_t *decoded_blocks);
+/* Several delta frames in one call (frame k: pcloud[k] against icloud[k]).  The prediction stages run one after the other;
+ * the intra-coded parts of ALL frames go through the intra coder as ONE pipelined batch -- its serial range-coder stage is
+ * latency bound, so a batch of 29 frames takes about as long as one.  Same streams as frame-by-frame calls. */
+int ccv2_encode_delta_batch(ccv2_codec *c, int nframes, const void *const *icloud, const size_t *ni, const void *const *pcloud, const size_t *np,
+                            int icp_on_original, void *const *i_out, const size_t *i_cap, size_t *i_len,
+                            void *const *p_out, const size_t *p_cap, size_t *p_len, ccv2_delta_info *info /* nframes entries or NULL */);
+int ccv2_decode_delta_batch(ccv2_codec *c, int nframes, const void *const *icloud, const size_t *ni, const void *const *i_in, const size_t *i_len,
+                            const void *const *p_in, const size_t *p_len, void *const *pts_out, const size_t *cap_points, size_t *npts,
+                            uint64_t *decoded_blocks /* nframes entries or NULL */);
 /* simplifyPCloud alone (impl.hpp:318-400): one point per occupied voxel of the unit-box octree, DFS order. */
 int ccv2_simplify(ccv2_codec *c, const void *pts, size_t n, void *pts_out, size_t cap_points, size_t *npts);
 /* Upper bound of a P stream for a P cloud of np points. */

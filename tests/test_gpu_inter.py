@@ -187,3 +187,37 @@ def test_delta_frame_at_full_size_properties(K):
     print("1M-point delta frame: %d macroblocks, %d shared, %d predicted, %d of %d points intra; %d + %d bytes; predict %.1f ms, intra coder %.1f ms" % (
         info.macro_blocks, info.shared_blocks, info.converged_blocks, info.n_intra_points, info.n_p_points, len(i_s), len(p_s), info2.predict_ms, info2.intra_ms))
     c.close()
+
+
+def test_delta_batch_calls_equal_frame_by_frame_calls(K, oracle, gof):
+    """ccv2_encode_delta_batch / ccv2_decode_delta_batch: the intra parts of all frames go through the child codec as one
+    pipelined call; streams and clouds are those of frame-by-frame calls (every frame's I stream carries frame id 1)."""
+    import torch
+    kp = K.default_params(octree_bits=9)
+    op = oparams(oracle, kp)
+    dev = torch.device("cuda", 0)
+    c = K.Codec(kp)
+    empty = np.zeros((0, 32), np.uint8)
+    ics = [oracle.simplify(gof[0], op), oracle.simplify(gof[1], op), oracle.simplify(gof[0], op), empty]
+    pcs = [gof[1], gof[2], gof[0], gof[1][:5000]]                   # frame 2: identical clouds (almost nothing intra); frame 3: nothing to predict from
+    single = [c.encode_delta(i, p) for i, p in zip(ics, pcs)]
+    d_i = [torch.from_numpy(np.ascontiguousarray(i).reshape(-1).copy()).to(dev) for i in ics]
+    d_p = [torch.from_numpy(np.ascontiguousarray(p).reshape(-1).copy()).to(dev) for p in pcs]
+    d_is = [torch.empty(6 * p.shape[0] + 65536, dtype=torch.uint8, device=dev) for p in pcs]
+    d_ps = [torch.empty(30 * p.shape[0] + 64, dtype=torch.uint8, device=dev) for p in pcs]
+    ils, pls, infos = c.encode_delta_batch_raw([t.data_ptr() if t.numel() else None for t in d_i], [i.shape[0] for i in ics], [t.data_ptr() for t in d_p], [p.shape[0] for p in pcs],
+                                               [t.data_ptr() for t in d_is], [t.numel() for t in d_is], [t.data_ptr() for t in d_ps], [t.numel() for t in d_ps])
+    for k in range(4):
+        assert bytes(d_is[k][:ils[k]].cpu().numpy()) == single[k][0], k
+        assert bytes(d_ps[k][:pls[k]].cpu().numpy()) == single[k][1], k
+        assert infos[k].converged_blocks == single[k][2].converged_blocks
+        ri, rp, _ = oracle.encode_delta(ics[k], pcs[k], op)
+        assert single[k][0] == ri and single[k][1] == rp
+    d_out = [torch.zeros(32 * (i.shape[0] + p.shape[0] + 1), dtype=torch.uint8, device=dev) for i, p in zip(ics, pcs)]
+    ns, nbs = c.decode_delta_batch_raw([t.data_ptr() if t.numel() else None for t in d_i], [i.shape[0] for i in ics], [t.data_ptr() for t in d_is], ils, [t.data_ptr() if pl else None for t, pl in zip(d_ps, pls)], pls,
+                                       [t.data_ptr() for t in d_out], [t.numel() // 32 for t in d_out])
+    for k in range(4):
+        rdec, rnb = oracle.decode_delta(ics[k], single[k][0], single[k][1], op)
+        assert ns[k] == rdec.shape[0] and nbs[k] == rnb
+        assert np.array_equal(d_out[k][:32 * ns[k]].cpu().numpy().reshape(-1, 32), rdec)
+    c.close()

@@ -186,3 +186,45 @@ def test_baseline_config_0_end_to_end(exe, oracle, tmp_path):
     assert abs(float(f[10]) - q.psnr_db) < 1e-3
     for k in range(3):
         assert abs(float(f[11 + k]) - q.psnr_yuv[k]) < 1e-3
+
+
+@pytest.mark.gpu
+def test_delta_coding_through_the_cli_clone(exe, oracle, tmp_path):
+    """do_delta_coding (eval.hpp:854-889): a group of three frames; frame i+1 is coded against the encoder's simplified
+    cloud of frame i and decoded against the decoded frame i.  Stream sizes, the predictive CSV rows and the written
+    delta_decoded_pc_<n>.ply against the same pipeline run through the CPU oracle."""
+    d = tmp_path / "in"; d.mkdir()
+    gof = synth.gen_gof(30000, seed=3, frames=3)
+    raw = []
+    for k, cl in enumerate(gof):
+        c = cl.copy()
+        for a, nm in enumerate("xyz"):
+            c[nm] = (c[nm] * np.float32(2.0) + np.float32(a - 1.0)).astype(np.float32)
+        raw.append(c)
+        write_ply(d / ("frame_%04d.ply" % k), c, True)
+    out = tmp_path / "out"
+    r = subprocess.run([exe, "-b", "9", "-t", "1", "-j", "85", "-q", "1", "-d", "1", "-g", "3", "-o", str(out), "--intra_frame_quality_csv", str(tmp_path / "i.csv"),
+                        "--predictive_quality_csv", str(tmp_path / "p.csv"), str(d)], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr + r.stdout
+    norm, mn_bb, mx_bb = normalize_group([np.stack([c["x"], c["y"], c["z"]], 1) for c in raw], 0.2)
+    ncl = []
+    for c, nx in zip(raw, norm):
+        q = c.copy(); q["x"], q["y"], q["z"] = nx[:, 0], nx[:, 1], nx[:, 2]; ncl.append(q)
+    op = oracle.default_params(octree_bits=9, jpeg_quality=85)
+    prows = (tmp_path / "p.csv").read_text().strip().splitlines()
+    assert len(prows) == 3                                                                             # header + two predicted frames
+    for i in range(2):
+        ref, info, dbg = oracle.encode(ncl[i], op, frame_id=i + 1, debug=True)
+        rd, _ = oracle.decode(ref)
+        ri, rp, rinfo = oracle.encode_delta(dbg["output_cloud"], ncl[i + 1], op)
+        assert " encoded a predictive frame: coded %d bytes intra and %d inter frame encoded " % (len(ri), len(rp)) in r.stdout
+        pdec, _ = oracle.decode_delta(rd, ri, rp, op)
+        q = oracle.quality_metrics(ncl[i + 1], pdec)
+        f = prows[1 + i].split(";")
+        assert int(f[1]) == 30000 and int(f[2]) == pdec.shape[0] and int(f[3]) == len(ri) + len(rp)
+        assert abs(float(f[5]) - len(ri) / pdec.shape[0]) < 1e-4 and abs(float(f[6]) - len(rp) / pdec.shape[0]) < 1e-4 and float(f[7]) == 0
+        assert abs(float(f[8]) - q.symm_rms) < 1e-6 and abs(float(f[10]) - q.psnr_db) < 1e-3 and abs(float(f[11]) - q.psnr_yuv[0]) < 1e-3
+        xyz, rgb = read_ply_ascii(out / ("delta_decoded_pc_%d.ply" % (i + 1)))
+        assert np.array_equal(xyz, restore(pdec[:, :12].copy().view(np.float32).reshape(-1, 3), mn_bb, mx_bb))
+        assert np.array_equal(rgb, pdec[:, [18, 17, 16]])
+    assert len((tmp_path / "i.csv").read_text().strip().splitlines()) == 4
