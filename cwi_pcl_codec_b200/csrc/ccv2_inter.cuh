@@ -215,7 +215,7 @@ static int delta_predict(ccv2_codec *c, const void *icloud, size_t ni, const voi
   const float tfe = 1e-8f;                                                                // transformationepsilon_ is a float (codec.h:142,309)
   X.point_res = prm.point_resolution; X.tf_eps = (double)tfe; X.fit_eps = (double)(3 * tfe);
   mb_match_kernel<<<(unsigned)((ncP + 255) / 256), 256, 0, st>>>(X);
-  mb_icp_kernel<<<c->n_sm * 8, ICP_THREADS, 0, st>>>(X);
+  mb_icp_kernel<<<c->n_sm * 32, ICP_THREADS, 0, st>>>(X);
   mb_scan_kernel<<<1, 1024, 0, st>>>(X, want_out ? 1 : 0);
   mb_write_kernel<<<c->n_sm * 8, 128, 0, st>>>(X);
   launches += 4;
@@ -375,7 +375,7 @@ static int delta_apply(ccv2_codec *c, const void *icloud, size_t ni, const void 
   // larger prediction is redone below into a buffer of the right size
   X.out = dout ? (uint8_t *)pts_out : L.stage; X.out_cap = (uint32_t)std::min<size_t>(dout ? cap_points : std::min(cap_points, ncI), 0xFFFFFFFFu);
   X.color_offset = extra != 0;
-  pchunk_walk_kernel<<<1, 32, 0, st>>>(X);
+  pchunk_walk_kernel<<<1, 256, 0, st>>>(X);
   pchunk_prepare_kernel<<<(unsigned)((chunk_cap + 127) / 128), 128, 0, st>>>(X);
   pchunk_scan_kernel<<<1, 1024, 0, st>>>(X);
   pchunk_apply_kernel<<<c->n_sm * 8, 128, 0, st>>>(X);

@@ -9,8 +9,8 @@
 // a leaf = a run of equal codes, its point list = the run's index values (stable sort: input order).  What is new here:
 //   simplify_kernel      one thread per voxel: centre / centroid + integer colour mean           (HBM bound, 32 B out per voxel)
 //   mb_match_kernel      one thread per P macroblock: findLeaf in the I tree (binary search over sorted codes)
-//   mb_icp_kernel        one CTA per shared macroblock: the gates, then point-to-point ICP -- neighbour search by all
-//                        threads over shared-memory tiles of the target block, the closed-form alignment by ONE thread in
+//   mb_icp_kernel        one single-warp CTA per shared macroblock: the gates, then point-to-point ICP -- neighbour search by all
+//                        lanes over shared-memory tiles of the target block, the closed-form alignment by ONE thread in
 //                        double in the oracle's summation order (what makes the P stream bit-exact against it), transform
 //                        quantisation (quaternion or two-row mode)                                 (FP32 issue / latency bound)
 //   mb_scan_kernel       offsets of every macroblock's chunk, unpredicted points and predicted points (one CTA, chained)
@@ -271,8 +271,10 @@ __device__ inline void estimate_rigid_d(const float *s, const float *t, const ui
   T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
 }
 
-#define ICP_THREADS 128
-#define ICP_TILE 1024
+// One WARP per macroblock: a macroblock holds a patch of a surface -- a few dozen voxels (22 on average for the 1M-point frames at
+// 11 bits, at most 16^3) -- so 32 lanes cover the neighbour search and 32 single-warp CTAs per SM keep 4736 registrations in flight.
+#define ICP_THREADS 32
+#define ICP_TILE 512
 // nearest neighbour of every cur[i] among tgt[0..nt): float ((dx*dx + dy*dy) + dz*dz), first minimum.  All threads of the CTA.
 __device__ inline void icp_nn(const float *cur, uint32_t ns, const float *tgt, uint32_t nt, uint32_t *nn, float *d2, float *s_tile, bool tile_resident) {
   for (uint32_t i0 = 0; i0 < ns; i0 += ICP_THREADS) {
@@ -302,7 +304,7 @@ __device__ inline void icp_nn(const float *cur, uint32_t ns, const float *tgt, u
 
 // do_icp_prediction (impl.hpp:443-568) + compressRigidTransform for every shared macroblock; persistent CTAs take
 // macroblocks from a ticket.
-__global__ void __launch_bounds__(ICP_THREADS) mb_icp_kernel(InterCtx X) {
+__global__ void __launch_bounds__(ICP_THREADS) mb_icp_kernel(InterCtx X) {   // 128 registers: 16 warps per SM; capping at 64 (32 warps) spills the Jacobi arrays and is slower (4.2 against 3.5 ms per 1M-point frame)
   __shared__ float s_tile[3 * ICP_TILE];
   __shared__ float s_T[16], s_F[16];
   __shared__ uint32_t s_L; __shared__ int s_go, s_conv;
@@ -500,18 +502,35 @@ struct DeltaDecCtx {
   uint8_t *out; uint32_t out_cap;
   int color_offset;
 };
-// The chunk sizes chain: one thread walks them (impl.hpp:1136-1141).  A zero size or a chunk that runs past the end stops the walk.
-__global__ void pchunk_walk_kernel(DeltaDecCtx X) {
-  if (threadIdx.x || blockIdx.x) return;
+// The chunk sizes chain (impl.hpp:1136-1141): one thread walks them, out of shared-memory windows of the stream that the
+// whole CTA loads (a walk through global memory pays an L2 round trip per chunk: 4.1 ms for the 22 k chunks of a 1M-point
+// frame, measured; through the windows 0.5 ms).  A zero size or a chunk that runs past the end stops the walk.
+#define WALK_WIN 8192
+__global__ void __launch_bounds__(256) pchunk_walk_kernel(DeltaDecCtx X) {
+  __shared__ __align__(16) uint8_t s_win[WALK_WIN];
+  __shared__ uint32_t s_pos, s_n, s_stop;
   const uint32_t extra = X.color_offset ? 3 : 0;
-  uint32_t pos = 0, n = 0;
-  while (pos < X.p_len && n < X.chunk_cap) {
-    const uint32_t chunk = X.p_stream[pos];
-    if (chunk == 0 || chunk < 6 + extra || pos + 1 + chunk > X.p_len) break;
-    X.chunks[n++].pos = pos + 1;
-    pos += 1 + chunk;
+  if (threadIdx.x == 0) { s_pos = 0; s_n = 0; s_stop = 0; }
+  __syncthreads();
+  while (!s_stop) {
+    const uint32_t w0 = s_pos & ~15u, wn = min((uint32_t)WALK_WIN, X.p_len - w0);   // s_pos < p_len holds here
+    for (uint32_t k = threadIdx.x; k < wn; k += blockDim.x) s_win[k] = X.p_stream[w0 + k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t pos = s_pos, n = s_n; bool stop = false;
+      while (pos < w0 + wn) {
+        if (n >= X.chunk_cap) { stop = true; break; }
+        const uint32_t chunk = s_win[pos - w0];
+        if (chunk == 0 || chunk < 6 + extra || pos + 1 + chunk > X.p_len) { stop = true; break; }
+        X.chunks[n++].pos = pos + 1;
+        pos += 1 + chunk;
+      }
+      if (pos >= X.p_len) stop = true;
+      s_pos = pos; s_n = n; s_stop = stop ? 1u : 0u;
+    }
+    __syncthreads();
   }
-  X.totals[0] = n;
+  if (threadIdx.x == 0) X.totals[0] = s_n;
 }
 // one thread per chunk: key -> findLeaf, transform decompression (impl.hpp:1143-1166)
 __global__ void __launch_bounds__(128) pchunk_prepare_kernel(DeltaDecCtx X) {
