@@ -659,11 +659,12 @@ def run_inter_mode(args, torch, dist, K, rank, world, local, dev):
             local_oc[f] = d_oc[f][:32 * n.value]
             launches += 1
         t["intra_encode"] = time.perf_counter() - t0; t0 = time.perf_counter()
-        ns = codec.decode_batch_raw([d_str[f].data_ptr() for f in mine], lens, [d_dec[f].data_ptr() for f in mine], [NP] * len(mine)) if mine else []
-        launches += codec.last_launch_count if mine else 0
-        t["intra_decode"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        # the I frames' decode is submitted and collected at the end of the step: its serial entropy stage (latency bound, a few
+        # dozen warps) runs while the P frames are predicted and coded
+        pend = codec.submit_decode_raw([d_str[f].data_ptr() for f in mine], lens, [d_dec[f].data_ptr() for f in mine], [NP] * len(mine)) if mine else None
+        t["intra_decode_submit"] = time.perf_counter() - t0; t0 = time.perf_counter()
         pred = G.exchange_predictors(local_oc, NF, dist if world > 1 else None, device=dev)
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()               # the received clouds are complete (NOT a device-wide wait: the I frames' decode stays in flight)
         t["exchange"] = time.perf_counter() - t0; t0 = time.perf_counter()
         tot = {"i": 0, "p": 0, "mb": 0, "shared": 0, "conv": 0, "intra_pts": 0, "ppts": 0, "dec_pts": 0, "predict_ms": 0.0, "intra_ms": 0.0, "xbytes": 0}
         pf = [g for g in mine if g >= 1]
@@ -684,6 +685,10 @@ def run_inter_mode(args, torch, dist, K, rank, world, local, dev):
                 tot["i"] += il; tot["p"] += pl; tot["mb"] += info.macro_blocks; tot["shared"] += info.shared_blocks; tot["conv"] += info.converged_blocks
                 tot["intra_pts"] += info.n_intra_points; tot["ppts"] += info.n_p_points; tot["dec_pts"] += n; tot["predict_ms"] += info.predict_ms; tot["intra_ms"] += info.intra_ms
         t["delta_decode"] = td; t["delta_encode"] = time.perf_counter() - t0 - td
+        t0 = time.perf_counter()
+        ns = pend.wait() if pend is not None else []
+        launches += codec.last_launch_count if mine else 0
+        t["intra_decode_wait"] = time.perf_counter() - t0
         tot["intra_bytes"] = int(sum(lens)); tot["intra_voxels"] = int(sum(ns))
         return launches, t, tot
 

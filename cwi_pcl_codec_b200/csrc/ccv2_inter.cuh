@@ -272,8 +272,7 @@ int ccv2_encode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *
   if (!c || !i_len || !p_len || (ni && !icloud) || (np && !pcloud) || ni >= (1u << 28) || np >= (1u << 28) || (out_cloud && !n_out)) return CCV2_ERR_ARG;
   if (c->prm.macroblock_size < 1) { c->err = "macroblock_size must be >= 1"; return CCV2_ERR_ARG; }
   CU(cudaSetDevice(c->device));
-  finish_all(c);
-  c->err.clear();
+  c->err.clear();                                            // no finish_all: the delta path shares no workspace with submitted intra calls, which may stay in flight
   *i_len = 0; *p_len = 0; if (n_out) *n_out = 0;
   ccv2_delta_info li; memset(&li, 0, sizeof li);
   uint64_t launches = 0;
@@ -295,8 +294,7 @@ int ccv2_encode_delta_batch(ccv2_codec *c, int nframes, const void *const *iclou
   if (!c || nframes < 0 || (nframes && (!icloud || !ni || !pcloud || !np || !i_out || !i_cap || !i_len || !p_out || !p_cap || !p_len))) return CCV2_ERR_ARG;
   if (c->prm.macroblock_size < 1) { c->err = "macroblock_size must be >= 1"; return CCV2_ERR_ARG; }
   CU(cudaSetDevice(c->device));
-  finish_all(c);
-  c->err.clear();
+  c->err.clear();                                            // no finish_all: the delta path shares no workspace with submitted intra calls, which may stay in flight
   size_t tot = 0; std::vector<size_t> off(nframes + 1, 0);
   for (int k = 0; k < nframes; k++) {
     if ((ni[k] && !icloud[k]) || (np[k] && !pcloud[k]) || ni[k] >= (1u << 28) || np[k] >= (1u << 28)) return CCV2_ERR_ARG;
@@ -420,8 +418,7 @@ int ccv2_decode_delta_batch(ccv2_codec *c, int nframes, const void *const *iclou
   for (int k = 0; k < nframes; k++)
     if ((ni[k] && !icloud[k]) || (i_len[k] && !i_in[k]) || (p_len[k] && !p_in[k]) || ni[k] >= (1u << 28) || p_len[k] >= (1ull << 32) || (cap_points[k] && !pts_out[k])) return CCV2_ERR_ARG;
   CU(cudaSetDevice(c->device));
-  finish_all(c);
-  c->err.clear();
+  c->err.clear();                                            // no finish_all: the delta path shares no workspace with submitted intra calls, which may stay in flight
   uint64_t launches = 0;
   std::vector<const void *> ii; std::vector<size_t> il, cap, nin; std::vector<void *> oo; std::vector<int> who;
   for (int k = 0; k < nframes; k++) {

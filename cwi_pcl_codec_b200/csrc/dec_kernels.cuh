@@ -261,6 +261,9 @@ __device__ inline void dfs_walk_fast(DecFrame &f) {
 // while the range decoder is still producing them.  It only has to visit the branches above the bottom level: for
 // a branch at level depth-2 it records (prefix, child mask, stream offset of the first child) and skips the child
 // bytes -- dec_leaves_kernel turns those records into points in parallel afterwards.
+#ifndef WALK_NAP_NS
+#define WALK_NAP_NS 2048
+#endif
 __device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *lut, uint32_t *stack) {
   const uint32_t B = rg->B, d = rg->depth;
   const uint32_t rg_a = smem_addr(rg), lut_a = smem_addr(lut), st_a = smem_addr(stack);
@@ -271,8 +274,9 @@ __device__ inline void dfs_walk_ring(DecFrame &f, WalkRing *rg, const uint32_t *
   auto read_byte = [&](uint32_t &dst) -> bool {             // byte at stream offset pos; false when the producer died
     const uint32_t wi = pos >> 2;
     if (wi != cw) {
-      // the decoder publishes every 64 symbols (~8 us): sleep rather than take issue slots from the decoders on this SM
-      while (wi >= avail) { avail = lds_volatile_u32(prod_a); if (lds_volatile_u32(dead_a)) return false; if (wi >= avail) __nanosleep(256); }
+      // the decoder publishes every 64 symbols (8-15 us) into a ring 2048 symbols deep: sleep through most of that rather than
+      // take issue slots from the decoders on this SM (at 256 ns per nap the wake-ups alone were ~11 M instructions per frame)
+      while (wi >= avail) { avail = lds_volatile_u32(prod_a); if (lds_volatile_u32(dead_a)) return false; if (wi >= avail) __nanosleep(WALK_NAP_NS); }
       win = lds_volatile_u32(ring_a + ((wi & (RING_WORDS - 1)) << 2)); cw = wi;
       if ((wi >> 4) != pub) { pub = wi >> 4; sts_volatile_u32(cons_a, wi); }
     }

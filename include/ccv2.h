@@ -211,6 +211,8 @@ int ccv2_quality_metrics(ccv2_codec *c, const void *cloud_a, size_t na, const vo
  * epsilon 1e-8f, fitness epsilon 3e-8f, accepted when the fitness is below 2 x point_resolution) with the arithmetic
  * oracle/ccv2_oracle_inter.c states; no build of the reference reproduces another build's ICP bits, so parity for this path
  * is: bit-exact against the oracle, format + quality against the reference.
+ * The delta calls are synchronous, but they share no workspace with ccv2_submit_* calls of the same handle, which may stay in
+ * flight across them (bench.py --mode inter decodes a group's I frames while its P frames are being predicted).
  * All cloud and stream pointers may be host or device memory.  out_cloud (may be NULL) receives the predicted frame the
  * reference writes when write_out_cloud is set.  Macroblock size and colour offsets come from ccv2_params. */
 typedef struct ccv2_delta_info {

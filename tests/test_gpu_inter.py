@@ -221,3 +221,27 @@ def test_delta_batch_calls_equal_frame_by_frame_calls(K, oracle, gof):
         assert ns[k] == rdec.shape[0] and nbs[k] == rnb
         assert np.array_equal(d_out[k][:32 * ns[k]].cpu().numpy().reshape(-1, 32), rdec)
     c.close()
+
+
+def test_delta_calls_run_beside_submitted_intra_calls(K, oracle, gof):
+    """The delta path shares no workspace with submitted intra calls of the same handle: a decode in flight and a delta
+    encode / decode issued meanwhile both give their usual results (bench.py --mode inter relies on it)."""
+    import torch
+    kp = K.default_params(octree_bits=9)
+    op = oparams(oracle, kp)
+    dev = torch.device("cuda", 0)
+    c = K.Codec(kp)
+    streams = c.encode_batch([gof[0], gof[1], gof[2]])
+    icloud = c.output_cloud(0)
+    d_s = [torch.from_numpy(np.frombuffer(s, np.uint8).copy()).to(dev) for s in streams]
+    d_o = [torch.zeros(32 * g.shape[0], dtype=torch.uint8, device=dev) for g in gof]
+    pend = c.submit_decode_raw([t.data_ptr() for t in d_s], [t.numel() for t in d_s], [t.data_ptr() for t in d_o], [g.shape[0] for g in gof])
+    i_s, p_s, info = c.encode_delta(icloud, gof[1])
+    dec, nb = c.decode_delta(icloud, i_s, p_s)
+    ns = pend.wait()
+    ri, rp, _ = oracle.encode_delta(icloud, gof[1], op)
+    assert i_s == ri and p_s == rp and np.array_equal(dec, oracle.decode_delta(icloud, ri, rp, op)[0])
+    for k in range(3):
+        rd, _ = oracle.decode(streams[k])
+        assert ns[k] == rd.shape[0] and np.array_equal(d_o[k][:32 * ns[k]].cpu().numpy().reshape(-1, 32), rd)
+    c.close()
