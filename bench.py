@@ -774,7 +774,11 @@ def profile_roofline(K, lib, args, frames, alg_bytes_frame, frames_per_step, ste
     # the HBM-bound parallel kernels against their OWN algorithmic bytes (per frame: N points, V voxels), for context:
     # the dominant kernel above is a serial dependency chain whose HBM fraction is tiny by construction
     N_, V_ = float(len(frames[0])), (alg_bytes_frame - 32.0 * len(frames[0])) / 32.0 * 0.96
-    own = {"keygen_kernel": 32 * N_ + 12 * N_, "sort_pass_kernel": 24 * N_, "leaf_scan_kernel": 8 * N_ + 17 * V_,
+    # sort: packed (code, colour) words, 16 B per point and pass; the library always launches 8 pass kernels of which
+    # ceil((3 depth + 1) / 8) do work (the others return at once), so the per-launch average carries that factor
+    depth_ = getattr(K.profile_step, "depth", 13)
+    passes_ = (3 * depth_ + 1 + 7) // 8 if depth_ <= 13 else (3 * depth_ + 7) // 8
+    own = {"keygen_kernel": 32 * N_ + 8 * N_, "sort_pass_kernel": (16 if depth_ <= 13 else 24) * N_ * passes_ / 8.0, "leaf_scan_kernel": 8 * N_ + 17 * V_,
            "dec_leaves_kernel": 32 * V_ + 13 * V_ / 2.9 + 1.6 * V_, "hist_kernel": 1.6 * V_ + 0.25 * V_}
     hbm_kernels = {}
     for n_, ms_, k_, fpl_ in prof:

@@ -613,6 +613,7 @@ def profile_step(clouds, octree_bits=11, device=0):
     c = Codec(default_params(octree_bits=octree_bits), device)
     try:
         c.encode_batch(clouds)                      # warm-up (allocations)
+        profile_step.depth = int(c.debug_fetch(0, 5).depth)   # realised octree depth of the first frame (sort passes = ceil((3 depth + 1) / 8))
         c.set_profiling(True)
         streams = c.encode_batch(clouds)
         prof = c.profile()
