@@ -398,6 +398,8 @@ def main():
             return codec.submit_roundtrip_raw(hi, [NP] * FE, hs[k], [cap] * FE, ho[k], [NP] * FE)
         run_steps(2, submit_host)
         barrier()
+        if os.environ.get("CCV2_TRACE"):                         # developer aid: the library's timelines then carry times since this point, across calls
+            codec.timer_start()
         t0 = time.perf_counter()
         _, l2, n2 = run_steps(args.steps, submit_host)
         barrier()

@@ -302,6 +302,12 @@ __global__ void __launch_bounds__(256) zero_region_kernel(Frame *frames) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) p[i] = z;
 }
 
+// Device records -> their pinned host copy through zero-copy stores (see submit_call: the copy engine's in-order queue is the wrong
+// road for a small transfer that must not wait for large ones queued earlier).
+__global__ void __launch_bounds__(256) records_home_kernel(uint64_t *dst_host, const uint64_t *src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst_host[i] = src[i];
+}
+
 // Granlund-Montgomery division of a 32-bit value by an invariant d (2 <= d < 2^31): q = n / d exactly.
 struct FastDiv { uint32_t m, sh; };
 __host__ __device__ inline FastDiv fastdiv_make(uint32_t d) {
