@@ -212,7 +212,7 @@ def pcie_ceiling_same_buffers(torch, dist, world, dev, h_in, h_out, nframes, fra
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--mode", default="roundtrip", choices=["roundtrip", "decode", "tiles", "inter"],
