@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(ICP_THREADS) mb_icp_kernel(InterCtx X) {   // 
     if (threadIdx.x == 0) {
       atomicAdd(&X.ticket[4], 1u);                         // shared_macroblock_count
       bool do_icp = np > 6 ? ((np < ni * 2) && ((double)np >= (double)ni * 0.5)) : false;
+      if ((uint64_t)np * (uint64_t)ni > (1ull << 24)) do_icp = false;   // not in the reference: see oracle/ccv2_oracle_inter.c icp_prediction (macroblocks far beyond 16 voxels)
       if (do_icp) {                                        // colour variance gate, offsets (impl.hpp:463-535); index 0,1,2 = r,g,b = record bytes 18,17,16
         double in_av[3] = { 0, 0, 0 }, out_av[3] = { 0, 0, 0 }, in_var = 0, out_var = 0;
         for (uint32_t i = 0; i < ni; i++) { const uint32_t c = *(const uint32_t *)(X.I + 32ull * iv[is0 + i] + 16); in_av[0] += (double)((c >> 16) & 0xFF); in_av[1] += (double)((c >> 8) & 0xFF); in_av[2] += (double)(c & 0xFF); }

@@ -324,6 +324,10 @@ int orc_icp(const float *src, size_t ns, const float *tgt, size_t nt, int max_it
 /* do_icp_prediction (impl.hpp:443-568).  ic / pc: 32-byte records of the two blocks.  Returns 1 when a transform was found. */
 static int icp_prediction(const orc_params *p, const uint8_t *ic, size_t ni, const uint8_t *pc, size_t np, float *rt, int8_t rgb_off[3]) {
   int do_icp = np > 6 ? ((np < ni * 2) && ((double)np >= (double)ni * 0.5)) : 0;
+  /* NOT in the reference: a macroblock pair with more than 2^24 point pairs (only possible with macroblocks far larger than the
+   * reference's 16 voxels -- 16^3 x 16^3 is exactly 2^24) is not registered; its points are coded intra.  The exhaustive
+   * neighbour search of this restatement and of the CUDA kernel (one warp per macroblock) would take seconds per block there. */
+  if ((uint64_t)np * (uint64_t)ni > (1ull << 24)) do_icp = 0;
   if (!do_icp) return 0;
   double in_av[3] = { 0, 0, 0 }, out_av[3] = { 0, 0, 0 }, in_var = 0, out_var = 0;   /* index 0,1,2 = r,g,b (record bytes 18,17,16) */
   for (size_t i = 0; i < ni; i++) for (int a = 0; a < 3; a++) in_av[a] += (double)ic[32 * i + 18 - a];
