@@ -6,6 +6,9 @@
 // coder's call needs, one at the end.
 #pragma once
 
+// like CU(), but nothing stays queued behind the caller's back when a call fails half way: the inter path runs on fin_stream
+#define CUI(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e__); cudaStreamSynchronize(c->fin_stream); cudaGetLastError(); return CCV2_ERR_CUDA; } } while (0)
+
 namespace {
 
 // workspace of one grid (the front-end arrays a leaf scan needs; no JPEG or tree buffers)
@@ -104,7 +107,7 @@ size_t ccv2_max_p_stream_size(size_t np) { return 30 * np + 64; }
 
 int ccv2_simplify(ccv2_codec *c, const void *pts, size_t n, void *pts_out, size_t cap_points, size_t *npts) {
   if (!c || !npts || (n && !pts) || n >= (1u << 28)) return CCV2_ERR_ARG;
-  CU(cudaSetDevice(c->device));
+  CUI(cudaSetDevice(c->device));
   finish_all(c);
   *npts = 0;
   if (n == 0) return CCV2_OK;
@@ -113,7 +116,7 @@ int ccv2_simplify(ccv2_codec *c, const void *pts, size_t n, void *pts_out, size_
   Carver m(nullptr);
   m.take<EncFrame>(1); if (!din) m.take<uint8_t>(32 * n); m.take<uint8_t>(32 * n); const size_t goff = m.end();
   const size_t gbytes = carve_grid(nullptr, n, nullptr, nullptr);
-  CU(c->inter_ws.ensure(goff + gbytes + 256));
+  CUI(c->inter_ws.ensure(goff + gbytes + 256));
   Carver cv(c->inter_ws.p);
   EncFrame *d_rec = cv.take<EncFrame>(1);
   uint8_t *d_in = din ? (uint8_t *)pts : cv.take<uint8_t>(32 * n);
@@ -125,20 +128,20 @@ int ccv2_simplify(ccv2_codec *c, const void *pts, size_t n, void *pts_out, size_
   if (rc) { c->err = "octree depth > 21"; return rc; }
   cudaStream_t st = c->fin_stream;
   uint64_t launches = 0;
-  if (!din) CU(cudaMemcpyAsync(d_in, pts, 32 * n, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_rec, &h, sizeof h, cudaMemcpyHostToDevice, st));
+  if (!din) CUI(cudaMemcpyAsync(d_in, pts, 32 * n, cudaMemcpyHostToDevice, st));
+  CUI(cudaMemcpyAsync(d_rec, &h, sizeof h, cudaMemcpyHostToDevice, st));
   const EncParams P = grid_params(c->prm.octree_resolution, cen, !cen && c->allow_packed);
   launch_grid(st, d_rec, P, n, launches);
   simplify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_rec, P, d_s);
-  CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(&h, d_rec, sizeof h, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CUI(cudaGetLastError());
+  CUI(cudaMemcpyAsync(&h, d_rec, sizeof h, cudaMemcpyDeviceToHost, st));
+  CUI(cudaStreamSynchronize(st));
   if ((rc = grid_error(c, h, "simplify")) != CCV2_OK) return rc;
   *npts = h.V;
   c->launches = launches + 1;
   if (h.V == 0) return CCV2_OK;
   if (h.V > cap_points || !pts_out) return CCV2_ERR_CAPACITY;
-  CU(cudaMemcpy(pts_out, d_s, 32ull * h.V, dout ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+  CUI(cudaMemcpy(pts_out, d_s, 32ull * h.V, dout ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
   return CCV2_OK;
 }
 
@@ -172,7 +175,7 @@ static int delta_predict(ccv2_codec *c, const void *icloud, size_t ni, const voi
     return cv.end();
   };
   const size_t total = carve(nullptr);
-  CU(c->inter_ws.ensure(total + 256));
+  CUI(c->inter_ws.ensure(total + 256));
   carve(c->inter_ws.p);
   const uint8_t *I = di ? (const uint8_t *)icloud : L.dI, *Praw = dp ? (const uint8_t *)pcloud : L.dP;
   const uint8_t *Pc = orig ? Praw : L.S;                      // the cloud the P macroblock tree indexes
@@ -191,12 +194,12 @@ static int delta_predict(ccv2_codec *c, const void *icloud, size_t ni, const voi
   if ((rc = define_unit_box(h[1], mres)) != CCV2_OK || (rc = define_unit_box(h[2], mres)) != CCV2_OK) { c->err = "octree depth > 21"; return rc; }
   // ---- enqueue
   cudaStream_t st = c->fin_stream;
-  if (!c->inter_ev0) { CU(cudaEventCreate(&c->inter_ev0)); CU(cudaEventCreate(&c->inter_ev1)); }
-  CU(cudaEventRecord(c->inter_ev0, st));
-  if (!di && ni) CU(cudaMemcpyAsync(L.dI, icloud, 32 * ni, cudaMemcpyHostToDevice, st));
-  if (!dp && np) CU(cudaMemcpyAsync(L.dP, pcloud, 32 * np, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(L.rec, h, sizeof h, cudaMemcpyHostToDevice, st));
-  CU(cudaMemsetAsync(L.ticket, 0, 64, st));
+  if (!c->inter_ev0) { CUI(cudaEventCreate(&c->inter_ev0)); CUI(cudaEventCreate(&c->inter_ev1)); }
+  CUI(cudaEventRecord(c->inter_ev0, st));
+  if (!di && ni) CUI(cudaMemcpyAsync(L.dI, icloud, 32 * ni, cudaMemcpyHostToDevice, st));
+  if (!dp && np) CUI(cudaMemcpyAsync(L.dP, pcloud, 32 * np, cudaMemcpyHostToDevice, st));
+  CUI(cudaMemcpyAsync(L.rec, h, sizeof h, cudaMemcpyHostToDevice, st));
+  CUI(cudaMemsetAsync(L.ticket, 0, 64, st));
   if (!orig) {
     const EncParams P0 = grid_params(res, cen, !cen && c->allow_packed);
     launch_grid(st, L.rec + 0, P0, np, launches);
@@ -219,12 +222,12 @@ static int delta_predict(ccv2_codec *c, const void *icloud, size_t ni, const voi
   mb_scan_kernel<<<1, 1024, 0, st>>>(X, want_out ? 1 : 0);
   mb_write_kernel<<<c->n_sm * 8, 128, 0, st>>>(X);
   launches += 4;
-  CU(cudaGetLastError());
-  CU(cudaEventRecord(c->inter_ev1, st));
+  CUI(cudaGetLastError());
+  CUI(cudaEventRecord(c->inter_ev1, st));
   uint32_t tot[16];
-  CU(cudaMemcpyAsync(tot, L.ticket, 64, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h, L.rec, sizeof h, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CUI(cudaMemcpyAsync(tot, L.ticket, 64, cudaMemcpyDeviceToHost, st));
+  CUI(cudaMemcpyAsync(h, L.rec, sizeof h, cudaMemcpyDeviceToHost, st));
+  CUI(cudaStreamSynchronize(st));
   for (int g = orig ? 1 : 0; g < 3; g++) if ((rc = grid_error(c, h[g], g == 0 ? "P voxel grid" : g == 1 ? "P macroblock tree" : "I macroblock tree")) != CCV2_OK) return rc;
   const size_t plen = tot[1], nx = tot[2], nout = tot[3];
   float pms = 0; cudaEventElapsedTime(&pms, c->inter_ev0, c->inter_ev1);
@@ -238,12 +241,12 @@ static int delta_predict(ccv2_codec *c, const void *icloud, size_t ni, const voi
   *p_len = plen;
   if (plen) {
     if (!p_out || plen > p_cap) { c->err = "P stream buffer too small"; return CCV2_ERR_CAPACITY; }
-    CU(cudaMemcpy(p_out, L.pstr, plen, is_device_ptr(p_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+    CUI(cudaMemcpy(p_out, L.pstr, plen, is_device_ptr(p_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
   }
   if (want_out) {
     *n_out = nout;
     if (nout > out_cap_points) { c->err = "predicted-frame buffer too small"; return CCV2_ERR_CAPACITY; }
-    if (nout) CU(cudaMemcpy(out_cloud, L.outp, 32 * nout, is_device_ptr(out_cloud) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+    if (nout) CUI(cudaMemcpy(out_cloud, L.outp, 32 * nout, is_device_ptr(out_cloud) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
   }
   *n_intra = nx; if (intra_ptr) *intra_ptr = L.intra;
   return CCV2_OK;
@@ -271,7 +274,7 @@ int ccv2_encode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *
                       void *out_cloud, size_t out_cap_points, size_t *n_out, ccv2_delta_info *info) {
   if (!c || !i_len || !p_len || (ni && !icloud) || (np && !pcloud) || ni >= (1u << 28) || np >= (1u << 28) || (out_cloud && !n_out)) return CCV2_ERR_ARG;
   if (c->prm.macroblock_size < 1) { c->err = "macroblock_size must be >= 1"; return CCV2_ERR_ARG; }
-  CU(cudaSetDevice(c->device));
+  CUI(cudaSetDevice(c->device));
   c->err.clear();                                            // no finish_all: the delta path shares no workspace with submitted intra calls, which may stay in flight
   *i_len = 0; *p_len = 0; if (n_out) *n_out = 0;
   ccv2_delta_info li; memset(&li, 0, sizeof li);
@@ -293,7 +296,7 @@ int ccv2_encode_delta_batch(ccv2_codec *c, int nframes, const void *const *iclou
                             void *const *i_out, const size_t *i_cap, size_t *i_len, void *const *p_out, const size_t *p_cap, size_t *p_len, ccv2_delta_info *info) {
   if (!c || nframes < 0 || (nframes && (!icloud || !ni || !pcloud || !np || !i_out || !i_cap || !i_len || !p_out || !p_cap || !p_len))) return CCV2_ERR_ARG;
   if (c->prm.macroblock_size < 1) { c->err = "macroblock_size must be >= 1"; return CCV2_ERR_ARG; }
-  CU(cudaSetDevice(c->device));
+  CUI(cudaSetDevice(c->device));
   c->err.clear();                                            // no finish_all: the delta path shares no workspace with submitted intra calls, which may stay in flight
   size_t tot = 0; std::vector<size_t> off(nframes + 1, 0);
   for (int k = 0; k < nframes; k++) {
@@ -301,7 +304,7 @@ int ccv2_encode_delta_batch(ccv2_codec *c, int nframes, const void *const *iclou
     off[k] = tot; tot += (32 * std::max<size_t>(np[k], 1) + 255) & ~size_t(255);
     i_len[k] = 0; p_len[k] = 0;
   }
-  CU(c->inter_batch.ensure(tot + 256));
+  CUI(c->inter_batch.ensure(tot + 256));
   uint64_t launches = 0;
   std::vector<const void *> ip; std::vector<size_t> nx(nframes, 0), icap, ilen; std::vector<void *> io; std::vector<int> who;
   float pms = 0;
@@ -352,7 +355,7 @@ static int delta_apply(ccv2_codec *c, const void *icloud, size_t ni, const void 
     return cv.end();
   };
   const size_t total = carve(nullptr);
-  CU(c->inter_ws.ensure(total + 256));
+  CUI(c->inter_ws.ensure(total + 256));
   carve(c->inter_ws.p);
   const uint8_t *I = di ? (const uint8_t *)icloud : L.dI;
   EncFrame h; memset(&h, 0, sizeof h);
@@ -361,10 +364,10 @@ static int delta_apply(ccv2_codec *c, const void *icloud, size_t ni, const void 
   int rc;
   if ((rc = define_unit_box(h, mres)) != CCV2_OK) { c->err = "octree depth > 21"; return rc; }
   cudaStream_t st = c->fin_stream;
-  if (!di && ni) CU(cudaMemcpyAsync(L.dI, icloud, 32 * ni, cudaMemcpyHostToDevice, st));
-  if (!dps && p_len) CU(cudaMemcpyAsync(L.dps, p_in, p_len, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(L.rec, &h, sizeof h, cudaMemcpyHostToDevice, st));
-  CU(cudaMemsetAsync(L.totals, 0, 64, st));
+  if (!di && ni) CUI(cudaMemcpyAsync(L.dI, icloud, 32 * ni, cudaMemcpyHostToDevice, st));
+  if (!dps && p_len) CUI(cudaMemcpyAsync(L.dps, p_in, p_len, cudaMemcpyHostToDevice, st));
+  CUI(cudaMemcpyAsync(L.rec, &h, sizeof h, cudaMemcpyHostToDevice, st));
+  CUI(cudaMemsetAsync(L.totals, 0, 64, st));
   launch_grid(st, L.rec, grid_params(mres, false, false), ni, launches);
   DeltaDecCtx X; memset(&X, 0, sizeof X);
   X.gi = L.rec; X.I = I; X.p_stream = dps ? (const uint8_t *)p_in : L.dps; X.p_len = (uint32_t)p_len;
@@ -378,11 +381,11 @@ static int delta_apply(ccv2_codec *c, const void *icloud, size_t ni, const void 
   pchunk_scan_kernel<<<1, 1024, 0, st>>>(X);
   pchunk_apply_kernel<<<c->n_sm * 8, 128, 0, st>>>(X);
   launches += 4;
-  CU(cudaGetLastError());
+  CUI(cudaGetLastError());
   uint32_t tot[16];
-  CU(cudaMemcpyAsync(tot, L.totals, 64, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(&h, L.rec, sizeof h, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CUI(cudaMemcpyAsync(tot, L.totals, 64, cudaMemcpyDeviceToHost, st));
+  CUI(cudaMemcpyAsync(&h, L.rec, sizeof h, cudaMemcpyDeviceToHost, st));
+  CUI(cudaStreamSynchronize(st));
   if ((rc = grid_error(c, h, "I macroblock tree")) != CCV2_OK) return rc;
   const size_t npred = tot[1];
   if (decoded_blocks) *decoded_blocks = tot[2];
@@ -390,14 +393,14 @@ static int delta_apply(ccv2_codec *c, const void *icloud, size_t ni, const void 
   if (npred > cap_points) { c->err = "point buffer too small"; return CCV2_ERR_CAPACITY; }
   if (!dout && npred) {
     if (npred > ncI) {                                       // repeated blocks: stage again with room for all of them
-      DevBuf big; CU(big.ensure(32 * npred));
+      DevBuf big; CUI(big.ensure(32 * npred));
       X.out = (uint8_t *)big.p; X.out_cap = (uint32_t)npred;
       pchunk_apply_kernel<<<c->n_sm * 8, 128, 0, st>>>(X);
       cudaError_t e = cudaMemcpyAsync(pts_out, big.p, 32 * npred, cudaMemcpyDeviceToHost, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
       big.release();
-      CU(e);
-    } else CU(cudaMemcpy(pts_out, L.stage, 32 * npred, cudaMemcpyDeviceToHost));
+      CUI(e);
+    } else CUI(cudaMemcpy(pts_out, L.stage, 32 * npred, cudaMemcpyDeviceToHost));
   }
   return CCV2_OK;
 }
@@ -417,7 +420,7 @@ int ccv2_decode_delta_batch(ccv2_codec *c, int nframes, const void *const *iclou
   if (!c || nframes < 0 || (nframes && (!icloud || !ni || !i_in || !i_len || !p_in || !p_len || !pts_out || !cap_points || !npts))) return CCV2_ERR_ARG;
   for (int k = 0; k < nframes; k++)
     if ((ni[k] && !icloud[k]) || (i_len[k] && !i_in[k]) || (p_len[k] && !p_in[k]) || ni[k] >= (1u << 28) || p_len[k] >= (1ull << 32) || (cap_points[k] && !pts_out[k])) return CCV2_ERR_ARG;
-  CU(cudaSetDevice(c->device));
+  CUI(cudaSetDevice(c->device));
   c->err.clear();                                            // no finish_all: the delta path shares no workspace with submitted intra calls, which may stay in flight
   uint64_t launches = 0;
   std::vector<const void *> ii; std::vector<size_t> il, cap, nin; std::vector<void *> oo; std::vector<int> who;
