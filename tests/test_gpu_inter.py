@@ -245,3 +245,30 @@ def test_delta_calls_run_beside_submitted_intra_calls(K, oracle, gof):
         rd, _ = oracle.decode(streams[k])
         assert ns[k] == rd.shape[0] and np.array_equal(d_o[k][:32 * ns[k]].cpu().numpy().reshape(-1, 32), rd)
     c.close()
+
+
+def test_delta_frame_golden_hashes_on_the_gpu(K, golden_dir):
+    """The same frozen inputs through the CUDA path WITHOUT running the oracle: stream hashes, statistics, decoded frame."""
+    import hashlib
+    import importlib.util
+    import json
+    import os
+    spec = importlib.util.spec_from_file_location("make_delta_golden", os.path.join(golden_dir, "make_delta_golden.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    want = json.load(open(os.path.join(golden_dir, "delta_hashes.json")))
+    frames = m.load_inputs()
+    for name, kw in m.DELTA_CASES.items():
+        kw = dict(kw)
+        orig = bool(kw.pop("_icp_on_original", 0))
+        if "do_centroid" in kw:
+            kw["do_voxel_grid_centroid"] = kw.pop("do_centroid")
+        c = K.Codec(K.default_params(**kw))
+        c.encode_batch([frames[0]])
+        ic = c.output_cloud(0)
+        i_s, p_s, info = c.encode_delta(ic, frames[1], icp_on_original=orig)
+        dec, nb = c.decode_delta(ic, i_s, p_s)
+        got = {"i_sha256": hashlib.sha256(i_s).hexdigest(), "p_sha256": hashlib.sha256(p_s).hexdigest(), "i_len": len(i_s), "p_len": len(p_s),
+               "macro_blocks": int(info.macro_blocks), "shared_blocks": int(info.shared_blocks), "converged_blocks": int(info.converged_blocks),
+               "n_intra_points": int(info.n_intra_points), "decoded_points": int(dec.shape[0]), "decoded_sha256": hashlib.sha256(dec.tobytes()).hexdigest()}
+        assert got == want[name], name
+        c.close()

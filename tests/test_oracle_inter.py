@@ -205,3 +205,18 @@ def test_delta_frame_of_disjoint_clouds_is_all_intra(gof):
     simp = O.simplify(far, p)
     ref, _ = O.decode(O.encode(simp, O.default_params(octree_bits=8, create_scalable=1, jpeg_quality=75))[0])
     assert nb == 0 and np.array_equal(dec, ref)
+
+
+def test_delta_frame_golden_hashes(golden_dir):
+    """Frozen inputs (tests/golden/delta_inputs.npz) and the SHA-256 of the oracle's I and P streams, block statistics and
+    decoded frame (tests/golden/delta_hashes.json, written by make_delta_golden.py)."""
+    import importlib.util
+    import json
+    import os
+    spec = importlib.util.spec_from_file_location("make_delta_golden", os.path.join(golden_dir, "make_delta_golden.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    want = json.load(open(os.path.join(golden_dir, "delta_hashes.json")))
+    frames = m.load_inputs()
+    assert sorted(want) == sorted(m.DELTA_CASES)
+    for name, kw in m.DELTA_CASES.items():
+        assert m.run_case(frames, kw) == want[name], name
