@@ -12,11 +12,12 @@
 //     are written straight into device destinations, or into the set's staging area and from there by ONE copy-engine
 //     transfer per frame into pinned host memory.  Pageable host destinations get a per-call staging area and are
 //     copied when the call is collected.
-//   * ccv2_submit_* enqueue a call and return a ticket; ccv2_wait collects it.  Two calls may be in flight, sharing the
+//   * ccv2_submit_* enqueue a call and return a ticket; ccv2_wait collects it.  Three calls may be in flight, sharing the
 //     rings: the next call's uploads and front-ends run while the previous call's serial stages drain, which is what
 //     hides the pipeline's fill and drain (0.3-0.5 s against 0.6 s of PCIe time per 1024-frame call).
 //   * No host synchronisation inside a group: all sizes (depth, V, B, J, stream length) are device-side values in the
-//     frame records; the records come back once per call.
+//     frame records; the records come back once per call, stored into their pinned host copy by a kernel (records_home_kernel:
+//     a copy-engine transfer would queue behind the cloud transfers of later calls).
 #include "../../include/ccv2.h"
 #include "common.cuh"
 #include "enc_kernels.cuh"
