@@ -790,7 +790,7 @@ def profile_roofline(K, lib, args, frames, alg_bytes_frame, frames_per_step, ste
     step_gbs = alg_bytes_frame * frames_per_step / step_s / 1e9
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "frac_step": step_gbs / peak, "achieved_step": step_gbs,
-            "frac_note": "frac / achieved: the dominant kernel's own launch in the profiling step (frames_per_launch frames, one stream; a latency-bound serial kernel, so this only reflects how few frames one launch holds). frac_step / achieved_step: algorithmic bytes x frames per step / measured ms_per_step -- the whole pipeline against the HBM peak",
+            "frac_note": "frac / achieved: the dominant kernel's own launch in the profiling step (frames_per_launch frames, one stream; a latency-bound serial kernel, so this only reflects how few frames one launch holds; calls of 256+ device-resident frames, like the timed steps, run the same stage as rc_decode_lps_kernel, 8 frames per warp). frac_step / achieved_step: algorithmic bytes x frames per step / measured ms_per_step -- the whole pipeline against the HBM peak",
             "hbm_bound_kernels_vs_own_bytes": hbm_kernels,
             "peak_source": which, "avg_launch_ms": avg_s * 1e3, "frames_per_launch": frames_per_launch,
             "algorithmic_bytes_per_frame": alg_bytes_frame, "share_of_step": tot_ms / total_ms,
