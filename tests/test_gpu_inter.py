@@ -146,6 +146,17 @@ def test_delta_frame_device_pointers_and_facade(K, oracle, gof):
     n, nb = c.decode_delta_raw(d_i.data_ptr(), icloud.shape[0], d_is.data_ptr(), il, d_ps.data_ptr(), pl, d_out.data_ptr(), icloud.shape[0] + gof[1].shape[0])
     rdec, _ = oracle.decode_delta(icloud, ri, rp, op)
     assert n == rdec.shape[0] and np.array_equal(d_out[:32 * n].cpu().numpy().reshape(-1, 32), rdec)
+    # the predicted frame into device memory, and simplifyPCloud device to device
+    _, _, _, roc = oracle.encode_delta(icloud, gof[1], op, want_out_cloud=True)
+    d_oc = torch.zeros(32 * (roc.shape[0] + 5), dtype=torch.uint8, device=dev)
+    il, pl, no, info = c.encode_delta_raw(d_i.data_ptr(), icloud.shape[0], d_p.data_ptr(), gof[1].shape[0], d_is.data_ptr(), d_is.numel(), d_ps.data_ptr(), d_ps.numel(),
+                                          out_ptr=d_oc.data_ptr(), out_cap=roc.shape[0] + 5)
+    assert no == roc.shape[0] and np.array_equal(d_oc[:32 * no].cpu().numpy().reshape(-1, 32), roc)
+    import ctypes as C
+    nv = C.c_size_t()
+    d_sv = torch.zeros(32 * gof[1].shape[0], dtype=torch.uint8, device=dev)
+    c._check(c._L.ccv2_simplify(c._h, d_p.data_ptr(), gof[1].shape[0], d_sv.data_ptr(), gof[1].shape[0], C.byref(nv)))
+    assert np.array_equal(d_sv[:32 * nv.value].cpu().numpy().reshape(-1, 32), oracle.simplify(gof[1], op))
     c.close()
     # the reference-shaped class: evaluate_compression's constructor arguments (eval.hpp:377-395), then its calls
     cdc = K.OctreePointCloudCodecV2(K.MANUAL_CONFIGURATION, False, 2.0 ** -9, 2.0 ** -9, True, 0, True, 8, 1, False, False, False, 85, 1)
@@ -272,3 +283,32 @@ def test_delta_frame_golden_hashes_on_the_gpu(K, golden_dir):
                "n_intra_points": int(info.n_intra_points), "decoded_points": int(dec.shape[0]), "decoded_sha256": hashlib.sha256(dec.tobytes()).hexdigest()}
         assert got == want[name], name
         c.close()
+
+
+def test_delta_decoder_with_a_block_named_several_times(K, oracle, gof):
+    """A P stream may name the same I macroblock more than once (nothing in the format forbids it): the decoder then writes
+    more predicted points than the I cloud has.  Host and device destinations, against the oracle."""
+    import torch
+    kp = K.default_params(octree_bits=8)
+    op = oparams(oracle, kp)
+    ic_full = oracle.simplify(gof[0], op)
+    ri, rp, _ = oracle.encode_delta(ic_full, gof[1], op)
+    chunk = rp[:19]                                               # [18][key][6 words]
+    key = np.frombuffer(chunk[1:7], np.int16).astype(np.int64)
+    mres = 16.0 / 256
+    xyz = np.ascontiguousarray(ic_full[:, :12]).view(np.float32).reshape(-1, 3).astype(np.float64)
+    sel = np.all(np.floor(xyz / mres).astype(np.int64) == key, axis=1)
+    ic = np.ascontiguousarray(ic_full[sel])                       # the I cloud is just that macroblock
+    assert 0 < ic.shape[0] < 600
+    ps = chunk * 5
+    rdec, rnb = oracle.decode_delta(ic, ri, ps, op)
+    assert rnb == 5 and rdec.shape[0] > 5 * ic.shape[0]
+    c = K.Codec(kp)
+    dec, nb = c.decode_delta(ic, ri, ps, cap_points=rdec.shape[0] + 7)          # host destination
+    assert nb == 5 and np.array_equal(dec, rdec)
+    dev = torch.device("cuda", 0)
+    d_i = torch.from_numpy(ic.reshape(-1).copy()).to(dev); d_is = torch.from_numpy(np.frombuffer(ri, np.uint8).copy()).to(dev); d_ps = torch.from_numpy(np.frombuffer(ps, np.uint8).copy()).to(dev)
+    d_o = torch.zeros(32 * (rdec.shape[0] + 7), dtype=torch.uint8, device=dev)
+    n, nb = c.decode_delta_raw(d_i.data_ptr(), ic.shape[0], d_is.data_ptr(), len(ri), d_ps.data_ptr(), len(ps), d_o.data_ptr(), rdec.shape[0] + 7)
+    assert n == rdec.shape[0] and nb == 5 and np.array_equal(d_o[:32 * n].cpu().numpy().reshape(-1, 32), rdec)
+    c.close()
