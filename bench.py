@@ -661,13 +661,15 @@ def run_inter_mode(args, torch, dist, K, rank, world, local, dev):
             local_oc[f] = d_oc[f][:32 * n.value]
             launches += 1
         t["intra_encode"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        # the exchange comes BEFORE the asynchronous decode is submitted: NCCL's kernels would otherwise share a hardware queue with one of
+        # the (by then ~60) streams of the codec and its child and sit behind a 0.18 s serial decode kernel (measured: 180 ms instead of 9)
+        pred = G.exchange_predictors(local_oc, NF, dist if world > 1 else None, device=dev)
+        torch.cuda.current_stream().synchronize()               # the received clouds are complete
+        t["exchange"] = time.perf_counter() - t0; t0 = time.perf_counter()
         # the I frames' decode is submitted and collected at the end of the step: its serial entropy stage (latency bound, a few
         # dozen warps) runs while the P frames are predicted and coded
         pend = codec.submit_decode_raw([d_str[f].data_ptr() for f in mine], lens, [d_dec[f].data_ptr() for f in mine], [NP] * len(mine)) if mine else None
         t["intra_decode_submit"] = time.perf_counter() - t0; t0 = time.perf_counter()
-        pred = G.exchange_predictors(local_oc, NF, dist if world > 1 else None, device=dev)
-        torch.cuda.current_stream().synchronize()               # the received clouds are complete (NOT a device-wide wait: the I frames' decode stays in flight)
-        t["exchange"] = time.perf_counter() - t0; t0 = time.perf_counter()
         tot = {"i": 0, "p": 0, "mb": 0, "shared": 0, "conv": 0, "intra_pts": 0, "ppts": 0, "dec_pts": 0, "predict_ms": 0.0, "intra_ms": 0.0, "xbytes": 0}
         pf = [g for g in mine if g >= 1]
         td = 0.0
