@@ -272,7 +272,7 @@ extern "C" {
 int ccv2_encode_delta(ccv2_codec *c, const void *icloud, size_t ni, const void *pcloud, size_t np, int icp_on_original,
                       void *i_out, size_t i_cap, size_t *i_len, void *p_out, size_t p_cap, size_t *p_len,
                       void *out_cloud, size_t out_cap_points, size_t *n_out, ccv2_delta_info *info) {
-  if (!c || !i_len || !p_len || (ni && !icloud) || (np && !pcloud) || ni >= (1u << 28) || np >= (1u << 28) || (out_cloud && !n_out)) return CCV2_ERR_ARG;
+  if (!c || !i_len || !p_len || (ni && !icloud) || (np && !pcloud) || ni >= (1u << 28) || np >= (1u << 27) || (out_cloud && !n_out)) return CCV2_ERR_ARG;   // np < 2^27: the P stream's byte offsets are 32-bit (30 bytes per macroblock at most)
   if (c->prm.macroblock_size < 1) { c->err = "macroblock_size must be >= 1"; return CCV2_ERR_ARG; }
   CUI(cudaSetDevice(c->device));
   c->err.clear();                                            // no finish_all: the delta path shares no workspace with submitted intra calls, which may stay in flight
@@ -300,7 +300,7 @@ int ccv2_encode_delta_batch(ccv2_codec *c, int nframes, const void *const *iclou
   c->err.clear();                                            // no finish_all: the delta path shares no workspace with submitted intra calls, which may stay in flight
   size_t tot = 0; std::vector<size_t> off(nframes + 1, 0);
   for (int k = 0; k < nframes; k++) {
-    if ((ni[k] && !icloud[k]) || (np[k] && !pcloud[k]) || ni[k] >= (1u << 28) || np[k] >= (1u << 28)) return CCV2_ERR_ARG;
+    if ((ni[k] && !icloud[k]) || (np[k] && !pcloud[k]) || ni[k] >= (1u << 28) || np[k] >= (1u << 27)) return CCV2_ERR_ARG;
     off[k] = tot; tot += (32 * std::max<size_t>(np[k], 1) + 255) & ~size_t(255);
     i_len[k] = 0; p_len[k] = 0;
   }

@@ -213,6 +213,7 @@ int ccv2_quality_metrics(ccv2_codec *c, const void *cloud_a, size_t na, const vo
  * is: bit-exact against the oracle, format + quality against the reference.
  * The delta calls are synchronous, but they share no workspace with ccv2_submit_* calls of the same handle, which may stay in
  * flight across them (bench.py --mode inter decodes a group's I frames while its P frames are being predicted).
+ * Limits: pcloud below 2^27 points, icloud below 2^28.
  * All cloud and stream pointers may be host or device memory.  out_cloud (may be NULL) receives the predicted frame the
  * reference writes when write_out_cloud is set.  Macroblock size and colour offsets come from ccv2_params. */
 typedef struct ccv2_delta_info {
