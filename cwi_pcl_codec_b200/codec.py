@@ -526,6 +526,19 @@ class Codec:
         return buf
 
 
+def strip_chunk_sizes(p_stream):
+    """The P stream generatePointCloudDeltaFrame writes (impl.hpp:650-660): the same chunks as encodePointCloudDeltaFrame's
+    (impl.hpp:877-883) WITHOUT their leading size byte.  Host-side re-framing of a finished stream."""
+    out, pos, n = bytearray(), 0, len(p_stream)
+    while pos < n:
+        size = p_stream[pos]
+        if size == 0 or pos + 1 + size > n:
+            raise ValueError("malformed P stream")
+        out += p_stream[pos + 1:pos + 1 + size]
+        pos += 1 + size
+    return bytes(out)
+
+
 class OctreePointCloudCodecV2:
     """Python mirror of pcl::io::OctreePointCloudCodecV2<PointXYZRGB> (codec.h:70-368) over the C ABI.
 
@@ -577,6 +590,13 @@ class OctreePointCloudCodecV2:
         info = r[2]
         self._mb = (info.shared_percentage, info.convergence_percentage)
         return r[0], r[1], (r[3] if write_out_cloud else np.zeros((0, 32), np.uint8))
+
+    def generatePointCloudDeltaFrame(self, icloud, pcloud, icp_on_original=False, write_out_cloud=True):
+        """codec.h:180-182, impl.hpp:577-786: the older form of the delta encoder -- the same prediction, chunks written without
+        their size byte (no decoder of the reference reads that layout; kept for callers that store it).  Returns
+        (i_coded_data, p_coded_data, out_cloud)."""
+        i_s, p_s, oc = self.encodePointCloudDeltaFrame(icloud, pcloud, icp_on_original, write_out_cloud)
+        return i_s, strip_chunk_sizes(p_s), oc
 
     def decodePointCloudDeltaFrame(self, icloud, i_coded_data, p_coded_data):
         """codec.h:186-190: returns the decoded frame."""

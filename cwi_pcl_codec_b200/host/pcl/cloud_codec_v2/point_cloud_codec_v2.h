@@ -13,6 +13,7 @@
 #include <iostream>
 #include <iterator>
 #include <unordered_map>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -107,8 +108,6 @@ public:
 
   // codec.h:184-186, impl.hpp:787-1112: pcloud_arg coded against icloud_arg -- the P stream (macroblock chunks) and the I
   // stream (an intra frame of what no macroblock predicted); out_cloud_arg receives the predicted frame when write_out_cloud.
-  // (generatePointCloudDeltaFrame, codec.h:180-182, is the older form of the same call that writes chunks without their
-  // size byte, which no decoder of the reference reads; it is not provided.)
   void encodePointCloudDeltaFrame(const PointCloudConstPtr &icloud_arg, const PointCloudConstPtr &pcloud_arg, PointCloudPtr &out_cloud_arg,
                                   std::ostream &i_coded_data, std::ostream &p_coded_data, bool icp_on_original = false, bool write_out_cloud = false) {
     ensure();
@@ -128,6 +127,20 @@ public:
     if (write_out_cloud) { oc.resize(no); out_cloud_arg->points.insert(out_cloud_arg->points.end(), oc.begin(), oc.end()); out_cloud_arg->width = (std::uint32_t)out_cloud_arg->points.size(); }
     shared_macroblock_percentage_ = info.shared_percentage; shared_macroblock_convergence_percentage_ = info.convergence_percentage;
     delta_info_ = info;
+  }
+  // codec.h:180-182, impl.hpp:577-786: the older form of the delta encoder.  Same prediction; its P stream is the chunk list
+  // WITHOUT the size bytes (impl.hpp:650-660), which no decoder of the reference reads -- produced by re-framing the stream.
+  void generatePointCloudDeltaFrame(const PointCloudConstPtr &icloud_arg, const PointCloudConstPtr &pcloud_arg, PointCloudPtr &out_cloud_arg,
+                                    std::ostream &i_coded_data, std::ostream &p_coded_data, bool icp_on_original = false, bool write_out_cloud = true) {
+    std::stringstream p_sized;
+    encodePointCloudDeltaFrame(icloud_arg, pcloud_arg, out_cloud_arg, i_coded_data, p_sized, icp_on_original, write_out_cloud);
+    const std::string s = p_sized.str();
+    for (size_t pos = 0; pos < s.size();) {
+      const size_t size = (unsigned char)s[pos];
+      if (size == 0 || pos + 1 + size > s.size()) break;
+      p_coded_data.write(s.data() + pos + 1, (std::streamsize)size);
+      pos += 1 + size;
+    }
   }
   // codec.h:188-190, impl.hpp:1120-1235: predicted macroblocks first (chunk order), then the intra-coded rest, appended to out_cloud_arg
   void decodePointCloudDeltaFrame(const PointCloudConstPtr &icloud_arg, PointCloudPtr &out_cloud_arg, std::istream &i_coded_data, std::istream &p_coded_data) {

@@ -220,3 +220,24 @@ def test_delta_frame_golden_hashes(golden_dir):
     assert sorted(want) == sorted(m.DELTA_CASES)
     for name, kw in m.DELTA_CASES.items():
         assert m.run_case(frames, kw) == want[name], name
+
+
+def test_generate_delta_frame_layout_is_the_chunk_list_without_size_bytes(gof):
+    """generatePointCloudDeltaFrame (impl.hpp:650-660) writes key, transform words and offsets of every predicted macroblock
+    with no size byte in front; the facades produce it by re-framing encodePointCloudDeltaFrame's stream."""
+    from cwi_pcl_codec_b200 import codec as K
+    p = O.default_params(octree_bits=9, do_icp_color_offset=1)
+    _, _, dbg = O.encode(gof[0], p, debug=True)
+    _, p_s, info = O.encode_delta(dbg["output_cloud"], gof[1], p)
+    g = K.strip_chunk_sizes(p_s)
+    chunks = parse_p_stream(p_s, True)
+    assert len(g) == len(p_s) - len(chunks)
+    pos = 0
+    for key, words, off in chunks:
+        n = 6 + 2 * words.size + 3
+        assert struct.unpack("<3h", g[pos:pos + 6]) == key and np.array_equal(np.frombuffer(g[pos + 6:pos + 6 + 2 * words.size], np.int16), words)
+        assert struct.unpack("<3b", g[pos + n - 3:pos + n]) == off
+        pos += n
+    assert pos == len(g)
+    with pytest.raises(ValueError):
+        K.strip_chunk_sizes(p_s[:-1])
