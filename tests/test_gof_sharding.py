@@ -66,3 +66,38 @@ def test_predictors_travel_to_the_neighbour_rank(oracle):
         _, _, dbg = oracle.encode(frames[g - 1], prm, debug=True)
         i_s, p_s, _ = oracle.encode_delta(dbg["output_cloud"], frames[g], prm)
         assert got[g] == (i_s, p_s), g
+
+
+def _worker3(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nf = 8
+    local = {f: torch.full((32 * (f + 1),), f, dtype=torch.uint8) for f in gof.owned_frames(nf, rank, world)}   # "cloud" f: f + 1 records of value f
+    pred = gof.exchange_predictors(local, nf, dist)
+    q.put((rank, {g: (int(t.numel()), int(t[0]) if t.numel() else -1, bool((t == t[0]).all())) for g, t in pred.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_three_ranks_every_frame_gets_its_predecessor():
+    """World size 3: every rank receives from its left neighbour and sends to its right one, several frames per pair, in frame order."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 1000
+    procs = [ctx.Process(target=_worker3, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(3):
+        rank, out = q.get(timeout=120)
+        assert sorted(out) == [g for g in gof.owned_frames(8, rank, 3) if g >= 1]
+        got.update(out)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for g in range(1, 8):
+        assert got[g] == (32 * g, g - 1, True), g
