@@ -241,3 +241,26 @@ def test_generate_delta_frame_layout_is_the_chunk_list_without_size_bytes(gof):
     assert pos == len(g)
     with pytest.raises(ValueError):
         K.strip_chunk_sizes(p_s[:-1])
+
+
+def test_quaternion_coder_branches_and_the_signed_comparison_quirk():
+    """QuaternionCoding (quaternion_coding_impl.hpp:55-222) picks the component it drops by SIGNED comparisons
+    (`w > x && w > y && w > z`, ...): all four cases are reachable, and a rotation whose largest component is negative (about
+    -z by 2 rad: w = 0.54, z = -0.84) lands in the w case, clamps z and fails the 1e-3 check of compressRigidTransform
+    (rigid_transform_coding_impl.hpp:99-108), which then stores two matrix rows and a sign word instead."""
+    def which(words):
+        return ((int(words[1]) & 1) << 1) | (int(words[2]) & 1)
+    seen = set()
+    for axis, ang, want in [([1, 0, 0], 0.3, 3), ([1, 0, 0], 2.0, 0), ([0, 1, 0], 2.9, 1), ([0, 0, 1], 3.1, 2), ([1, 1, 1], 2.0, 3), ([1, 1, 1], 2.9, 0)]:
+        M = np.eye(4, dtype=np.float32); M[:3, :3] = rot(axis, ang)
+        w = O.compress_rigid_transform(M)
+        assert w.size == 6 and which(w) == want, (axis, ang)
+        seen.add(want)
+        assert np.abs(O.decompress_rigid_transform(w)[:3, :3] - M[:3, :3]).max() < 1e-4
+    assert seen == {0, 1, 2, 3}
+    M = np.eye(4, dtype=np.float32); M[:3, :3] = rot([0, 0, -1], 2.0)
+    w = O.compress_rigid_transform(M)
+    assert w.size == 10                                           # two rows + sign word + translation
+    D = O.decompress_rigid_transform(w)
+    assert np.abs(D[:2, :3] - M[:2, :3]).max() < 1e-4 and np.abs(D[2, :3] - M[2, :3]).max() < 5e-3   # third row rebuilt from column norms
+    assert int(w[6]) == sum(1 << l for l in range(3) if M[2, l] < 0)
