@@ -312,3 +312,26 @@ def test_delta_decoder_with_a_block_named_several_times(K, oracle, gof):
     n, nb = c.decode_delta_raw(d_i.data_ptr(), ic.shape[0], d_is.data_ptr(), len(ri), d_ps.data_ptr(), len(ps), d_o.data_ptr(), rdec.shape[0] + 7)
     assert n == rdec.shape[0] and nb == 5 and np.array_equal(d_o[:32 * n].cpu().numpy().reshape(-1, 32), rdec)
     c.close()
+
+
+def test_delta_decoder_two_row_transform_mode(K, oracle, gof):
+    """A chunk whose transform is stored as two matrix rows + sign word (10 words: what compressRigidTransform writes when the
+    quantised quaternion misses the matrix, rigid_transform_coding_impl.hpp:110-122): decoder against the oracle."""
+    kp = K.default_params(octree_bits=8)
+    op = oparams(oracle, kp)
+    ic = oracle.simplify(gof[0], op)
+    ri, rp, _ = oracle.encode_delta(ic, gof[1], op)
+    M = np.eye(4, dtype=np.float32)
+    c_, s_ = np.cos(2.0), np.sin(-2.0)
+    M[:2, :2] = [[c_, -s_], [s_, c_]]                             # rotation about -z by 2 rad: the coder's signed comparison drops into two-row mode
+    M[:3, 3] = [0.01, -0.02, 0.005]
+    w = oracle.compress_rigid_transform(M)
+    assert w.size == 10
+    chunks = [bytes([6 + 20]) + rp[1:7] + w.tobytes(), rp[:19], bytes([6 + 20]) + rp[20:26] + w.tobytes()]
+    ps = b"".join(chunks)
+    rdec, rnb = oracle.decode_delta(ic, ri, ps, op)
+    assert rnb == 3
+    c = K.Codec(kp)
+    dec, nb = c.decode_delta(ic, ri, ps)
+    assert nb == 3 and dec.shape == rdec.shape and np.array_equal(dec, rdec)
+    c.close()
