@@ -10,8 +10,8 @@
  * Points are PCL's 32-byte PointXYZRGB records: x,y,z float32 at 0/4/8, data[3] at 12, b,g,r,a uint8 at
  * 16..19, padding to 32 (the struct the reference instantiates, cloud_codec_v2/src/point_cloud_codec_v2.cpp:45).
  * Every data pointer may be host (pageable or pinned) or device memory of the codec's device; the library
- * detects which.  Cloud buffers (input and output) must be 16-byte aligned -- PCL's own PointXYZRGB is EIGEN_ALIGN16, so
- * cloud->points.data() always is; stream buffers need no alignment.  All functions return 0 on success or a negative ccv2_status.  No exceptions cross the ABI.
+ * detects which.  DEVICE cloud buffers (input and output) must be 16-byte aligned (kernels move records as 16-byte
+ * words); host buffers are staged by the copy engines and need no alignment, nor do streams.  All functions return 0 on success or a negative ccv2_status.  No exceptions cross the ABI.
  * A codec handle owns its CUDA streams and workspaces and is not thread-safe (like the reference object).
  * There is no CPU fallback: without a CUDA device ccv2_create fails with CCV2_ERR_CUDA.
  *
